@@ -1,0 +1,545 @@
+// Context, device upload of the panel, and the batch pipeline behind idp_match_batch / idp_match_batch_device.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "idp_kernels.cuh"
+
+namespace idp {
+
+int base_to_nibble(unsigned char c);
+
+#define CUDA_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t err__ = (expr);                                                                         \
+        if (err__ != cudaSuccess) {                                                                         \
+            set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__);        \
+            return IDP_ERR_CUDA;                                                                            \
+        }                                                                                                   \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return IDP_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); return IDP_ERR_NOMEM; }
+        cap = want;
+        return IDP_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+template <class T>
+static int upload(const std::vector<T> &v, DevBuf &b, size_t min_elems = 1) {
+    size_t n = std::max(v.size(), min_elems);
+    int rc = b.ensure(n * sizeof(T));
+    if (rc) return rc;
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return IDP_OK;
+}
+
+enum { EV_START = 0, EV_SCAN, EV_GAPPED, EV_THREE, EV_END, EV_SW5_A, EV_SW5_B, EV_SW3_A, EV_SW3_B, EV_COUNT };
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    // staging for the host-pointer path
+    DevBuf seq4, seq_off, len, ref_idx, ustart, uend, flags, five, three;
+    // scratch of the chain
+    DevBuf fall, all_list, seg_off, seg_cnt, pair_work, pair_primer, pair_score, fin;
+    Counters *d_ctr = nullptr, *h_ctr = nullptr;
+    size_t pair_cap = 0;
+    bool busy = false;
+    // chunk bookkeeping for the host-pointer path
+    int64_t chunk_begin = 0, chunk_n = 0;
+    long launches = 0;
+};
+
+constexpr int kSlots = 3;
+
+}  // namespace idp
+
+using namespace idp;
+
+struct idp_ctx {
+    const idp_panel *panel = nullptr;
+    int device = 0, sm_count = 148;
+    DevPanel dp{};
+    DevBuf b_pmask, b_pinfo, b_positive, b_loc_key[2], b_loc_primer[2], b_mate_off, b_mate_idx, b_smat;
+    DevBuf b_keys[2], b_offcnt[2], b_postings[2];
+    Slot slots[kSlots];
+    cudaStream_t user_stream = nullptr;
+    idp_timings last{};
+    int rw = 4, nq = 32;
+};
+
+namespace idp {
+
+static int upload_panel(idp_ctx *c) {
+    const idp_panel &p = *c->panel;
+    DevPanel &d = c->dp;
+    int rc;
+    d.n_primers = p.n; d.ww = p.ww; d.window_bases = p.window_bases; d.max_seq_len = p.max_seq_len;
+    if ((rc = upload(p.pmask, c->b_pmask))) return rc;
+    d.pmask = c->b_pmask.as<uint32_t>();
+    std::vector<int4> info(p.n);
+    for (int i = 0; i < p.n; ++i) info[i] = make_int4(p.plen[i], p.cap_full[i], p.acc_full[i], p.seq_len[i]);
+    if ((rc = upload(info, c->b_pinfo))) return rc;
+    d.pinfo = c->b_pinfo.as<int4>();
+    if ((rc = upload(p.positive, c->b_positive))) return rc;
+    d.positive = c->b_positive.as<uint8_t>();
+    for (int s = 0; s < 2; ++s) {
+        if ((rc = upload(p.loc_sortkey[s], c->b_loc_key[s]))) return rc;
+        if ((rc = upload(p.loc_primer[s], c->b_loc_primer[s]))) return rc;
+        d.loc_sortkey[s] = c->b_loc_key[s].as<int64_t>();
+        d.loc_primer[s] = c->b_loc_primer[s].as<int32_t>();
+        d.n_loc[s] = (int32_t)p.loc_primer[s].size();
+    }
+    for (int w = 0; w < 2; ++w) {
+        const KmerIndexHost &h = p.kidx[w];
+        DevKmerIndex &k = d.kidx[w];
+        k.k = h.k > 0 ? h.k : -1;
+        k.window = p.max_primer_length;
+        k.slot_mask = 0; k.shift = 63; k.keys = nullptr; k.off_cnt = nullptr; k.postings = nullptr;
+        if (h.k > 0) {
+            std::vector<OffCnt> oc(h.keys.size());
+            for (size_t i = 0; i < oc.size(); ++i) oc[i] = OffCnt{h.off[i], h.cnt[i]};
+            if ((rc = upload(h.keys, c->b_keys[w]))) return rc;
+            if ((rc = upload(oc, c->b_offcnt[w]))) return rc;
+            if ((rc = upload(h.postings, c->b_postings[w]))) return rc;
+            int bits = 0;
+            while ((size_t(1) << bits) < h.keys.size()) ++bits;
+            k.slot_mask = (uint32_t)h.keys.size() - 1; k.shift = 64 - bits;
+            k.keys = c->b_keys[w].as<uint64_t>(); k.off_cnt = c->b_offcnt[w].as<OffCnt>(); k.postings = c->b_postings[w].as<uint32_t>();
+        }
+    }
+    if ((rc = upload(p.mate_off, c->b_mate_off))) return rc;
+    if ((rc = upload(p.mate_idx, c->b_mate_idx))) return rc;
+    d.mate_off = c->b_mate_off.as<int32_t>(); d.mate_idx = c->b_mate_idx.as<int32_t>();
+    d.match_score = p.params.match_score; d.mismatch_score = p.params.mismatch_score;
+    d.gap_open = p.params.gap_open; d.gap_extend = p.params.gap_extend;
+    d.smat = nullptr;
+    if (!p.smat16.empty()) { if ((rc = upload(p.smat16, c->b_smat))) return rc; d.smat = c->b_smat.as<int32_t>(); }
+    d.slop = p.params.slop; d.three_prime = p.params.three_prime;
+    d.max_mismatch_rate = p.params.max_mismatch_rate; d.min_alignment_score_rate = p.params.min_alignment_score_rate;
+    const int wb = p.window_bases;
+    c->rw = wb <= 32 ? 4 : wb <= 40 ? 5 : wb <= 64 ? 8 : wb <= 128 ? 16 : 32;
+    c->nq = p.max_seq_len <= 32 ? 32 : p.max_seq_len <= 64 ? 64 : 0;
+    return IDP_OK;
+}
+
+template <int RW>
+static void launch_scan(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp_result *five, unsigned *fall, Counters *ctr) {
+    const int grid = (R.n + 255) / 256;
+    scan_kernel<RW><<<grid, 256, 0, st>>>(c->dp, R, five, fall, ctr);
+}
+
+template <bool LOCAL, bool SMAT>
+static void launch_sw_pairs_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, const unsigned *work_read, Counters *ctr,
+                              const unsigned *pw, const unsigned *pp, int *ps) {
+    const int grid = c->sm_count * 8;
+    switch (c->nq) {
+        case 32: sw_pairs_kernel<32, LOCAL, SMAT><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps); break;
+        case 64: sw_pairs_kernel<64, LOCAL, SMAT><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps); break;
+        default: sw_pairs_kernel<0, LOCAL, SMAT><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps); break;
+    }
+}
+static void launch_sw_pairs(const idp_ctx *c, cudaStream_t st, bool local, const DevReads &R, const unsigned *work_read, Counters *ctr,
+                            const unsigned *pw, const unsigned *pp, int *ps) {
+    const bool smat = c->dp.smat != nullptr;
+    if (local) { if (smat) launch_sw_pairs_t<true, true>(c, st, R, work_read, ctr, pw, pp, ps); else launch_sw_pairs_t<true, false>(c, st, R, work_read, ctr, pw, pp, ps); }
+    else { if (smat) launch_sw_pairs_t<false, true>(c, st, R, work_read, ctr, pw, pp, ps); else launch_sw_pairs_t<false, false>(c, st, R, work_read, ctr, pw, pp, ps); }
+}
+
+template <bool LOCAL, bool SMAT>
+static void launch_sw_all_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, const unsigned *work_read, const unsigned *n_work,
+                            Fin *fin, Counters *ctr, int as5) {
+    const int threads = c->dp.n_primers <= 32 ? 32 : c->dp.n_primers <= 64 ? 64 : 128;
+    const int grid = c->sm_count * (threads == 128 ? 8 : threads == 64 ? 16 : 32);
+    switch (c->nq) {
+        case 32: sw_all_kernel<32, LOCAL, SMAT><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5); break;
+        case 64: sw_all_kernel<64, LOCAL, SMAT><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5); break;
+        default: sw_all_kernel<0, LOCAL, SMAT><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5); break;
+    }
+}
+static void launch_sw_all(const idp_ctx *c, cudaStream_t st, bool local, const DevReads &R, const unsigned *work_read, const unsigned *n_work,
+                          Fin *fin, Counters *ctr, int as5) {
+    const bool smat = c->dp.smat != nullptr;
+    if (local) { if (smat) launch_sw_all_t<true, true>(c, st, R, work_read, n_work, fin, ctr, as5); else launch_sw_all_t<true, false>(c, st, R, work_read, n_work, fin, ctr, as5); }
+    else { if (smat) launch_sw_all_t<false, true>(c, st, R, work_read, n_work, fin, ctr, as5); else launch_sw_all_t<false, false>(c, st, R, work_read, n_work, fin, ctr, as5); }
+}
+
+static void launch_finalize_pairs(const idp_ctx *c, cudaStream_t st, const DevReads &R, const unsigned *work_read, const unsigned *n_work_ptr,
+                                  unsigned n_work_fixed, const unsigned *seg_off, const int *seg_cnt, const unsigned *pp, const int *ps,
+                                  idp_result *out, Counters *ctr, int three) {
+    const int grid = c->sm_count * 8;
+    if (c->dp.max_seq_len <= 64) finalize_pairs_kernel<64><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, n_work_fixed, seg_off, seg_cnt, pp, ps, out, ctr, three);
+    else finalize_pairs_kernel<kMaxPrimerBases><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, n_work_fixed, seg_off, seg_cnt, pp, ps, out, ctr, three);
+}
+static void launch_finalize_all(const idp_ctx *c, cudaStream_t st, const DevReads &R, const unsigned *work_read, const unsigned *n_work_ptr,
+                                const Fin *fin, idp_result *out, int three) {
+    const int grid = c->sm_count * 8;
+    if (c->dp.max_seq_len <= 64) finalize_all_kernel<64><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, three);
+    else finalize_all_kernel<kMaxPrimerBases><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, three);
+}
+
+// Enqueue the whole matcher chain for reads already on the device.  Nothing here waits on the host.
+static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R, idp_result *five, idp_result *three) {
+    const idp_panel &p = *c->panel;
+    const size_t n = (size_t)R.n;
+    int rc;
+    const bool k_gapped = p.kidx[1].k > 0, do3 = p.params.three_prime >= 0;
+    if ((rc = s.fall.ensure(n * 4))) return rc;
+    if (k_gapped || do3) {
+        if (s.pair_cap < 2 * n + 4096) s.pair_cap = 2 * n + 4096;
+        if ((rc = s.seg_off.ensure(n * 4)) || (rc = s.seg_cnt.ensure(n * 4)) || (rc = s.pair_work.ensure(s.pair_cap * 4)) ||
+            (rc = s.pair_primer.ensure(s.pair_cap * 4)) || (rc = s.pair_score.ensure(s.pair_cap * 4))) return rc;
+    }
+    if (!k_gapped || do3) { if ((rc = s.fin.ensure(n * sizeof(Fin)))) return rc; }
+    if (do3) { if ((rc = s.all_list.ensure(n * 4))) return rc; }
+    Counters *ctr = s.d_ctr;
+    unsigned *fall = s.fall.as<unsigned>();
+    s.launches = 0;
+    CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(Counters), st));
+    CUDA_TRY(cudaEventRecord(s.ev[EV_START], st));
+    if (n > 0) {
+        switch (c->rw) {
+            case 4: launch_scan<4>(c, st, R, five, fall, ctr); break;
+            case 5: launch_scan<5>(c, st, R, five, fall, ctr); break;
+            case 8: launch_scan<8>(c, st, R, five, fall, ctr); break;
+            case 16: launch_scan<16>(c, st, R, five, fall, ctr); break;
+            default: launch_scan<32>(c, st, R, five, fall, ctr); break;
+        }
+        ++s.launches;
+    }
+    CUDA_TRY(cudaEventRecord(s.ev[EV_SCAN], st));
+    // ---- 5' gapped stage over the fall-through list ----
+    if (n > 0) {
+        if (k_gapped) {
+            const int words = (p.n + 31) / 32;
+            const size_t smem = (size_t)8 * words * 4;
+            cand5_kernel<<<c->sm_count * 4, 256, smem, st>>>(c->dp, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(),
+                                                            (unsigned)s.pair_cap, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>());
+            CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st));
+            launch_sw_pairs(c, st, false, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>());
+            CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st));
+            launch_finalize_pairs(c, st, R, fall, &ctr->n_fall, 0u, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(),
+                                  s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), five, ctr, 0);
+            s.launches += 3;
+        } else {
+            CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st));
+            launch_sw_all(c, st, false, R, fall, &ctr->n_fall, s.fin.as<Fin>(), ctr, 1);
+            CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st));
+            launch_finalize_all(c, st, R, fall, &ctr->n_fall, s.fin.as<Fin>(), five, 0);
+            s.launches += 2;
+        }
+    } else { CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st)); CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st)); }
+    CUDA_TRY(cudaEventRecord(s.ev[EV_GAPPED], st));
+    // ---- 3' stage (IP:483-516) ----
+    if (do3 && n > 0 && three) {
+        CUDA_TRY(cudaMemsetAsync(&ctr->n_pairs, 0, sizeof(unsigned), st));
+        cand3_kernel<<<(R.n + 255) / 256, 256, 0, st>>>(c->dp, R, five, ctr, s.all_list.as<unsigned>(), s.pair_work.as<unsigned>(),
+                                                       s.pair_primer.as<unsigned>(), (unsigned)s.pair_cap, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>());
+        CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_A], st));
+        launch_sw_pairs(c, st, true, R, nullptr, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>());
+        launch_sw_all(c, st, true, R, s.all_list.as<unsigned>(), &ctr->n_all, s.fin.as<Fin>(), ctr, 0);
+        CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_B], st));
+        launch_finalize_pairs(c, st, R, nullptr, nullptr, (unsigned)R.n, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(),
+                              s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), three, ctr, 1);
+        launch_finalize_all(c, st, R, s.all_list.as<unsigned>(), &ctr->n_all, s.fin.as<Fin>(), three, 1);
+        s.launches += 5;
+    } else { CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_A], st)); CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_B], st)); }
+    CUDA_TRY(cudaEventRecord(s.ev[EV_THREE], st));
+    if (n > 0) { metrics_kernel<<<std::min<int>((R.n + 255) / 256, c->sm_count * 8), 256, 0, st>>>(R, five, ctr); ++s.launches; }
+    CUDA_TRY(cudaMemcpyAsync(s.h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(s.ev[EV_END], st));
+    CUDA_TRY(cudaGetLastError());
+    return IDP_OK;
+}
+
+static void add_timings(idp_ctx *c, Slot &s, bool first) {
+    idp_timings &t = c->last;
+    float ms = 0;
+    auto el = [&](int a, int b) { ms = 0; cudaEventElapsedTime(&ms, s.ev[a], s.ev[b]); return ms; };
+    if (first) t.ms_total = 0;
+    t.ms_scan += el(EV_START, EV_SCAN);
+    t.ms_gapped += el(EV_SCAN, EV_GAPPED);
+    t.ms_three_prime += el(EV_GAPPED, EV_THREE);
+    t.ms_sw_score += el(EV_SW5_A, EV_SW5_B) + el(EV_SW3_A, EV_SW3_B);
+    t.n_fallthrough += s.h_ctr->n_fall;
+    t.n_alignments_5p += (int64_t)s.h_ctr->n_align5;
+    t.n_alignments_3p += (int64_t)s.h_ctr->n_align3;
+    t.sw_cells += (int64_t)s.h_ctr->sw_cells;
+    t.scan_base_compares += (int64_t)s.h_ctr->base_compares;
+    t.kernel_launches += s.launches;
+}
+
+}  // namespace idp
+
+extern "C" {
+
+int idp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void *idp_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); set_error("cudaHostAlloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void idp_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int idp_ctx_create(const idp_panel *panel, int device, idp_ctx **out) {
+    if (!panel || !out) { set_error("idp_ctx_create: NULL argument"); return IDP_ERR_ARG; }
+    int ndev = idp_device_count();
+    if (ndev <= 0) { set_error("no CUDA device is usable; the IdentifyPrimers GPU path has no CPU fallback"); return IDP_ERR_CUDA; }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (0..%d)", device, ndev - 1); return IDP_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return IDP_ERR_CUDA; }
+    auto *c = new idp_ctx();
+    c->panel = panel; c->device = device; c->sm_count = prop.multiProcessorCount;
+    int rc = upload_panel(c);
+    if (rc) { idp_ctx_destroy(c); return rc; }
+    for (Slot &s : c->slots) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); idp_ctx_destroy(c); return IDP_ERR_CUDA; }
+        for (auto &e : s.ev) if (cudaEventCreate(&e) != cudaSuccess) { set_error("cudaEventCreate failed"); idp_ctx_destroy(c); return IDP_ERR_CUDA; }
+        if (cudaMalloc(&s.d_ctr, sizeof(Counters)) != cudaSuccess || cudaHostAlloc(&s.h_ctr, sizeof(Counters), cudaHostAllocDefault) != cudaSuccess) {
+            set_error("counter allocation failed"); idp_ctx_destroy(c); return IDP_ERR_NOMEM;
+        }
+    }
+    *out = c;
+    return IDP_OK;
+}
+
+void idp_ctx_destroy(idp_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (Slot &s : c->slots) {
+        for (DevBuf *b : {&s.seq4, &s.seq_off, &s.len, &s.ref_idx, &s.ustart, &s.uend, &s.flags, &s.five, &s.three, &s.fall, &s.all_list,
+                          &s.seg_off, &s.seg_cnt, &s.pair_work, &s.pair_primer, &s.pair_score, &s.fin}) b->release();
+        if (s.d_ctr) cudaFree(s.d_ctr);
+        if (s.h_ctr) cudaFreeHost(s.h_ctr);
+        for (auto &e : s.ev) if (e) cudaEventDestroy(e);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    for (DevBuf *b : {&c->b_pmask, &c->b_pinfo, &c->b_positive, &c->b_loc_key[0], &c->b_loc_key[1], &c->b_loc_primer[0], &c->b_loc_primer[1],
+                      &c->b_mate_off, &c->b_mate_idx, &c->b_smat, &c->b_keys[0], &c->b_keys[1], &c->b_offcnt[0], &c->b_offcnt[1],
+                      &c->b_postings[0], &c->b_postings[1]}) b->release();
+    delete c;
+}
+
+int idp_ctx_set_stream(idp_ctx *ctx, void *cuda_stream) {
+    if (!ctx) { set_error("idp_ctx_set_stream: NULL context"); return IDP_ERR_ARG; }
+    ctx->user_stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return IDP_OK;
+}
+
+int idp_ctx_timings(const idp_ctx *ctx, idp_timings *out) {
+    if (!ctx || !out) { set_error("idp_ctx_timings: NULL argument"); return IDP_ERR_ARG; }
+    *out = ctx->last;
+    return IDP_OK;
+}
+
+static int check_reads(const idp_reads *reads, int32_t n_reads, idp_result *five) {
+    if (!reads || n_reads < 0 || !five) { set_error("NULL reads / results or negative count"); return IDP_ERR_ARG; }
+    if (n_reads > 0 && (!reads->seq4 || !reads->flags)) { set_error("reads.seq4 and reads.flags are required"); return IDP_ERR_ARG; }
+    if (reads->fixed_len <= 0 && n_reads > 0 && (!reads->seq_off || !reads->len)) { set_error("reads.seq_off and reads.len are required unless fixed_len > 0"); return IDP_ERR_ARG; }
+    if (reads->fixed_len > kMaxReadLen) { set_error("reads longer than %d bases are not supported", kMaxReadLen); return IDP_ERR_UNSUPPORTED; }
+    return IDP_OK;
+}
+
+int idp_match_batch_device(idp_ctx *c, const idp_reads *reads, int32_t n_reads, idp_result *five, idp_result *three,
+                           int64_t *metrics160, int64_t *n_gapped_alignments) {
+    if (!c) { set_error("NULL context"); return IDP_ERR_ARG; }
+    int rc = check_reads(reads, n_reads, five);
+    if (rc) return rc;
+    if (c->panel->params.three_prime >= 0 && !three) { set_error("three_prime >= 0 needs a `three` result array"); return IDP_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    Slot &s = c->slots[0];
+    cudaStream_t st = c->user_stream ? c->user_stream : s.stream;
+    DevReads R{reads->seq4, reads->seq_off, reads->len, reads->ref_idx, reads->unclipped_start, reads->unclipped_end, reads->flags, reads->fixed_len, n_reads};
+    c->last = idp_timings{};
+    for (int attempt = 0;; ++attempt) {
+        if ((rc = enqueue_chain(c, s, st, R, five, three))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (s.h_ctr->overflow == 0) break;
+        if (attempt >= 6) { set_error("candidate pair buffer overflow persists after %d retries", attempt); return IDP_ERR_NOMEM; }
+        s.pair_cap *= 4;  // rare: a read listed far more -K candidates than budgeted; redo the batch with more room
+    }
+    c->last = idp_timings{};
+    add_timings(c, s, true);
+    float ms = 0; cudaEventElapsedTime(&ms, s.ev[EV_START], s.ev[EV_END]);
+    c->last.ms_total = ms; c->last.n_reads = n_reads;
+    if (metrics160) for (int i = 0; i < 160; ++i) metrics160[i] += (int64_t)s.h_ctr->metrics[i];
+    if (n_gapped_alignments) *n_gapped_alignments += (int64_t)s.h_ctr->n_align5;
+    return IDP_OK;
+}
+
+// host-pointer path: chunks of reads flow through kSlots streams so that H2D, kernels and D2H overlap
+int idp_match_batch(idp_ctx *c, const idp_reads *reads, int32_t n_reads, idp_result *five, idp_result *three,
+                    int64_t *metrics160, int64_t *n_gapped_alignments) {
+    if (!c) { set_error("NULL context"); return IDP_ERR_ARG; }
+    int rc = check_reads(reads, n_reads, five);
+    if (rc) return rc;
+    const bool do3 = c->panel->params.three_prime >= 0;
+    if (do3 && !three) { set_error("three_prime >= 0 needs a `three` result array"); return IDP_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->last = idp_timings{};
+    c->last.n_reads = n_reads;
+    const char *env = getenv("IDP_CHUNK_READS");
+    int64_t chunk = env ? atoll(env) : (1 << 20);
+    if (chunk < 2) chunk = 2;
+    const bool have_loc = reads->ref_idx && reads->unclipped_start && reads->unclipped_end;
+    bool first = true;
+    int64_t total_metrics[160] = {0}, total_align = 0;
+
+    auto harvest = [&](Slot &s) -> int {
+        if (!s.busy) return IDP_OK;
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        s.busy = false;
+        if (s.h_ctr->overflow) { set_error("candidate pair buffer overflow in a chunk (raise IDP_CHUNK_READS granularity)"); return IDP_ERR_NOMEM; }
+        add_timings(c, s, first);
+        first = false;
+        for (int i = 0; i < 160; ++i) total_metrics[i] += (int64_t)s.h_ctr->metrics[i];
+        total_align += (int64_t)s.h_ctr->n_align5;
+        return IDP_OK;
+    };
+
+    int slot_i = 0;
+    cudaEvent_t ev_begin, ev_finish;
+    CUDA_TRY(cudaEventCreate(&ev_begin));
+    CUDA_TRY(cudaEventCreate(&ev_finish));
+    bool began = false;
+    for (int64_t b = 0; b < n_reads;) {
+        int64_t e = std::min<int64_t>(b + chunk, n_reads);
+        if (e < n_reads && (reads->flags[e - 1] & IDP_F_MATE_NEXT)) ++e;  // never split a template
+        const int64_t cn = e - b;
+        Slot &s = c->slots[slot_i];
+        slot_i = (slot_i + 1) % kSlots;
+        if ((rc = harvest(s))) return rc;
+        cudaStream_t st = s.stream;
+        if (!began) { CUDA_TRY(cudaEventRecord(ev_begin, st)); began = true; }
+        // byte range of this chunk's bases
+        uint64_t byte0, byte1;
+        if (reads->fixed_len > 0) { const uint64_t stride = (uint64_t)((reads->fixed_len + 1) >> 1); byte0 = (uint64_t)b * stride; byte1 = (uint64_t)e * stride; }
+        else { byte0 = reads->seq_off[b]; byte1 = 0; for (int64_t r = b; r < e; ++r) byte1 = std::max<uint64_t>(byte1, reads->seq_off[r] + (uint64_t)((reads->len[r] + 1) >> 1)); if (byte1 < byte0) byte1 = byte0; }
+        if ((rc = s.seq4.ensure(byte1 - byte0 + 16)) || (rc = s.flags.ensure(cn * 2)) || (rc = s.five.ensure(cn * sizeof(idp_result)))) return rc;
+        if (do3 && (rc = s.three.ensure(cn * sizeof(idp_result)))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(s.seq4.p, reads->seq4 + byte0, byte1 - byte0, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s.flags.p, reads->flags + b, cn * 2, cudaMemcpyHostToDevice, st));
+        c->last.h2d_bytes += (int64_t)(byte1 - byte0) + cn * 2;
+        DevReads R{};
+        R.n = (int32_t)cn; R.fixed_len = reads->fixed_len; R.flags = s.flags.as<uint16_t>();
+        R.seq4 = s.seq4.as<uint8_t>() - (reads->fixed_len > 0 ? 0 : byte0);
+        if (reads->fixed_len <= 0) {
+            if ((rc = s.seq_off.ensure(cn * 8)) || (rc = s.len.ensure(cn * 4))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(s.seq_off.p, reads->seq_off + b, cn * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(s.len.p, reads->len + b, cn * 4, cudaMemcpyHostToDevice, st));
+            R.seq_off = s.seq_off.as<uint64_t>(); R.len = s.len.as<int32_t>();
+            c->last.h2d_bytes += cn * 12;
+        }
+        if (have_loc) {
+            if ((rc = s.ref_idx.ensure(cn * 4)) || (rc = s.ustart.ensure(cn * 4)) || (rc = s.uend.ensure(cn * 4))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(s.ref_idx.p, reads->ref_idx + b, cn * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(s.ustart.p, reads->unclipped_start + b, cn * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(s.uend.p, reads->unclipped_end + b, cn * 4, cudaMemcpyHostToDevice, st));
+            R.ref_idx = s.ref_idx.as<int32_t>(); R.ustart = s.ustart.as<int32_t>(); R.uend = s.uend.as<int32_t>();
+            c->last.h2d_bytes += cn * 12;
+        }
+        if ((rc = enqueue_chain(c, s, st, R, s.five.as<idp_result>(), do3 ? s.three.as<idp_result>() : nullptr))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(five + b, s.five.p, cn * sizeof(idp_result), cudaMemcpyDeviceToHost, st));
+        c->last.d2h_bytes += cn * (int64_t)sizeof(idp_result);
+        if (do3) { CUDA_TRY(cudaMemcpyAsync(three + b, s.three.p, cn * sizeof(idp_result), cudaMemcpyDeviceToHost, st)); c->last.d2h_bytes += cn * (int64_t)sizeof(idp_result); }
+        s.busy = true;
+        b = e;
+    }
+    for (int k = 0; k < kSlots; ++k) if ((rc = harvest(c->slots[k]))) return rc;
+    if (began) {
+        CUDA_TRY(cudaEventRecord(ev_finish, c->slots[0].stream));
+        CUDA_TRY(cudaEventSynchronize(ev_finish));
+        float ms = 0; cudaEventElapsedTime(&ms, ev_begin, ev_finish);
+        c->last.ms_total = ms;
+    }
+    cudaEventDestroy(ev_begin); cudaEventDestroy(ev_finish);
+    if (metrics160) for (int i = 0; i < 160; ++i) metrics160[i] += total_metrics[i];
+    if (n_gapped_alignments) *n_gapped_alignments += total_align;
+    return IDP_OK;
+}
+
+// ---- batched AsyncAligner.align (AA:37-54) ----
+__global__ void align_kernel(DevPanel P, const uint32_t *__restrict__ qwords, int qw, const int32_t *__restrict__ qlen,
+                             const uint8_t *__restrict__ tseq4, const uint64_t *__restrict__ toff, const int32_t *__restrict__ tlen,
+                             int n, int mode, int32_t *__restrict__ score, int32_t *__restrict__ tstart, int32_t *__restrict__ tend) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Oriented T{tseq4 + toff[i], tlen[i], false};
+    const Traced tr = sw_trace<kMaxPrimerBases>(P, qwords + (size_t)i * qw, qlen[i], T, tlen[i], mode);
+    score[i] = tr.score; tstart[i] = tr.t_start; tend[i] = tr.t_end;
+}
+
+int idp_align_batch(idp_ctx *c, int mode, const char *queries, const int64_t *q_off, const char *targets, const int64_t *t_off,
+                    int32_t n, int32_t *score, int32_t *target_start, int32_t *target_end) {
+    if (!c || !queries || !q_off || !targets || !t_off || n < 0 || !score || !target_start || !target_end) { set_error("idp_align_batch: NULL argument"); return IDP_ERR_ARG; }
+    if (mode != IDP_MODE_LOCAL && mode != IDP_MODE_GLOCAL && mode != IDP_MODE_GLOBAL) { set_error("unknown alignment mode %d", mode); return IDP_ERR_ARG; }
+    if (n == 0) return IDP_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int maxq = 1;
+    for (int i = 0; i < n; ++i) {
+        const int64_t ql = q_off[i + 1] - q_off[i], tl = t_off[i + 1] - t_off[i];
+        if (ql < 1 || ql > kMaxPrimerBases) { set_error("query %d: length %lld outside [1, %d]", i, (long long)ql, kMaxPrimerBases); return IDP_ERR_UNSUPPORTED; }
+        if (tl < 0 || tl > kMaxReadLen) { set_error("target %d: length %lld outside [0, %d]", i, (long long)tl, kMaxReadLen); return IDP_ERR_UNSUPPORTED; }
+        maxq = std::max<int>(maxq, (int)ql);
+    }
+    const int qw = (maxq + 7) / 8;
+    std::vector<uint32_t> qwords((size_t)n * qw, 0);
+    std::vector<int32_t> qlen(n), tlen(n);
+    std::vector<uint64_t> toff(n);
+    std::vector<uint8_t> tseq;
+    auto code = [](char ch, bool &ok) { int v = base_to_nibble((unsigned char)ch); if (v == 15 && ch != 'N') ok = false; if (ch >= 'a' && ch <= 'z') ok = false; return v; };
+    bool ok = true;
+    for (int i = 0; i < n; ++i) {
+        qlen[i] = (int32_t)(q_off[i + 1] - q_off[i]); tlen[i] = (int32_t)(t_off[i + 1] - t_off[i]);
+        for (int b = 0; b < qlen[i]; ++b) qwords[(size_t)i * qw + b / 8] |= (uint32_t)code(queries[q_off[i] + b], ok) << (4 * (b % 8));
+        toff[i] = tseq.size();
+        for (int b = 0; b < tlen[i]; b += 2) {
+            const int hi = code(targets[t_off[i] + b], ok), lo = b + 1 < tlen[i] ? code(targets[t_off[i] + b + 1], ok) : 0;
+            tseq.push_back((uint8_t)((hi << 4) | lo));
+        }
+    }
+    if (!ok) { set_error("idp_align_batch: only upper-case IUPAC bases and '=' are supported"); return IDP_ERR_UNSUPPORTED; }
+    if (tseq.empty()) tseq.push_back(0);
+    DevBuf d_q, d_ql, d_t, d_to, d_tl, d_out;
+    int rc;
+    auto cleanup = [&]() { d_q.release(); d_ql.release(); d_t.release(); d_to.release(); d_tl.release(); d_out.release(); };
+    if ((rc = upload(qwords, d_q)) || (rc = upload(qlen, d_ql)) || (rc = upload(tseq, d_t)) || (rc = upload(toff, d_to)) || (rc = upload(tlen, d_tl)) ||
+        (rc = d_out.ensure((size_t)n * 12))) { cleanup(); return rc; }
+    int32_t *o = d_out.as<int32_t>();
+    cudaStream_t st = c->user_stream ? c->user_stream : c->slots[0].stream;
+    align_kernel<<<(n + 127) / 128, 128, 0, st>>>(c->dp, d_q.as<uint32_t>(), qw, d_ql.as<int32_t>(), d_t.as<uint8_t>(), d_to.as<uint64_t>(), d_tl.as<int32_t>(),
+                                                 n, mode, o, o + n, o + 2 * (size_t)n);
+    cudaError_t e1 = cudaMemcpyAsync(score, o, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaMemcpyAsync(target_start, o + n, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+    cudaError_t e3 = cudaMemcpyAsync(target_end, o + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+    cudaError_t e4 = cudaStreamSynchronize(st);
+    cleanup();
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+        set_error("idp_align_batch: CUDA failure: %s", cudaGetErrorString(e4 != cudaSuccess ? e4 : (e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3))));
+        return IDP_ERR_CUDA;
+    }
+    return IDP_OK;
+}
+
+}  // extern "C"

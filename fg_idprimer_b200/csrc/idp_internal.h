@@ -1,0 +1,85 @@
+// Internal declarations shared by the host side (panel build, context, pipeline) and the CUDA kernels.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/idprimer.h"
+
+namespace idp {
+
+constexpr int kMaxPrimerBases = 256;   // longest primer sequence the kernels cover
+constexpr int kMaxK = 16;              // k-mer key = 4 bits/base in a 64-bit word
+constexpr int kMaxReadLen = 4095;      // target start/end are carried in 12 bits next to the score
+constexpr int32_t kNegInf = INT32_MIN / 2;  // fgbio Aligner.MinStartScore
+
+void set_error(const char *fmt, ...);
+
+struct OffCnt { uint32_t off, cnt; };
+
+// ---- device view of a k-mer index: open-addressing table keyed by the k nibbles of a k-mer ----
+struct DevKmerIndex {
+    int32_t k;                 // <= 0: no filter (all primers are candidates, PM:100)
+    int32_t window;            // maxPrimerLength, the width of the read window searched (PM:75, 110)
+    uint32_t slot_mask;        // slots - 1
+    int32_t shift;             // 64 - log2(slots)
+    const uint64_t *keys;      // 0 = empty slot (a real key never has a zero nibble)
+    const OffCnt *off_cnt;      // postings offset / count per slot
+    const uint32_t *postings;  // primer indices in the iteration order of the reference's Set[Primer]
+};
+
+// ---- device view of the panel ----
+struct DevPanel {
+    int32_t n_primers;
+    int32_t ww;                // 32-bit words per primer in pmask (8 bases per word)
+    int32_t window_bases;      // leading read bases the scan kernel looks at
+    int32_t max_seq_len;
+    const uint32_t *pmask;     // [n][ww] IUPAC masks, base i in nibble i, padded with 0xF
+    // [n] {Primer.length (PR:206), early-exit cap of numMismatches and largest accepted mismatch count when the read
+    //      is at least Primer.length long (PM:130-134), primer.sequence.length}
+    const int4 *pinfo;
+    const uint8_t *positive;   // [n]
+    // location matcher (PM:156-214): per strand, mapped primers sorted by (ref_idx, key); key = start (+) / end (-)
+    const int64_t *loc_sortkey[2];  // (ref_idx << 32) | key
+    const int32_t *loc_primer[2];
+    int32_t n_loc[2];
+    DevKmerIndex kidx[2];      // 0: ungapped matcher (-k), 1: gapped matcher (-K)
+    // pair_id groups for 3' matching (IP:496): opposite-strand primers of the same pair, file order
+    const int32_t *mate_off;   // [n+1]
+    const int32_t *mate_idx;
+    // scoring (IP:364-372)
+    int32_t match_score, mismatch_score, gap_open, gap_extend;
+    const int32_t *smat;       // NULL or [16*16] primer nibble x read nibble, INT32_MIN = missing
+    int32_t slop, three_prime;
+    double max_mismatch_rate, min_alignment_score_rate;
+};
+
+struct KmerIndexHost {
+    int k = -1;
+    std::vector<uint64_t> keys;
+    std::vector<uint32_t> off, cnt;   // per slot
+    std::vector<uint32_t> postings;
+    std::unordered_map<std::string, std::pair<uint32_t, uint32_t>> by_string;  // kmer -> (offset, count)
+};
+
+}  // namespace idp
+
+struct idp_panel {
+    int32_t n = 0;
+    idp_params params{};
+    std::vector<int32_t> score_matrix;        // 128*128 copy or empty
+    std::vector<std::string> pair_id, primer_id, sequence, ref_name;
+    std::vector<int32_t> ref_idx, start, end, seq_len, plen, pair_of, cap_full, acc_full;
+    std::vector<uint8_t> positive;
+    std::vector<uint32_t> hash;
+    int32_t ww = 0, window_bases = 0, max_seq_len = 0, max_primer_length = 0;
+    std::vector<uint32_t> pmask;
+    std::vector<int64_t> loc_sortkey[2];
+    std::vector<int32_t> loc_primer[2];
+    std::vector<int32_t> mate_off, mate_idx;
+    std::vector<int32_t> smat16;              // 16*16 nibble scoring table or empty
+    idp::KmerIndexHost kidx[2];
+};

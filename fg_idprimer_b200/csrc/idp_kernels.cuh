@@ -1,0 +1,765 @@
+// CUDA kernels of the IdentifyPrimers matching path (sm_100a).  Host launchers are in idp_ctx.cu.
+//
+// Data model on the device
+//   reads   : BAM-native 4-bit bases, SoA (DevReads); never unpacked to ASCII.
+//   panel   : DevPanel (idp_internal.h) -- primer IUPAC masks 8 bases / 32-bit word, k-mer hash tables whose posting
+//             lists are in the reference's Set iteration order, per-strand sorted location arrays.
+//   results : idp_result (32 B) per read.
+//
+// Kernels (reference function each one covers)
+//   scan_kernel        basesInSequencingOrder (PM:39-45) + LocationBasedPrimerMatcher.find (PM:194-213) +
+//                      getPrimersForAlignmentTasks (PM:98-116) + mismatchAlign / numMismatches (PM:128-147) +
+//                      getBestUngappedAlignment (PM:237-248); reads with no match go to the fall-through list
+//   cand5_kernel       GappedAlignmentBasedPrimerMatcher.toAlignmentTasks candidates under -K (PM:287-296, 108-116)
+//   cand3_kernel       matchThreePrime's primersToCheck (IP:490-499)
+//   sw_pairs_kernel    fgbio Aligner.align, score only, one thread per (read, primer) pair (IP:446-448, 509-513)
+//   sw_all_kernel      the same when every primer is a candidate: one block per read, best two kept on chip
+//   finalize_kernel    getBestGappedAlignment (PM:305-328) + traceback of the winner + finalizedGappedAlignment (IP:459-471)
+//   metrics_kernel     TemplateType + TemplateTypeMetric counter (TemplateType.scala:52-63, IP:413)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "idp_internal.h"
+
+namespace idp {
+
+struct DevReads {
+    const uint8_t *seq4;
+    const uint64_t *seq_off;
+    const int32_t *len;
+    const int32_t *ref_idx;
+    const int32_t *ustart;
+    const int32_t *uend;
+    const uint16_t *flags;
+    int32_t fixed_len;
+    int32_t n;
+};
+
+// device-side counters of one batch (one per stream slot)
+struct Counters {
+    unsigned int n_fall;          // reads that fell through to the gapped stage
+    unsigned int n_pairs;         // (read, primer) pairs emitted for sw_pairs_kernel
+    unsigned int n_all;           // 3' reads that take every primer
+    unsigned int overflow;        // pair buffer too small: number of work items not emitted
+    unsigned long long n_align5;  // alignments performed by the 5' aligner (IP:424)
+    unsigned long long n_align3;
+    unsigned long long sw_cells;
+    unsigned long long base_compares;
+    unsigned long long metrics[160];
+};
+
+// the winner (and runner-up) of one read's gapped candidates, before traceback
+struct Fin {
+    int32_t primer, raw, raw_next;
+    int16_t qlen, qlen_next;
+    int32_t count;  // number of candidates aligned; 0 = none
+};
+
+__device__ __forceinline__ void read_geom(const DevReads &R, int r, const uint8_t *&s, int &len) {
+    if (R.fixed_len > 0) { len = R.fixed_len; s = R.seq4 + (size_t)r * (size_t)((R.fixed_len + 1) >> 1); }
+    else { len = R.len[r]; s = R.seq4 + R.seq_off[r]; }
+}
+__device__ __forceinline__ uint32_t stored_nib(const uint8_t *s, int i) {
+    uint32_t b = __ldg(s + (i >> 1));
+    return (i & 1) ? (b & 15u) : (b >> 4);
+}
+// htsjdk 2.16 SequenceUtil.complement touches only A<->T, C<->G (nibbles 1<->8, 2<->4); every other code is kept (PM:42)
+__device__ __forceinline__ uint32_t comp_nib(uint32_t x) { return (uint32_t)(0xFEDCBA9176523480ull >> (4 * x)) & 15u; }
+
+// a read viewed in a given orientation: forward = as stored, rc = reverse-complemented
+struct Oriented {
+    const uint8_t *s;
+    int len;
+    bool rc;
+    __device__ __forceinline__ uint32_t nib(int j) const { return rc ? comp_nib(stored_nib(s, len - 1 - j)) : stored_nib(s, j); }
+};
+// sequencing order (PM:39-45): raw when unmapped or positive strand, else reverse complement
+__device__ __forceinline__ bool seq_order_is_rc(uint16_t fl) { return !(fl & IDP_F_UNMAPPED) && (fl & IDP_F_REVERSE); }
+
+__device__ __forceinline__ void write_result(idp_result *dst, const idp_result &v) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(&v);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    d[0] = src[0];
+    d[1] = src[1];
+}
+__device__ __forceinline__ idp_result none_result() {
+    idp_result r;
+    r.primer = -1; r.type = IDP_NONE; r.status = 0; r.multi = 0; r.reserved = 0;
+    r.mm = 0; r.next_mm = 0; r.raw_score = 0; r.raw_next = 0; r.q_len = 0; r.q_len_next = 0; r.t_start = 0; r.t_end = 0;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel A+B: scan.  One thread per read.
+// ---------------------------------------------------------------------------------------------------------------
+struct Best2 {  // getBestUngappedAlignment (PM:237-248) as a running stable top-2 on key = mm / Primer.length
+    int bp = -1, bmm = 0, sp = -1, smm = 0;
+    double bkey = 0.0, skey = 0.0;
+    __device__ __forceinline__ void offer(int p, int mm, double key) {
+        if (bp < 0 || key < bkey) { sp = bp; smm = bmm; skey = bkey; bp = p; bmm = mm; bkey = key; }
+        else if (sp < 0 || key < skey) { sp = p; smm = mm; skey = key; }
+    }
+};
+
+template <int RW>
+struct ScanCtx {
+    uint32_t win[RW];  // read prefix in sequencing order, base i in nibble i, zero beyond the read
+    int len;
+    unsigned long long compares;
+};
+
+// numMismatches + mismatchAlign (PM:128-147).  Returns true and mm when the rate test passes.
+template <int RW>
+__device__ __forceinline__ bool mismatch_align(const DevPanel &P, ScanCtx<RW> &c, int p, int &mm_out) {
+    const int4 info = __ldg(&P.pinfo[p]);  // {Primer.length, cap, accept, sequence.length}
+    const uint32_t *pm = P.pmask + (size_t)p * P.ww;
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < RW; ++w) {
+        if (w < P.ww) {
+            uint32_t x = c.win[w] & ~__ldg(&pm[w]);  // read mask not a subset of primer mask (PM:143)
+            x |= x >> 1;
+            x |= x >> 2;
+            total += __popc(x & 0x11111111u);
+        }
+    }
+    c.compares += (unsigned)min(c.len, info.w);
+    int cap, acc;
+    if (c.len >= info.x) { cap = info.y; acc = info.z; }
+    else {  // short read: length = min(bases.length, primer.length) in the JVM's double arithmetic (PM:130-134)
+        const int length = c.len;
+        const double max_mismatches = (double)length * P.max_mismatch_rate;
+        const double capd = floor(max_mismatches) + 1.0;
+        cap = capd > 1e9 ? 1000000000 : (int)capd;
+        const int mm = min(total, cap);
+        mm_out = mm;
+        return __ddiv_rn((double)mm, (double)length) <= P.max_mismatch_rate;
+    }
+    const int mm = min(total, cap);  // the while loop stops counting once count > maxMismatches (PM:142)
+    mm_out = mm;
+    return mm <= acc;
+}
+
+template <int RW>
+__global__ void __launch_bounds__(256) scan_kernel(DevPanel P, DevReads R, idp_result *__restrict__ five,
+                                                   unsigned int *__restrict__ fall, Counters *__restrict__ ctr) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = r < R.n;
+    bool need_gapped = false;
+    ScanCtx<RW> c;
+    c.compares = 0;
+    if (active) {
+        const uint16_t fl = R.flags[r];
+        const uint8_t *s;
+        read_geom(R, r, s, c.len);
+        Oriented o{s, c.len, seq_order_is_rc(fl)};
+        // basesInSequencingOrder (PM:39-45), only the prefix the matchers can look at
+        const int nb = min(c.len, P.window_bases);
+#pragma unroll
+        for (int w = 0; w < RW; ++w) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const int i = w * 8 + b;
+                if (i < nb) v |= o.nib(i) << (4 * b);
+            }
+            c.win[w] = v;
+        }
+        idp_result res = none_result();
+        // ---- LocationBasedPrimerMatcher.find (PM:194-213) ----
+        if (!(fl & IDP_F_UNMAPPED)) {
+            const int strand = (fl & IDP_F_REVERSE) ? 1 : 0;
+            const int nl = P.n_loc[strand];
+            if (nl > 0) {
+                const int pos = strand ? R.uend[r] : R.ustart[r];  // PM:180, 186
+                const int ref = R.ref_idx[r];
+                if (ref >= 0) {
+                    const int64_t lo = ((int64_t)ref << 32) | (uint32_t)max(pos - P.slop, 0);
+                    const int64_t hi = ((int64_t)ref << 32) | (uint32_t)(pos + P.slop);
+                    const int64_t *keys = P.loc_sortkey[strand];
+                    int a = 0, b = nl;
+                    while (a < b) { const int m = (a + b) >> 1; if (__ldg(&keys[m]) < lo) a = m + 1; else b = m; }
+                    // exactly one primer within slop, else "well I give up" (PM:198-206)
+                    if (a < nl && __ldg(&keys[a]) <= hi && !(a + 1 < nl && __ldg(&keys[a + 1]) <= hi)) {
+                        const int p = __ldg(&P.loc_primer[strand][a]);
+                        int mm;
+                        if (mismatch_align<RW>(P, c, p, mm)) { res.primer = p; res.type = IDP_LOCATION; res.mm = mm; }
+                    }
+                }
+            }
+        }
+        // ---- UngappedAlignmentBasedPrimerMatcher.find (PM:230-248) ----
+        if (res.type == IDP_NONE) {
+            Best2 best;
+            const DevKmerIndex &ix = P.kidx[0];
+            if (ix.k <= 0) {  // PM:100: every primer, file order
+                for (int p = 0; p < P.n_primers; ++p) {
+                    int mm;
+                    if (mismatch_align<RW>(P, c, p, mm)) best.offer(p, mm, __ddiv_rn((double)mm, (double)__ldg(&P.pinfo[p]).x));
+                }
+            } else if (c.len >= ix.k) {  // PM:108-116
+                const int end = min(ix.window, c.len) - ix.k + 1;
+                const uint64_t kmask = ix.k >= 16 ? ~0ull : ((1ull << (4 * ix.k)) - 1ull);
+                uint64_t key = 0;
+#pragma unroll
+                for (int i = 0; i < RW * 8; ++i) {
+                    key = ((key << 4) | ((c.win[i >> 3] >> (4 * (i & 7))) & 15u)) & kmask;
+                    const int start = i - (ix.k - 1);
+                    if (start >= 0 && start < end && key != 0) {
+                        uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> ix.shift);
+                        for (;;) {
+                            const uint64_t kk = __ldg(&ix.keys[h]);
+                            if (kk == key) {
+                                const OffCnt oc = ix.off_cnt[h];
+                                for (uint32_t j = 0; j < oc.cnt; ++j) {
+                                    const int p = (int)__ldg(&ix.postings[oc.off + j]);
+                                    // .distinct (PM:114): a primer already holding a top-2 slot is skipped; one that lost
+                                    // before loses again (strict comparisons), so no visited set is needed
+                                    if (p == best.bp || p == best.sp) continue;
+                                    int mm;
+                                    if (mismatch_align<RW>(P, c, p, mm)) best.offer(p, mm, __ddiv_rn((double)mm, (double)__ldg(&P.pinfo[p]).x));
+                                }
+                                break;
+                            }
+                            if (kk == 0) break;
+                            h = (h + 1) & ix.slot_mask;
+                        }
+                    }
+                }
+            }
+            if (best.bp >= 0) {
+                res.primer = best.bp; res.type = IDP_UNGAPPED; res.mm = best.bmm;
+                res.next_mm = best.sp >= 0 ? best.smm : IDP_NEXT_NA;               // PM:244-245
+                if (!(res.mm <= res.next_mm)) res.status = IDP_STATUS_REQ_MM_LE_NEXT;  // PMa:102
+            }
+        }
+        need_gapped = res.type == IDP_NONE;
+        write_result(&five[r], res);
+    }
+    // fall-through list (IP:444-450), warp-aggregated append
+    const unsigned ballot = __ballot_sync(0xffffffffu, need_gapped);
+    if (ballot) {
+        const int lane = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane == __ffs(ballot) - 1) base = atomicAdd(&ctr->n_fall, __popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+        if (need_gapped) fall[base + __popc(ballot & ((1u << lane) - 1u))] = (unsigned)r;
+    }
+    // statistics: base comparisons, one atomic per warp
+    unsigned long long cmp = c.compares;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cmp += __shfl_xor_sync(0xffffffffu, cmp, d);
+    if ((threadIdx.x & 31) == 0 && cmp) atomicAdd(&ctr->base_compares, cmp);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Candidate emission for the 5' gapped stage under -K: one warp per fall-through read.  Walks the read's k-mers in
+// order; a per-warp bitmap in shared memory implements `.distinct` (PM:114).  Pass 1 sets bits and counts, pass 2
+// clears them again while emitting, so the bitmap is zero for the next read.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool kmer_lookup(const DevKmerIndex &ix, uint64_t key, OffCnt &oc) {
+    if (key == 0) return false;
+    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> ix.shift);
+    for (;;) {
+        const uint64_t kk = __ldg(&ix.keys[h]);
+        if (kk == key) { oc = ix.off_cnt[h]; return true; }
+        if (kk == 0) return false;
+        h = (h + 1) & ix.slot_mask;
+    }
+}
+
+__global__ void __launch_bounds__(256) cand5_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ fall,
+                                                    Counters *__restrict__ ctr, unsigned int *__restrict__ pair_work,
+                                                    unsigned int *__restrict__ pair_primer, unsigned int pair_cap,
+                                                    unsigned int *__restrict__ seg_off, int *__restrict__ seg_cnt) {
+    extern __shared__ uint32_t bitmap_all[];
+    const int warps_per_block = blockDim.x >> 5, wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int words = (P.n_primers + 31) >> 5;
+    uint32_t *bitmap = bitmap_all + (size_t)wib * words;
+    for (int i = lane; i < words; i += 32) bitmap[i] = 0;
+    __syncwarp();
+    const DevKmerIndex &ix = P.kidx[1];
+    const unsigned n_work = ctr->n_fall;
+    const uint64_t kmask = ix.k >= 16 ? ~0ull : ((1ull << (4 * ix.k)) - 1ull);
+    for (unsigned w = blockIdx.x * warps_per_block + wib; w < n_work; w += gridDim.x * warps_per_block) {
+        const int r = (int)fall[w];
+        const uint16_t fl = R.flags[r];
+        const uint8_t *s; int len;
+        read_geom(R, r, s, len);
+        Oriented o{s, len, seq_order_is_rc(fl)};
+        const int end = len >= ix.k ? min(ix.window, len) - ix.k + 1 : 0;
+        unsigned base = 0, count = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            unsigned emitted = 0;
+            uint64_t key = 0;
+            for (int i = 0; i < end + ix.k - 1; ++i) {
+                key = ((key << 4) | o.nib(i)) & kmask;
+                if (i < ix.k - 1) continue;
+                OffCnt oc;
+                if (!kmer_lookup(ix, key, oc)) continue;
+                for (uint32_t j0 = 0; j0 < oc.cnt; j0 += 32) {
+                    const uint32_t j = j0 + lane;
+                    bool fresh = false;
+                    uint32_t p = 0;
+                    if (j < oc.cnt) {
+                        p = __ldg(&ix.postings[oc.off + j]);
+                        const uint32_t bit = 1u << (p & 31);
+                        if (pass == 0) fresh = !(atomicOr(&bitmap[p >> 5], bit) & bit);
+                        else fresh = (atomicAnd(&bitmap[p >> 5], ~bit) & bit) != 0;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, fresh);
+                    if (pass == 1 && fresh && count != 0xffffffffu) {
+                        const unsigned at = base + emitted + __popc(m & ((1u << lane) - 1u));
+                        pair_work[at] = w;
+                        pair_primer[at] = p;
+                    }
+                    emitted += __popc(m);
+                }
+            }
+            if (pass == 0) {
+                count = emitted;
+                if (lane == 0 && count) base = atomicAdd(&ctr->n_pairs, count);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (count && (unsigned long long)base + count > pair_cap) {  // does not fit: report, emit nothing
+                    if (lane == 0) { atomicAdd(&ctr->overflow, 1u); seg_off[w] = 0; seg_cnt[w] = -1; }
+                    count = 0xffffffffu;
+                } else if (lane == 0) { seg_off[w] = base; seg_cnt[w] = (int)count; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Candidate selection for 3' matching (IP:490-499): one thread per read.  Reads with a short candidate list emit
+// pairs; reads that must try every primer go to the `all` list (handled by sw_all_kernel).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int mate_of(const DevReads &R, int r) {
+    const uint16_t fl = R.flags[r];
+    if ((fl & IDP_F_MATE_NEXT) && r + 1 < R.n) return r + 1;
+    if (r > 0 && (R.flags[r - 1] & IDP_F_MATE_NEXT)) return r - 1;
+    return -1;
+}
+
+__global__ void __launch_bounds__(256) cand3_kernel(DevPanel P, DevReads R, const idp_result *__restrict__ five,
+                                                    Counters *__restrict__ ctr, unsigned int *__restrict__ all_list,
+                                                    unsigned int *__restrict__ pair_work, unsigned int *__restrict__ pair_primer,
+                                                    unsigned int pair_cap, unsigned int *__restrict__ seg_off, int *__restrict__ seg_cnt) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int count = 0, first = -1, mode = 0;  // mode 0: nothing, 1: single primer, 2: mates of own primer, 3: all primers
+    if (r < R.n) {
+        const int mate = mate_of(R, r);
+        const int own_type = five[r].type, own_primer = five[r].primer;
+        int other_type = IDP_NONE, other_primer = -1;
+        if (mate >= 0) { other_type = five[mate].type; other_primer = five[mate].primer; }
+        if (other_type != IDP_NONE) { mode = 1; count = 1; first = other_primer; }                       // IP:495
+        else if (own_type != IDP_NONE) { mode = 2; first = own_primer; count = P.mate_off[own_primer + 1] - P.mate_off[own_primer]; }  // IP:496
+        else mode = 3;                                                                                   // IP:497
+    }
+    // all-primer reads
+    const unsigned ball = __ballot_sync(0xffffffffu, mode == 3);
+    if (ball) {
+        unsigned b = 0;
+        if (lane == __ffs(ball) - 1) b = atomicAdd(&ctr->n_all, __popc(ball));
+        b = __shfl_sync(0xffffffffu, b, __ffs(ball) - 1);
+        if (mode == 3) all_list[b + __popc(ball & ((1u << lane) - 1u))] = (unsigned)r;
+    }
+    // pair emission, warp-aggregated reservation
+    int incl = count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned base = 0;
+    if (lane == 31 && total) base = atomicAdd(&ctr->n_pairs, (unsigned)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (r < R.n) {
+        if (mode == 3) { seg_off[r] = 0; seg_cnt[r] = -2; }  // handled through the all list
+        else if ((unsigned long long)base + total > pair_cap) { if (count) atomicAdd(&ctr->overflow, 1u); seg_off[r] = 0; seg_cnt[r] = count ? -1 : 0; }
+        else {
+            const unsigned at = base + (unsigned)(incl - count);
+            seg_off[r] = at; seg_cnt[r] = count;
+            if (mode == 1) { pair_work[at] = (unsigned)r; pair_primer[at] = (unsigned)first; }
+            else if (mode == 2) {
+                const int o0 = P.mate_off[first];
+                for (int j = 0; j < count; ++j) { pair_work[at + j] = (unsigned)r; pair_primer[at + j] = (unsigned)P.mate_idx[o0 + j]; }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Smith-Waterman, score only.  fgbio Aligner's three matrices (Diagonal / Left / Up) with gap cost open + L*extend,
+// free leading and trailing target gaps in Glocal, clamp-at-zero Diagonal in Local.  One thread owns one alignment:
+// the query (primer) indexes NQ register-resident rows, the target (read) is streamed column by column.
+//   D(i,j) = s(q_i,t_j) + max(D,L,U)(i-1,j-1)      U(i,j) = max(D(i-1,j)+o+e, U(i-1,j)+e)
+//   L(i,j) = max(D(i,j-1)+o+e, L(i,j-1)+e)          M = max(D,L,U) is kept per row for the next column's diagonal
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int score_of(const DevPanel &P, uint32_t q, uint32_t t) { return q == t ? P.match_score : P.mismatch_score; }
+
+template <int NQ, bool LOCAL, bool SMAT>
+__device__ __forceinline__ int sw_score(const DevPanel &P, const int32_t *__restrict__ smat, const uint32_t *__restrict__ qwords, int n,
+                                        int n_warp_max, const Oriented &T, int m, bool &missing) {
+    const int oe = P.gap_open + P.gap_extend, e = P.gap_extend;
+    if (m == 0) return LOCAL ? 0 : P.gap_open + n * P.gap_extend;
+    uint32_t q[(NQ + 7) / 8];
+#pragma unroll
+    for (int w = 0; w < (NQ + 7) / 8; ++w) q[w] = w < P.ww ? __ldg(&qwords[w]) : 0u;
+    int D[NQ], L[NQ], M[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        if (LOCAL) { D[i] = 0; L[i] = 0; M[i] = 0; }
+        else { D[i] = kNegInf; L[i] = kNegInf; M[i] = P.gap_open + (i + 1) * P.gap_extend; }  // Up(i,0)
+    }
+    int best = LOCAL ? 0 : kNegInf;
+    for (int j = 0; j < m; ++j) {
+        const uint32_t t = T.nib(j);
+        int mdiag = 0, d_up = 0, u_up = 0;  // row 0 is all zero in Glocal and Local
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            if (i >= n_warp_max) break;
+            if (i < n) {
+                const uint32_t qc = (q[i >> 3] >> (4 * (i & 7))) & 15u;
+                int s;
+                if (SMAT) { s = smat[qc * 16 + t]; if (s == INT32_MIN) { missing = true; s = 0; } }
+                else s = qc == t ? P.match_score : P.mismatch_score;
+                int dn = mdiag + s;
+                if (LOCAL) dn = max(dn, 0);
+                const int un = __viaddmax_s32(d_up, oe, u_up + e);
+                const int ln = __viaddmax_s32(D[i], oe, L[i] + e);
+                mdiag = M[i];
+                const int mn = __vimax3_s32(dn, ln, un);
+                D[i] = dn; L[i] = ln; M[i] = mn;
+                d_up = dn; u_up = un;
+                if (LOCAL) best = max(best, dn);
+                else if (i == n - 1) best = max(best, mn);
+            }
+        }
+    }
+    return best;
+}
+
+// generic fallback for primers longer than the register-resident variants cover: rows live in local memory
+template <bool LOCAL, bool SMAT>
+__device__ int sw_score_generic(const DevPanel &P, const int32_t *__restrict__ smat, const uint32_t *__restrict__ qwords, int n,
+                                const Oriented &T, int m, bool &missing) {
+    const int oe = P.gap_open + P.gap_extend, e = P.gap_extend;
+    if (m == 0) return LOCAL ? 0 : P.gap_open + n * P.gap_extend;
+    int D[kMaxPrimerBases], L[kMaxPrimerBases], M[kMaxPrimerBases];
+    for (int i = 0; i < n; ++i) {
+        if (LOCAL) { D[i] = 0; L[i] = 0; M[i] = 0; }
+        else { D[i] = kNegInf; L[i] = kNegInf; M[i] = P.gap_open + (i + 1) * P.gap_extend; }
+    }
+    int best = LOCAL ? 0 : kNegInf;
+    for (int j = 0; j < m; ++j) {
+        const uint32_t t = T.nib(j);
+        int mdiag = 0, d_up = 0, u_up = 0;
+        for (int i = 0; i < n; ++i) {
+            const uint32_t qc = (__ldg(&qwords[i >> 3]) >> (4 * (i & 7))) & 15u;
+            int s;
+            if (SMAT) { s = smat[qc * 16 + t]; if (s == INT32_MIN) { missing = true; s = 0; } }
+            else s = qc == t ? P.match_score : P.mismatch_score;
+            int dn = mdiag + s;
+            if (LOCAL) dn = max(dn, 0);
+            const int un = max(d_up + oe, u_up + e);
+            const int ln = max(D[i] + oe, L[i] + e);
+            mdiag = M[i];
+            const int mn = max(dn, max(ln, un));
+            D[i] = dn; L[i] = ln; M[i] = mn;
+            d_up = dn; u_up = un;
+            if (LOCAL) best = max(best, dn);
+            else if (i == n - 1) best = max(best, mn);
+        }
+    }
+    return best;
+}
+
+// the target of one (read, primer) task: 5' = read prefix of |primer|+slop bases in sequencing order (PM:292-293);
+// 3' = reverse complement of the whole read in sequencing order (IP:502-506)
+__device__ __forceinline__ Oriented make_target(const DevPanel &P, const DevReads &R, int r, int primer_seq_len, bool three_prime, int &m) {
+    const uint8_t *s; int len;
+    read_geom(R, r, s, len);
+    const bool so_rc = seq_order_is_rc(R.flags[r]);
+    if (three_prime) { m = len; return Oriented{s, len, !so_rc}; }
+    m = min(primer_seq_len + P.slop, len);
+    return Oriented{s, len, so_rc};
+}
+
+constexpr int32_t kScoreMissing = INT32_MIN;  // pair touched a base pair the scoring matrix has no entry for
+
+template <int NQ, bool LOCAL, bool SMAT>
+__global__ void __launch_bounds__(128) sw_pairs_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
+                                                       Counters *ctr, const unsigned int *__restrict__ pair_work,
+                                                       const unsigned int *__restrict__ pair_primer, int *__restrict__ pair_score) {
+    __shared__ int32_t smat_s[256];
+    if (SMAT) { for (int i = threadIdx.x; i < 256; i += blockDim.x) smat_s[i] = P.smat[i]; __syncthreads(); }
+    const unsigned n_pairs = ctr->n_pairs;
+    unsigned long long cells = 0;
+    for (unsigned base = blockIdx.x * blockDim.x; base < n_pairs; base += gridDim.x * blockDim.x) {
+        const unsigned t = base + threadIdx.x;
+        const bool active = t < n_pairs;
+        int n = 0, m = 0, p = 0;
+        Oriented T{nullptr, 0, false};
+        if (active) {
+            const unsigned w = pair_work[t];
+            const int r = work_read ? (int)work_read[w] : (int)w;
+            p = (int)pair_primer[t];
+            n = __ldg(&P.pinfo[p]).w;
+            T = make_target(P, R, r, n, LOCAL, m);
+        }
+        const int n_warp_max = __reduce_max_sync(0xffffffffu, n);
+        if (active) {
+            bool missing = false;
+            int sc;
+            if (NQ > 0) sc = sw_score<(NQ > 0 ? NQ : 8), LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, n_warp_max, T, m, missing);
+            else sc = sw_score_generic<LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, T, m, missing);
+            pair_score[t] = missing ? kScoreMissing : sc;
+            cells += (unsigned long long)n * (unsigned long long)m;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, d);
+    if ((threadIdx.x & 31) == 0 && cells) atomicAdd(&ctr->sw_cells, cells);
+}
+
+// running best two by the stable sortBy(-score / query.length) of PM:308-310; ties keep the lower candidate ordinal
+struct GBest2 {
+    int b_ord = -1, b_primer = 0, b_score = 0, b_qlen = 1;
+    int s_ord = -1, s_primer = 0, s_score = 0, s_qlen = 1;
+    __device__ __forceinline__ static bool before(int sa, int qa, int oa, int sb, int qb, int ob) {
+        const double ka = -__ddiv_rn((double)sa, (double)qa), kb = -__ddiv_rn((double)sb, (double)qb);
+        return ka < kb || (ka == kb && oa < ob);
+    }
+    __device__ __forceinline__ void offer(int ord, int primer, int score, int qlen) {
+        if (ord < 0) return;
+        if (b_ord < 0 || before(score, qlen, ord, b_score, b_qlen, b_ord)) {
+            s_ord = b_ord; s_primer = b_primer; s_score = b_score; s_qlen = b_qlen;
+            b_ord = ord; b_primer = primer; b_score = score; b_qlen = qlen;
+        } else if (s_ord < 0 || before(score, qlen, ord, s_score, s_qlen, s_ord)) {
+            s_ord = ord; s_primer = primer; s_score = score; s_qlen = qlen;
+        }
+    }
+    __device__ __forceinline__ void merge_from_lane(int src_lane_xor) {
+        const int o1 = __shfl_xor_sync(0xffffffffu, b_ord, src_lane_xor), p1 = __shfl_xor_sync(0xffffffffu, b_primer, src_lane_xor);
+        const int c1 = __shfl_xor_sync(0xffffffffu, b_score, src_lane_xor), q1 = __shfl_xor_sync(0xffffffffu, b_qlen, src_lane_xor);
+        const int o2 = __shfl_xor_sync(0xffffffffu, s_ord, src_lane_xor), p2 = __shfl_xor_sync(0xffffffffu, s_primer, src_lane_xor);
+        const int c2 = __shfl_xor_sync(0xffffffffu, s_score, src_lane_xor), q2 = __shfl_xor_sync(0xffffffffu, s_qlen, src_lane_xor);
+        offer(o1, p1, c1, q1);
+        offer(o2, p2, c2, q2);
+    }
+};
+
+// Every primer is a candidate (no -K, or 3' with no 5' match anywhere): one block per read, threads stride the panel
+// in file order, the best two are reduced on chip.  Nothing per-pair ever touches HBM.
+template <int NQ, bool LOCAL, bool SMAT>
+__global__ void __launch_bounds__(128) sw_all_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
+                                                     const unsigned int *__restrict__ n_work_ptr, Fin *__restrict__ fin,
+                                                     Counters *__restrict__ ctr_out, int count_as_5p) {
+    __shared__ int32_t smat_s[256];
+    __shared__ int red[4][8];  // per-warp GBest2
+    if (SMAT) { for (int i = threadIdx.x; i < 256; i += blockDim.x) smat_s[i] = P.smat[i]; __syncthreads(); }
+    const unsigned n_work = *n_work_ptr;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    unsigned long long cells = 0;
+    for (unsigned w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int r = (int)work_read[w];
+        GBest2 g;
+        bool any_missing = false;
+        for (int p0 = 0; p0 < P.n_primers; p0 += blockDim.x) {
+            const int p = p0 + threadIdx.x;
+            const bool active = p < P.n_primers;
+            int n = 0, m = 0;
+            Oriented T{nullptr, 0, false};
+            if (active) { n = __ldg(&P.pinfo[p]).w; T = make_target(P, R, r, n, LOCAL, m); }
+            const int n_warp_max = __reduce_max_sync(0xffffffffu, n);
+            if (active) {
+                bool missing = false;
+                int sc;
+                if (NQ > 0) sc = sw_score<(NQ > 0 ? NQ : 8), LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, n_warp_max, T, m, missing);
+                else sc = sw_score_generic<LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, T, m, missing);
+                any_missing |= missing;
+                g.offer(p, p, sc, n);
+                cells += (unsigned long long)n * (unsigned long long)m;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) g.merge_from_lane(d);
+        const bool miss_block = __syncthreads_or(any_missing);
+        if (lane == 0) { red[wib][0] = g.b_ord; red[wib][1] = g.b_primer; red[wib][2] = g.b_score; red[wib][3] = g.b_qlen;
+                         red[wib][4] = g.s_ord; red[wib][5] = g.s_primer; red[wib][6] = g.s_score; red[wib][7] = g.s_qlen; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            GBest2 t;
+            for (int k = 0; k < nwarps; ++k) { t.offer(red[k][0], red[k][1], red[k][2], red[k][3]); t.offer(red[k][4], red[k][5], red[k][6], red[k][7]); }
+            Fin f;
+            f.count = P.n_primers; f.primer = t.b_primer; f.raw = miss_block ? kScoreMissing : t.b_score; f.qlen = (int16_t)t.b_qlen;
+            f.raw_next = t.s_ord >= 0 ? t.s_score : 0; f.qlen_next = (int16_t)(t.s_ord >= 0 ? t.s_qlen : 0);
+            fin[w] = f;
+            if (count_as_5p) atomicAdd(&ctr_out->n_align5, (unsigned long long)P.n_primers);
+            else atomicAdd(&ctr_out->n_align3, (unsigned long long)P.n_primers);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, d);
+    if (lane == 0 && cells) atomicAdd(&ctr_out->sw_cells, cells);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Traceback-equivalent: re-align the winner carrying, next to every score, the target offset at which its path left
+// the free first row (Glocal) / a zero cell (Local).  The tie rules are the ones an explicit traceback would follow:
+// Diagonal over Left over Up for the diagonal move, Diagonal over gap extension, strict '>' for the end cell scanning
+// target positions (and query rows in Local) in ascending order.  Returns score, targetStart (1-based), targetEnd.
+// ---------------------------------------------------------------------------------------------------------------
+struct Traced { int score, t_start, t_end; bool missing; };
+
+template <int TN>
+__device__ Traced sw_trace(const DevPanel &P, const uint32_t *__restrict__ qwords, int n, const Oriented &T, int m, int mode) {
+    const int oe = P.gap_open + P.gap_extend, e = P.gap_extend;
+    Traced out{0, 1, 0, false};
+    const bool local = mode == IDP_MODE_LOCAL, global = mode == IDP_MODE_GLOBAL;
+    if (m == 0) { out.score = local ? 0 : P.gap_open + n * P.gap_extend; return out; }
+    int D[TN], L[TN], M[TN];
+    short sD[TN], sL[TN], sM[TN];
+    for (int i = 0; i < n; ++i) {
+        sD[i] = 0; sL[i] = 0; sM[i] = 0;
+        if (local) { D[i] = 0; L[i] = 0; M[i] = 0; }
+        else { D[i] = kNegInf; L[i] = kNegInf; M[i] = P.gap_open + (i + 1) * P.gap_extend; }
+    }
+    int best = kNegInf, bi = 0, bj = 0, bstart = 0;
+    for (int j = 1; j <= m; ++j) {
+        const uint32_t t = T.nib(j - 1);
+        // row 0: all matrices zero / Done in Glocal and Local; Global has only Left = open + j*extend
+        int mdiag, smdiag, d_up, sd_up, u_up, su_up;
+        if (!global) { mdiag = 0; smdiag = j - 1; d_up = 0; sd_up = j; u_up = 0; su_up = j; }
+        else { mdiag = j == 1 ? 0 : P.gap_open + (j - 1) * P.gap_extend; smdiag = 0; d_up = kNegInf; sd_up = 0; u_up = kNegInf; su_up = 0; }
+        for (int i = 0; i < n; ++i) {
+            const uint32_t qc = (__ldg(&qwords[i >> 3]) >> (4 * (i & 7))) & 15u;
+            int s;
+            if (P.smat) { s = __ldg(&P.smat[qc * 16 + t]); if (s == INT32_MIN) { out.missing = true; s = 0; } }
+            else s = qc == t ? P.match_score : P.mismatch_score;
+            int dn = mdiag + s, sdn = smdiag;
+            if (local && dn < 0) { dn = 0; sdn = j; }
+            int un, sun, ln, sln;
+            { const int a = d_up + oe, b = u_up + e; if (a >= b) { un = a; sun = sd_up; } else { un = b; sun = su_up; } }
+            { const int a = D[i] + oe, b = L[i] + e; if (a >= b) { ln = a; sln = sD[i]; } else { ln = b; sln = sL[i]; } }
+            int mn = dn, smn = sdn;
+            if (ln > mn) { mn = ln; smn = sln; }
+            if (un > mn) { mn = un; smn = sun; }
+            mdiag = M[i]; smdiag = sM[i];
+            D[i] = dn; sD[i] = (short)sdn; L[i] = ln; sL[i] = (short)sln; M[i] = mn; sM[i] = (short)smn;
+            d_up = dn; sd_up = sdn; u_up = un; su_up = sun;
+            if (local) {  // best over all cells: lowest row, then lowest column, then Diagonal / Left / Up
+                if (dn > best || (dn == best && i + 1 < bi)) { best = dn; bi = i + 1; bj = j; bstart = sdn; }
+                if (ln > best || (ln == best && i + 1 < bi)) { best = ln; bi = i + 1; bj = j; bstart = sln; }
+                if (un > best || (un == best && i + 1 < bi)) { best = un; bi = i + 1; bj = j; bstart = sun; }
+            } else if (i == n - 1 && (!global || j == m)) {
+                if (dn > best) { best = dn; bj = j; bstart = sdn; }
+                if (ln > best) { best = ln; bj = j; bstart = sln; }
+                if (un > best) { best = un; bj = j; bstart = sun; }
+            }
+        }
+    }
+    out.score = best; out.t_start = bstart + 1; out.t_end = bj;
+    return out;
+}
+
+// getBestGappedAlignment (PM:305-328) + GappedAlignmentPrimerMatch requires (PMa:113-114) + the score-rate filter (IP:464-469)
+template <int TN>
+__device__ void finish_gapped(const DevPanel &P, const DevReads &R, int r, const Fin &f, bool three_prime, idp_result *__restrict__ out) {
+    idp_result res = none_result();
+    if (f.count > 0) {
+        if (f.raw == kScoreMissing) res.status = IDP_STATUS_SCORE_MISSING;
+        else if (!(f.count == 1 && f.raw < 0)) {  // PM:314
+            int m;
+            const int n = __ldg(&P.pinfo[f.primer]).w;
+            Oriented T = make_target(P, R, r, n, three_prime, m);
+            const Traced tr = sw_trace<TN>(P, P.pmask + (size_t)f.primer * P.ww, n, T, m, three_prime ? IDP_MODE_LOCAL : IDP_MODE_GLOCAL);
+            res.primer = f.primer; res.type = IDP_GAPPED; res.multi = f.count > 1;
+            res.raw_score = tr.score; res.q_len = f.qlen;
+            res.raw_next = f.count > 1 ? f.raw_next : 0; res.q_len_next = f.count > 1 ? f.qlen_next : 0;
+            res.t_start = (int16_t)tr.t_start; res.t_end = (int16_t)tr.t_end;
+            const double score = res.multi ? __ddiv_rn((double)res.raw_score, (double)res.q_len) : (double)res.raw_score;
+            const double second = res.multi ? __ddiv_rn((double)res.raw_next, (double)res.q_len_next) : 0.0;
+            if (!(score >= second)) res.status = IDP_STATUS_REQ_SCORE_GE_SECOND;
+            else if (!(tr.t_start <= tr.t_end)) res.status = IDP_STATUS_REQ_START_LE_END;
+            const double rate = __ddiv_rn(score, (double)__ldg(&P.pinfo[f.primer]).x);  // IP:467
+            if (!(rate >= P.min_alignment_score_rate)) { const uint8_t st = res.status; res = none_result(); res.status = st; }
+        }
+    }
+    // a read that reached the gapped stage keeps a require-failure recorded by the ungapped stage (none can exist: it had no match)
+    write_result(&out[r], res);
+}
+
+// pair mode: one thread per work item picks the best two of its segment, then finishes
+template <int TN>
+__global__ void __launch_bounds__(128) finalize_pairs_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
+                                                             const unsigned int *__restrict__ n_work_ptr, unsigned int n_work_fixed,
+                                                             const unsigned int *__restrict__ seg_off, const int *__restrict__ seg_cnt,
+                                                             const unsigned int *__restrict__ pair_primer, const int *__restrict__ pair_score,
+                                                             idp_result *__restrict__ out, Counters *__restrict__ ctr_out, int three_prime) {
+    const unsigned n_work = n_work_ptr ? *n_work_ptr : n_work_fixed;
+    unsigned long long aligned = 0;
+    for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
+        const int cnt = seg_cnt[w];
+        if (cnt < 0) continue;  // -1: did not fit (reported through Counters::overflow); -2: handled by the all-primers path
+        const int r = work_read ? (int)work_read[w] : (int)w;
+        Fin f;
+        f.count = cnt; f.primer = -1; f.raw = 0; f.raw_next = 0; f.qlen = 0; f.qlen_next = 0;
+        if (cnt > 0) {
+            GBest2 g;
+            bool missing = false;
+            const unsigned o = seg_off[w];
+            for (int j = 0; j < cnt; ++j) {
+                const int p = (int)pair_primer[o + j], sc = pair_score[o + j];
+                if (sc == kScoreMissing) missing = true;
+                g.offer(j, p, sc, __ldg(&P.pinfo[p]).w);
+            }
+            f.primer = g.b_primer; f.raw = missing ? kScoreMissing : g.b_score; f.qlen = (int16_t)g.b_qlen;
+            f.raw_next = g.s_ord >= 0 ? g.s_score : 0; f.qlen_next = (int16_t)(g.s_ord >= 0 ? g.s_qlen : 0);
+            aligned += (unsigned)cnt;
+        }
+        finish_gapped<TN>(P, R, r, f, three_prime != 0, out);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) aligned += __shfl_xor_sync(0xffffffffu, aligned, d);
+    if ((threadIdx.x & 31) == 0 && aligned) atomicAdd(three_prime ? &ctr_out->n_align3 : &ctr_out->n_align5, aligned);
+}
+
+// all-primers mode: sw_all_kernel left one Fin per work item
+template <int TN>
+__global__ void __launch_bounds__(128) finalize_all_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
+                                                           const unsigned int *__restrict__ n_work_ptr, const Fin *__restrict__ fin,
+                                                           idp_result *__restrict__ out, int three_prime) {
+    const unsigned n_work = *n_work_ptr;
+    for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x)
+        finish_gapped<TN>(P, R, (int)work_read[w], fin[w], three_prime != 0, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TemplateTypeMetric counter (IP:413; TemplateType.scala:52-63): one thread per read, R1 of each template counts
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) metrics_kernel(DevReads R, const idp_result *__restrict__ five, Counters *__restrict__ ctr) {
+    __shared__ unsigned int hist[160];
+    for (int i = threadIdx.x; i < 160; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R.n; r += gridDim.x * blockDim.x) {
+        const uint16_t fl = R.flags[r];
+        if (r > 0 && (R.flags[r - 1] & IDP_F_MATE_NEXT)) continue;  // this read is an R2
+        const bool has_r2 = (fl & IDP_F_MATE_NEXT) && r + 1 < R.n;
+        const bool m1 = !(fl & IDP_F_UNMAPPED);
+        int tt, t2 = IDP_NONE;
+        if (!has_r2) tt = m1 ? 3 : 4;
+        else {
+            const bool m2 = !(R.flags[r + 1] & IDP_F_UNMAPPED);
+            tt = (m1 && m2) ? 0 : (m1 != m2 ? 1 : 2);
+            t2 = five[r + 1].type;
+        }
+        const int bin = ((tt * 2 + ((fl & IDP_F_FR_PAIR) ? 1 : 0)) * 4 + five[r].type) * 4 + t2;
+        atomicAdd(&hist[bin], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 160; i += blockDim.x) if (hist[i]) atomicAdd(&ctr->metrics[i], (unsigned long long)hist[i]);
+}
+
+}  // namespace idp

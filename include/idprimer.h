@@ -1,0 +1,200 @@
+/*
+ * idprimer.h -- C-ABI of the B200-native IdentifyPrimers matching path (libidprimer_b200.so).
+ *
+ * This is the drop-in boundary for fg-idprimer's Location -> Ungapped -> Gapped matcher chain.  One
+ * idp_match_batch() call replaces one IdentifyPrimers.processBatch() (IdentifyPrimers.scala:381-436):
+ * it runs toPrimeMatchFuture (IP:441-452) for every read, matchThreePrime (IP:483-516) when enabled,
+ * and accumulates the TemplateTypeMetric counter (IP:413, 425-426).  Plain pointers and sizes only; no
+ * exceptions cross the boundary; errors are a non-zero return plus idp_last_error().
+ *
+ * Citations: IP = src/main/scala/com/fulcrumgenomics/identifyprimers/IdentifyPrimers.scala,
+ * PM = .../PrimerMatcher.scala, PMa = .../PrimerMatch.scala, PR = .../Primer.scala,
+ * AA = src/main/scala/com/fulcrumgenomics/alignment/AsyncAligner.scala (all under /root/reference).
+ *
+ * There is no CPU fallback: every matching entry point fails with IDP_ERR_CUDA when no sm_100 device
+ * is usable.  idp_panel_create() and the idp_panel_* / idp_format_* helpers are pure host code.
+ */
+#ifndef IDPRIMER_H
+#define IDPRIMER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDP_ABI_VERSION 1
+
+/* ---- return codes ---- */
+#define IDP_OK               0
+#define IDP_ERR_ARG          1   /* NULL / out-of-range argument                                  */
+#define IDP_ERR_UNSUPPORTED  2   /* input the GPU path does not cover (see idp_last_error())      */
+#define IDP_ERR_CUDA         3   /* CUDA failure or no usable device                              */
+#define IDP_ERR_NOMEM        4
+
+/* ---- read flags: the SAM flag bits the path consults + two host-derived bits ---- */
+#define IDP_F_PAIRED     0x0001  /* rec.paired                       (PMa:84)                      */
+#define IDP_F_UNMAPPED   0x0004  /* rec.unmapped                     (PM:41, PM:194)               */
+#define IDP_F_REVERSE    0x0010  /* rec.negativeStrand               (PM:41, PM:179)               */
+#define IDP_F_FIRST      0x0040  /* rec.firstOfPair                  (PMa:84)                      */
+#define IDP_F_SECOND     0x0080
+#define IDP_F_FR_PAIR    0x1000  /* fgbio SamRecord.isFrPair of R1, computed by the host (IP:413)  */
+#define IDP_F_MATE_NEXT  0x2000  /* this read is R1 of a template and the next read is its R2.
+                                    Must not be set on an R2.  Reads of one template are adjacent. */
+
+/* ---- match types (PMa:33-37) and per-read status ---- */
+#define IDP_NONE      0
+#define IDP_LOCATION  1   /* LocationBasedPrimerMatch      (PMa:96)  */
+#define IDP_UNGAPPED  2   /* UngappedAlignmentPrimerMatch  (PMa:101) */
+#define IDP_GAPPED    3   /* GappedAlignmentPrimerMatch    (PMa:111) */
+
+#define IDP_STATUS_OK                  0
+#define IDP_STATUS_REQ_MM_LE_NEXT      1  /* require(numMismatches <= nextNumMismatches) would throw (PMa:102) */
+#define IDP_STATUS_REQ_SCORE_GE_SECOND 2  /* require(score >= secondBestScore) would throw           (PMa:113) */
+#define IDP_STATUS_REQ_START_LE_END    3  /* require(start <= end) would throw                       (PMa:114) */
+#define IDP_STATUS_SCORE_MISSING       4  /* scoring matrix has no entry for a base pair (IP:277 NoSuchElementException) */
+
+#define IDP_NEXT_NA 2147483647            /* Int.MaxValue, rendered "na" (PMa:104) */
+
+/* alignment modes of fgbio's Aligner, numbered like the ksw mapping at AA:124-128 */
+#define IDP_MODE_LOCAL  0
+#define IDP_MODE_GLOCAL 1
+#define IDP_MODE_GLOBAL 3
+
+/* ---- option surface of the tool that reaches the hot path (IP:170-185) ---- */
+typedef struct {
+    int32_t slop;                 /* -S, default 5                                               */
+    int32_t three_prime;          /* -3, default -1 (3' matching off)                            */
+    int32_t match_score;          /* --match-score 1                                             */
+    int32_t mismatch_score;       /* --mismatch-score -4                                         */
+    int32_t gap_open;             /* --gap-open -6                                               */
+    int32_t gap_extend;           /* --gap-extend -1                                             */
+    int32_t k_ungapped;           /* -k; <= 0 means None                                         */
+    int32_t k_gapped;             /* -K; <= 0 means None                                         */
+    double  max_mismatch_rate;    /* --max-mismatch-rate 0.05                                    */
+    double  min_alignment_score_rate; /* --min-alignment-score-rate 0.01                         */
+    const int32_t *score_matrix;  /* --scoring-matrix: NULL, or int32[128*128] indexed
+                                     [primer_base*128 + read_base], INT32_MIN = no entry (IP:252-278) */
+} idp_params;
+
+/* one row of the primer TSV, already parsed and upper-cased by the host (PR:54-112, PR:182-188) */
+typedef struct {
+    const char *pair_id;
+    const char *primer_id;
+    const char *sequence;         /* sequencing order, upper case, A/C/G/T/IUPAC/'.'              */
+    const char *ref_name;         /* "" (or NULL) = unmapped primer                                */
+    int32_t ref_idx;              /* index of ref_name in the reads' sequence dictionary; <0 if absent */
+    int32_t start, end;           /* 1-based inclusive; Primer.length = end-start+1 when mapped (PR:206) */
+    uint8_t positive_strand;
+} idp_primer;
+
+/* a batch of reads, structure of arrays, template by template (R1 then R2) */
+typedef struct {
+    const uint8_t  *seq4;             /* BAM-native 4-bit bases (=ACMGRSVTWYHKDBN -> 0..15), first base in the
+                                         high nibble, each read starting on a byte boundary                  */
+    const uint64_t *seq_off;          /* [n] byte offset of each read in seq4; NULL when fixed_len > 0        */
+    const int32_t  *len;              /* [n] read length in bases;             NULL when fixed_len > 0        */
+    const int32_t  *ref_idx;          /* [n] reference index (-1 unmapped);    NULL if no read is mapped      */
+    const int32_t  *unclipped_start;  /* [n] rec.unclippedStart (PM:180);      NULL if no read is mapped      */
+    const int32_t  *unclipped_end;    /* [n] rec.unclippedEnd   (PM:186);      NULL if no read is mapped      */
+    const uint16_t *flags;            /* [n] IDP_F_* bits                                                     */
+    int32_t fixed_len;                /* >0: every read has this length and occupies (fixed_len+1)/2 bytes    */
+} idp_reads;
+
+/* one PrimerMatch (PMa:96-117) as integers; the JVM-side doubles are derived with idp_result_score() */
+typedef struct {
+    int32_t primer;       /* index into the panel; -1 = no match                                              */
+    uint8_t type;         /* IDP_NONE / LOCATION / UNGAPPED / GAPPED                                          */
+    uint8_t status;       /* IDP_STATUS_*: non-zero where the reference would have thrown                     */
+    uint8_t multi;        /* gapped: 1 if two or more candidates were aligned (PM:317 vs PM:313)              */
+    uint8_t reserved;
+    int32_t mm;           /* location / ungapped: numMismatches                                               */
+    int32_t next_mm;      /* ungapped: nextNumMismatches or IDP_NEXT_NA                                       */
+    int32_t raw_score;    /* gapped: Alignment.score of the best candidate                                    */
+    int32_t raw_next;     /* gapped: Alignment.score of the runner-up (0 when !multi)                         */
+    int16_t q_len;        /* gapped: alignment.query.length of the best candidate (PM:301)                    */
+    int16_t q_len_next;   /* gapped: same for the runner-up (0 when !multi)                                   */
+    int16_t t_start;      /* gapped: Alignment.targetStart, 1-based (PM:315, 323)                             */
+    int16_t t_end;        /* gapped: Alignment.targetEnd                                                      */
+} idp_result;             /* 32 bytes */
+
+/* device-side timing and work counters of the last idp_match_batch*() call on a context */
+typedef struct {
+    float    ms_total;            /* first H2D/kernel to last D2H/kernel, CUDA events                          */
+    float    ms_scan;             /* kernel A+B: k-mer prefilter + location + ungapped scan                    */
+    float    ms_gapped;           /* candidate emission + Smith-Waterman score + finalize + traceback (5')     */
+    float    ms_three_prime;      /* the same for the 3' pass                                                  */
+    float    ms_sw_score;         /* the score-only Smith-Waterman kernel alone (5' + 3')                      */
+    int64_t  n_reads;
+    int64_t  n_fallthrough;       /* reads that reached the gapped stage                                       */
+    int64_t  n_alignments_5p;     /* gapped alignments, 5' (== the reference's numAlignments, IP:424)          */
+    int64_t  n_alignments_3p;
+    int64_t  sw_cells;            /* sum over alignments of |query| * |target|                                 */
+    int64_t  scan_base_compares;  /* sum over (read, candidate) of min(readLen, primer bytes)                  */
+    int64_t  kernel_launches;     /* kernels of this library launched by the call                              */
+    int64_t  h2d_bytes, d2h_bytes;
+} idp_timings;
+
+typedef struct idp_panel idp_panel;  /* immutable after create; shareable across threads and devices           */
+typedef struct idp_ctx   idp_ctx;    /* one per calling thread and device: streams, staging, scratch           */
+
+/* ---- library ---- */
+int         idp_abi_version(void);
+const char *idp_last_error(void);                       /* thread-local message of the last failing call     */
+int         idp_device_count(void);                     /* number of usable CUDA devices (0 if none)         */
+
+/* ---- panel: the three matchers' immutable state (IP:223-234; PM:62-117, 156-175) ---- */
+int  idp_panel_create(const idp_primer *primers, int32_t n, const idp_params *params, idp_panel **out);
+void idp_panel_destroy(idp_panel *panel);
+int32_t  idp_panel_size(const idp_panel *panel);
+int32_t  idp_panel_primer_length(const idp_panel *panel, int32_t i);          /* Primer.length (PR:206)       */
+uint32_t idp_panel_primer_hash(const idp_panel *panel, int32_t i);            /* Scala case-class hashCode    */
+/* kmerToPrimers(kmer) in the iteration order the reference's Set has (PM:78-91, 113); which: 0 = -k, 1 = -K  */
+int32_t  idp_panel_kmer_postings(const idp_panel *panel, int which, const char *kmer, int32_t *out, int32_t cap);
+
+/* ---- context ---- */
+int  idp_ctx_create(const idp_panel *panel, int device, idp_ctx **out);
+void idp_ctx_destroy(idp_ctx *ctx);
+/* run on the caller's CUDA stream (a cudaStream_t passed as void*); NULL = the context's own stream */
+int  idp_ctx_set_stream(idp_ctx *ctx, void *cuda_stream);
+int  idp_ctx_timings(const idp_ctx *ctx, idp_timings *out);
+
+/* pinned host memory for batches that are copied asynchronously (plain malloc'd buffers also work, slower) */
+void *idp_host_alloc(size_t bytes);
+void  idp_host_free(void *p);
+
+/* ---- the hot path ----
+ * processBatch (IP:381-436).  five[n] receives each read's 5' match, three[n] its 3' match (may be NULL when
+ * params.three_prime < 0).  metrics160 (may be NULL) is ADDED to: bin = ((template_type*2 + is_fr)*4 + r1_type)*4
+ * + r2_type with template_type in the order of TemplateType.scala:38-46.  *n_gapped_alignments (may be NULL) is
+ * ADDED to and equals the reference's numAlignments increment (5' alignments only, IP:424).
+ * All read arrays and result arrays are HOST pointers; copies are pipelined with compute. */
+int idp_match_batch(idp_ctx *ctx, const idp_reads *reads, int32_t n_reads, idp_result *five, idp_result *three,
+                    int64_t *metrics160, int64_t *n_gapped_alignments);
+/* Same, but every pointer inside `reads`, and `five`/`three`, are DEVICE pointers on the context's device
+ * (metrics160 / n_gapped_alignments stay host pointers).  No host<->device copy of reads or results happens. */
+int idp_match_batch_device(idp_ctx *ctx, const idp_reads *reads, int32_t n_reads, idp_result *five, idp_result *three,
+                           int64_t *metrics160, int64_t *n_gapped_alignments);
+
+/* ---- the aligner seam: a batched AsyncAligner.align (AA:37-54) ----
+ * queries/targets are ASCII, concatenated, with n+1 offsets; outputs are Alignment.score, targetStart and
+ * targetEnd (1-based).  mode is IDP_MODE_*; scoring comes from the context's panel parameters. */
+int idp_align_batch(idp_ctx *ctx, int mode, const char *queries, const int64_t *q_off, const char *targets,
+                    const int64_t *t_off, int32_t n, int32_t *score, int32_t *target_start, int32_t *target_end);
+
+/* ---- host-side result helpers (pure functions, same IEEE double operations as the JVM) ---- */
+double idp_result_score(const idp_result *r);        /* GappedAlignmentPrimerMatch.score        (PM:315, 321) */
+double idp_result_second(const idp_result *r);       /* GappedAlignmentPrimerMatch.secondBestScore (PM:315, 322) */
+int    idp_metric_bin(int template_type, int is_fr, int r1_type, int r2_type);
+void   idp_summary_metrics(const int64_t *metrics160, int64_t *out17);  /* IdentifyPrimersMetric.scala:34-89 */
+/* PrimerMatch.info(rec) (PMa:78-88), "none" for no match (IP:242); returns the string length */
+int    idp_format_info(const idp_panel *panel, const idp_result *r, uint16_t read_flags, char *buf, int32_t cap);
+/* pack ASCII bases to BAM nibbles / back (htsjdk SAMUtils.bytesToCompressedBases semantics) */
+void   idp_pack_bases(const char *ascii, int32_t n, uint8_t *seq4);
+void   idp_unpack_bases(const uint8_t *seq4, int32_t n, char *ascii);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDPRIMER_H */

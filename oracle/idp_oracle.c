@@ -586,7 +586,7 @@ static void gapped_over(const orc_panel *p, int mode, const int *cand, int nc, c
     }
     orc_best_gapped(cand, s->scores, s->qlens, s->ts, s->te, nc, out);
     finalize_gapped(p, out);
-    if (missing) out->status = ORC_ERR_SCORE_MISSING;
+    if (missing) { memset(out, 0, sizeof *out); out->primer = -1; out->status = ORC_ERR_SCORE_MISSING; } /* the JVM throws NoSuchElementException (IP:277) */
 }
 
 static void five_prime_match(const orc_panel *p, const orc_reads *rd, int r, scratch *s, orc_result *out, int64_t *n_align) {

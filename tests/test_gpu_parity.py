@@ -1,0 +1,314 @@
+"""GPU parity: the CUDA path (through the C-ABI, host buffers) against the CPU oracle on the same inputs, bit-exact on
+every result field, the 160-bin metric counter and the alignment count; plus the reference's own known-answer numbers."""
+import numpy as np
+import pytest
+
+import helpers as H
+import fg_idprimer_b200 as idp
+from fg_idprimer_b200 import _lib as L
+from fg_idprimer_b200 import synth
+from oracle import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+K = H.kats()
+FIELDS = ["primer", "type", "status", "multi", "mm", "next_mm", "raw_score", "raw_next", "q_len", "q_len_next", "t_start", "t_end"]
+
+
+def _opts_to_oracle(opts):
+    return O.make_params(slop=opts.get("slop", 5), three_prime=opts.get("three_prime", -1),
+                         max_mismatch_rate=opts.get("max_mismatch_rate", 0.05),
+                         min_alignment_score_rate=opts.get("min_alignment_score_rate", 0.01), match_score=opts.get("match_score", 1),
+                         mismatch_score=opts.get("mismatch_score", -4), gap_open=opts.get("gap_open", -6), gap_extend=opts.get("gap_extend", -1),
+                         k_ungapped=opts.get("ungapped_kmer_length"), k_gapped=opts.get("gapped_kmer_length"),
+                         score_matrix=opts.get("scoring_matrix"))
+
+
+def assert_same(got, want, what=""):
+    for f in FIELDS:
+        if not np.array_equal(got[f], want[f]):
+            bad = np.nonzero(got[f] != want[f])[0]
+            i = int(bad[0])
+            raise AssertionError(f"{what}: field {f} differs at {len(bad)} reads, first read {i}: gpu={got[i]} oracle={want[i]}")
+
+
+def run_both(primers, arrays, ref_names=H.DEFAULT_DICT, oracle_threads=8, **opts):
+    """primers: helpers.Primer list; arrays: oracle-style dict (ASCII bases + offsets)."""
+    gp = [idp.Primer(p.pair_id, p.primer_id, p.sequence, p.positive_strand, p.ref_name, p.start, p.end) for p in primers]
+    name_to_idx = {n: i for i, n in enumerate(ref_names)}
+    for p in primers:
+        if p.ref_name and p.ref_idx in (-1, None):
+            p.ref_idx = name_to_idx.get(p.ref_name, -2)
+    panel = O.Panel(primers, _opts_to_oracle(opts))
+    want5, want3, want_metrics, want_align = panel.process_batch(arrays, n_threads=oracle_threads)
+    with idp.IdentifyPrimers(gp, ref_names=ref_names, **opts) as tool:
+        batch = idp.ReadBatch.from_ascii(arrays["bases"], arrays["off"], arrays["flags"], arrays["ref_idx"], arrays["ustart"], arrays["uend"])
+        got5, got3 = tool.process_batch(batch)
+        assert_same(got5, want5, "5'")
+        if opts.get("three_prime", -1) >= 0:
+            assert_same(got3, want3, "3'")
+        assert np.array_equal(tool.metric_counter, want_metrics)
+        assert tool.num_alignments == want_align
+        t = tool.timings()
+        assert t["kernel_launches"] > 0
+        return got5, got3, tool.summary(), t
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the reference's own end-to-end known answers, through the GPU
+# ------------------------------------------------------------------------------------------------------------------
+def _ipt_opts():
+    p = K["ipt_params"]
+    return dict(slop=p["slop"], max_mismatch_rate=p["max_mismatches"] / p["primer_length"], min_alignment_score_rate=0.0,
+                match_score=p["match_score"], mismatch_score=p["mismatch_score"], gap_open=p["gap_open"], gap_extend=p["gap_extend"])
+
+
+@pytest.mark.parametrize("primers_mapped", [True, False])
+@pytest.mark.parametrize("reads_mapped", [True, False])
+def test_ipt_metrics_on_gpu(primers_mapped, reads_mapped):  # IdentifyPrimersTest.scala:299-403
+    primers = H.primers_from(K["ipt_panel"], mapped=primers_mapped)
+    recs = H.ipt_metrics_reads(H.primers_from(K["ipt_panel"], mapped=True))
+    if not reads_mapped:
+        recs = H.make_unmapped(recs)
+    _, _, summary, _ = run_both(primers, H.recs_to_arrays(recs), **_ipt_opts())
+    exp = dict(K["ipt_metrics"]["common"])
+    for k, v in list(exp.items()):
+        if isinstance(v, dict):
+            exp[k] = v["mapped" if reads_mapped else "unmapped"]
+    exp.update(K["ipt_metrics"]["mapped_primers_mapped_reads" if (primers_mapped and reads_mapped) else "otherwise"])
+    assert summary == exp
+
+
+def test_ipt_two_pairs_per_read_on_gpu():  # IdentifyPrimersTest.scala:238-297
+    primers = H.primers_from(K["ipt_panel_two_pairs"])
+    recs = H.pair_records(H.build_builder(primers))
+    gp = [idp.Primer(p.pair_id, p.primer_id, p.sequence, p.positive_strand, p.ref_name, p.start, p.end) for p in primers]
+    arrays = H.recs_to_arrays(recs)
+    run_both(primers, arrays, **_ipt_opts())
+    with idp.IdentifyPrimers(gp, ref_names=H.DEFAULT_DICT, **_ipt_opts()) as tool:
+        five, _ = tool.process_batch(idp.ReadBatch.from_ascii(arrays["bases"], arrays["off"], arrays["flags"], arrays["ref_idx"], arrays["ustart"], arrays["uend"]))
+        exp = K["ipt_per_read"]
+        for i in range(0, len(recs), 2):
+            tags = tool.pair_tags(recs[i].flags, recs[i + 1].flags, five[i], five[i + 1])
+            for rec in (recs[i], recs[i + 1]):
+                info = tags["f5"] if not rec.negative else tags["r5"]
+                got = info.split(",")[5] if "," in info else info
+                et = rec.tags.get("et")
+                if et is None:
+                    want = "none"
+                elif et == "no_edits":
+                    want = exp["no_edits"]
+                else:
+                    kind, n = et.split("_"); n = int(n)
+                    want = {"mis": "Ungapped" if n < exp["mis_lt"] else "none", "ins": "Gapped" if n < exp["ins_lt"] else "none",
+                            "del": "Gapped" if n <= exp["del_le"] else "none"}[kind]
+                assert got == want, (et, rec.bases, info)
+
+
+def test_pmt_panel_location_and_ungapped_on_gpu():  # PrimerMatcherTest.scala:236-374
+    primers = H.primers_from(K["pmt_panel"])
+    recs = []
+    for adjust in (0, 5, 6):
+        for p in primers:
+            start = p.start if p.positive_strand else p.end - 20 + 1
+            genomic = p.sequence if p.positive_strand else H.revcomp(p.sequence)
+            bases = genomic + "N" * 10 if p.positive_strand else "N" * 10 + genomic
+            recs.append(H.Rec(bases, False, not p.positive_strand, p.ref_idx, start + adjust))
+            recs.append(H.Rec(H.Rec(bases, False, not p.positive_strand).seq_order, True, False))
+    for rate in (0.0, 0.1, 1.0):
+        for k in (None, 5):
+            run_both(primers, H.recs_to_arrays(recs), slop=5, max_mismatch_rate=rate, ungapped_kmer_length=k, gapped_kmer_length=k)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# synthetic workloads of BASELINE.md at oracle-sized N
+# ------------------------------------------------------------------------------------------------------------------
+def _synth_primers(panel):
+    ref = {n: i for i, n in enumerate(panel.ref_names)}
+    return [H.Primer(p.pair_id, p.primer_id, p.sequence, p.positive_strand, p.ref_name, p.start, p.end, ref.get(p.ref_name, -1)) for p in panel.primers]
+
+
+@pytest.mark.parametrize("name,n_pairs", [("c1", 20000), ("c2", 20000), ("c3", 6000), ("c3b", 400), ("c4", 1500), ("c5", 3000)])
+def test_synthetic_workloads(name, n_pairs):
+    panel, reads, opts = synth.workload(name, n_pairs)
+    got5, got3, summary, t = run_both(_synth_primers(panel), reads.oracle_arrays(), ref_names=panel.ref_names, **opts)
+    assert summary["templates"] == n_pairs
+    assert (got5["type"] != 0).mean() > 0.9
+    if name == "c5":
+        assert summary["location"] > 0 and (got3["type"] == L.GAPPED).any()
+    if name == "c3b":
+        assert t["n_alignments_5p"] == t["n_fallthrough"] * len(panel.primers)
+
+
+def test_no_kmer_filters_and_unusual_options():
+    panel, reads, _ = synth.workload("c3", 1500)
+    prs = _synth_primers(panel)[:120]
+    arrays = reads.oracle_arrays()
+    run_both(prs, arrays, ref_names=panel.ref_names)                                            # all defaults (IP:170-183)
+    run_both(prs, arrays, ref_names=panel.ref_names, slop=0, max_mismatch_rate=0.2, ungapped_kmer_length=4, gapped_kmer_length=5)
+    run_both(prs, arrays, ref_names=panel.ref_names, slop=12, match_score=2, mismatch_score=-1, gap_open=-2, gap_extend=-2,
+             min_alignment_score_rate=0.5, gapped_kmer_length=8)
+    run_both(prs, arrays, ref_names=panel.ref_names, gap_open=0, gap_extend=0, mismatch_score=0, match_score=0, gapped_kmer_length=12)
+    run_both(prs, arrays, ref_names=panel.ref_names, three_prime=0, gapped_kmer_length=10, ungapped_kmer_length=6)
+
+
+def test_ties_near_duplicate_primers():
+    """Candidate order decides ties (PM:241, PM:309): near-duplicate primers, with and without the k-mer filters."""
+    rng = np.random.default_rng(11)
+    base = "ACGTTGCAAGGCTTACGATCGGA"
+    primers = []
+    for i in range(24):
+        s = list(base)
+        for j in rng.choice(len(base), size=i % 3, replace=False):
+            s[j] = "ACGT"[(("ACGT".index(s[j])) + 1) % 4]
+        seq = "".join(s)[: 18 + i % 6]
+        primers.append(H.Primer(f"p{i}", f"p{i}+", seq, True))
+        primers.append(H.Primer(f"p{i}", f"p{i}-", H.revcomp(seq)[: 18 + (i * 5) % 6], False))
+    recs = []
+    for i in range(600):
+        p = primers[int(rng.integers(0, len(primers)))]
+        s = list(p.sequence + "".join("ACGT"[x] for x in rng.integers(0, 4, 30)))
+        for j in rng.choice(20, size=int(rng.integers(0, 4)), replace=False):
+            s[j] = "ACGTN"[int(rng.integers(0, 5))]
+        if rng.random() < 0.3:
+            del s[int(rng.integers(2, 15))]
+        r = H.Rec("".join(s), True, False, paired=False)
+        recs.append(r)
+    arrays = H.recs_to_arrays(recs)
+    for k, kk in [(None, None), (4, 4), (6, 8), (3, 3)]:
+        run_both(primers, arrays, max_mismatch_rate=0.15, ungapped_kmer_length=k, gapped_kmer_length=kk, min_alignment_score_rate=0.0)
+        run_both(primers, arrays, max_mismatch_rate=0.15, ungapped_kmer_length=k, gapped_kmer_length=kk, three_prime=3, mismatch_score=-2)
+
+
+def test_ragged_short_empty_and_iupac_reads():
+    primers = H.primers_from(K["pmt_panel"]) + [H.Primer("7", "7+", "ACGTRYACGTNACGTMKACG", True), H.Primer("7", "7-", "TTGACCAGTWSGATTACA", False)]
+    rng = np.random.default_rng(5)
+    recs = [H.Rec("", True, False), H.Rec("A", True, False), H.Rec("ACGT", True, False), H.Rec("N" * 30, True, False),
+            H.Rec("=" * 12, True, False), H.Rec("ACGTAYACGTGACGTAGACG" + "RYKM=NBDHV", True, False)]
+    for _ in range(400):
+        n = int(rng.integers(0, 60))
+        alphabet = "ACGT" * 6 + "NRYKMSWBDHV="
+        s = "".join(alphabet[int(x)] for x in rng.integers(0, len(alphabet), n))
+        if rng.random() < 0.5 and n > 12:
+            p = primers[int(rng.integers(0, len(primers)))]
+            s = (p.sequence + s)[:n]
+        mapped = rng.random() < 0.4
+        neg = bool(rng.random() < 0.5)
+        stored = H.revcomp(s) if (mapped and neg) else s
+        recs.append(H.Rec(stored, not mapped, neg, ref_idx=int(rng.integers(0, 4)), start=int(rng.integers(-3, 1100))))
+    # pair some of them up, leave the rest as fragments
+    paired = H.pair_records(recs[:200]) + recs[200:]
+    arrays = H.recs_to_arrays(paired)
+    for opts in [dict(), dict(ungapped_kmer_length=5, gapped_kmer_length=5), dict(max_mismatch_rate=0.3, slop=3, three_prime=2),
+                 dict(max_mismatch_rate=1.0, min_alignment_score_rate=0.0, ungapped_kmer_length=2)]:
+        run_both(primers, arrays, **opts)
+
+
+def test_long_primers_use_wider_kernels():
+    rng = np.random.default_rng(9)
+    for plen in (40, 64, 100, 200):
+        primers = []
+        for i in range(6):
+            s = "".join("ACGT"[x] for x in rng.integers(0, 4, plen - i))
+            primers.append(H.Primer(f"p{i}", f"p{i}+", s, True))
+            primers.append(H.Primer(f"p{i}", f"p{i}-", "".join("ACGT"[x] for x in rng.integers(0, 4, plen // 2 + i)), False))
+        recs = []
+        for i in range(120):
+            p = primers[int(rng.integers(0, len(primers)))]
+            s = list(p.sequence + "".join("ACGT"[x] for x in rng.integers(0, 4, 60)))
+            if i % 3 == 0:
+                del s[plen // 3]
+            if i % 3 == 1:
+                s.insert(plen // 4, "G")
+            if i % 5 == 0:
+                s[3] = "N"
+            recs.append(H.Rec("".join(s)[: 250], True, False))
+        arrays = H.recs_to_arrays(recs)
+        run_both(primers, arrays, max_mismatch_rate=0.05, gapped_kmer_length=10, ungapped_kmer_length=8)
+        run_both(primers, arrays, max_mismatch_rate=0.05, three_prime=0)
+
+
+def test_scoring_matrix():
+    sm = np.full((128, 128), np.iinfo(np.int32).min, dtype=np.int32)
+    for a in "ACGT":
+        for b in "ACGTN":
+            sm[ord(a), ord(b)] = 2 if a == b else (-1 if b == "N" else -3)
+    for a, members in {"R": "AG", "Y": "CT", "N": "ACGT"}.items():
+        for b in "ACGT":
+            sm[ord(a), ord(b)] = 1 if b in members else -3
+    primers = [H.Primer("1", "1+", "ACGTRYACGTNACGTACGAT", True), H.Primer("1", "1-", "TTGACCAGTAGGATTACA", False),
+               H.Primer("2", "2+", "GGATCCRYTTAAGCCGTA", True), H.Primer("2", "2-", "CCATGGTTAACCGGTTAA", False)]
+    rng = np.random.default_rng(2)
+    recs = []
+    for i in range(300):
+        p = primers[i % 4]
+        s = list(p.sequence.replace("R", "A").replace("Y", "C").replace("N", "G") + "".join("ACGT"[x] for x in rng.integers(0, 4, 40)))
+        if i % 2:
+            del s[5 + i % 7]
+        if i % 7 == 0:
+            s[8] = "N"
+        if i % 50 == 0:
+            s[9] = "K"   # a read base the matrix has no entry for -> the reference would throw (status 4)
+        recs.append(H.Rec("".join(s), True, False))
+    got5, _, _, _ = run_both(primers, H.recs_to_arrays(recs), scoring_matrix=sm, gap_open=-4, gap_extend=-1, min_alignment_score_rate=0.1)
+    assert (got5["status"] == 4).any() and (got5["type"] == L.GAPPED).any()
+
+
+def test_align_batch_matches_oracle_aligner():  # AsyncAlignerTest.scala:33-57, all three modes
+    rng = np.random.default_rng(4)
+    queries, targets = [], []
+    for i in range(500):
+        n, m = int(rng.integers(1, 40)), int(rng.integers(0, 80))
+        q = "".join("ACGT"[x] for x in rng.integers(0, 4, n))
+        t = "".join("ACGT"[x] for x in rng.integers(0, 4, m))
+        if i % 2 and m > n:
+            pos = int(rng.integers(0, m - n + 1))
+            qq = list(q)
+            if n > 4 and i % 4 == 1:
+                del qq[n // 2]
+            t = t[:pos] + "".join(qq) + t[pos + len(qq):]
+        queries.append(q.encode()); targets.append(t.encode())
+    queries += [b"ACGTG", b"AATCGATA", b"GATTACA"]; targets += [b"ACGTG", b"AATGATA", b"TTTGATTACATTT"]
+    for scores in [dict(match_score=1, mismatch_score=-4, gap_open=-6, gap_extend=-1), dict(match_score=2, mismatch_score=-1, gap_open=-1, gap_extend=-1),
+                   dict(match_score=1, mismatch_score=-3, gap_open=0, gap_extend=-2)]:
+        params = O.make_params(**scores)
+        for mode in (L.MODE_LOCAL, L.MODE_GLOCAL, L.MODE_GLOBAL):
+            al = idp.AsyncCudaAligner(mode=mode, **scores)
+            score, ts, te = al.align(queries, targets)
+            al.close()
+            for i, (q, t) in enumerate(zip(queries, targets)):
+                a = O.align(params, mode, q, t)
+                assert (int(score[i]), int(ts[i]), int(te[i])) == (a["score"], a["target_start"], a["target_end"]), (mode, scores, q, t, a)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# size-independent properties at a size the oracle could not finish quickly
+# ------------------------------------------------------------------------------------------------------------------
+def test_large_batch_properties():
+    n_pairs = 1_000_000
+    panel, reads, opts = synth.workload("c2", n_pairs)
+    gp = panel.primers
+    seq4 = reads.seq4()
+    with idp.IdentifyPrimers(gp, **opts) as tool:
+        batch = idp.ReadBatch(seq4.reshape(-1), reads.flags, fixed_len=150)
+        five, _ = tool.process_batch(batch)
+        m1 = tool.metric_counter.copy()
+        assert tool.summary()["templates"] == n_pairs and tool.summary()["match_attempts"] == 2 * n_pairs
+        # idempotence and chunk-size independence
+        import os
+        os.environ["IDP_CHUNK_READS"] = "77777"
+        five_b, _ = tool.process_batch(batch)
+        del os.environ["IDP_CHUNK_READS"]
+        assert np.array_equal(five.view(np.uint8), five_b.view(np.uint8))
+        assert np.array_equal(tool.metric_counter, 2 * m1)
+        # permutation of templates permutes results
+        perm = np.random.default_rng(1).permutation(n_pairs)
+        ridx = np.stack([2 * perm, 2 * perm + 1], axis=1).reshape(-1)
+        five_p, _ = tool.process_batch(idp.ReadBatch(seq4[ridx].reshape(-1), reads.flags[ridx], fixed_len=150))
+        assert np.array_equal(five_p.view(np.uint8), five[ridx].view(np.uint8))
+        # matched primers belong to the amplicon the read was drawn from, a bounded prefix agrees with the oracle
+        hit = five["type"] != 0
+        assert (five["primer"][hit] // 2 == reads.truth[hit]).mean() > 0.999
+    lo, hi = 0, 40000
+    panel_o = O.Panel(_synth_primers(panel), _opts_to_oracle(opts))
+    want5, _, _, _ = panel_o.process_batch(reads.oracle_arrays(lo, hi), n_threads=8)
+    assert_same(five[lo:hi], want5, "prefix")
