@@ -60,6 +60,7 @@ struct Slot {
     bool busy = false;
     // chunk bookkeeping for the host-pointer path
     int64_t chunk_begin = 0, chunk_n = 0;
+    DevReads R{};
     long launches = 0;
 };
 
@@ -144,19 +145,19 @@ static void launch_scan(const idp_ctx *c, cudaStream_t st, const DevReads &R, id
 
 template <bool LOCAL, bool SMAT>
 static void launch_sw_pairs_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, const unsigned *work_read, Counters *ctr,
-                              const unsigned *pw, const unsigned *pp, int *ps) {
+                              const unsigned *pw, const unsigned *pp, int *ps, unsigned cap) {
     const int grid = c->sm_count * 8;
     switch (c->nq) {
-        case 32: sw_pairs_kernel<32, LOCAL, SMAT><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps); break;
-        case 64: sw_pairs_kernel<64, LOCAL, SMAT><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps); break;
-        default: sw_pairs_kernel<0, LOCAL, SMAT><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps); break;
+        case 32: sw_pairs_kernel<32, LOCAL, SMAT><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, cap); break;
+        case 64: sw_pairs_kernel<64, LOCAL, SMAT><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, cap); break;
+        default: sw_pairs_kernel<0, LOCAL, SMAT><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, cap); break;
     }
 }
 static void launch_sw_pairs(const idp_ctx *c, cudaStream_t st, bool local, const DevReads &R, const unsigned *work_read, Counters *ctr,
-                            const unsigned *pw, const unsigned *pp, int *ps) {
+                            const unsigned *pw, const unsigned *pp, int *ps, unsigned cap) {
     const bool smat = c->dp.smat != nullptr;
-    if (local) { if (smat) launch_sw_pairs_t<true, true>(c, st, R, work_read, ctr, pw, pp, ps); else launch_sw_pairs_t<true, false>(c, st, R, work_read, ctr, pw, pp, ps); }
-    else { if (smat) launch_sw_pairs_t<false, true>(c, st, R, work_read, ctr, pw, pp, ps); else launch_sw_pairs_t<false, false>(c, st, R, work_read, ctr, pw, pp, ps); }
+    if (local) { if (smat) launch_sw_pairs_t<true, true>(c, st, R, work_read, ctr, pw, pp, ps, cap); else launch_sw_pairs_t<true, false>(c, st, R, work_read, ctr, pw, pp, ps, cap); }
+    else { if (smat) launch_sw_pairs_t<false, true>(c, st, R, work_read, ctr, pw, pp, ps, cap); else launch_sw_pairs_t<false, false>(c, st, R, work_read, ctr, pw, pp, ps, cap); }
 }
 
 template <bool LOCAL, bool SMAT>
@@ -229,7 +230,7 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
             cand5_kernel<<<c->sm_count * 4, 256, smem, st>>>(c->dp, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(),
                                                             (unsigned)s.pair_cap, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>());
             CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st));
-            launch_sw_pairs(c, st, false, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>());
+            launch_sw_pairs(c, st, false, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), (unsigned)s.pair_cap);
             CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st));
             launch_finalize_pairs(c, st, R, fall, &ctr->n_fall, 0u, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(),
                                   s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), five, ctr, 0);
@@ -249,7 +250,7 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
         cand3_kernel<<<(R.n + 255) / 256, 256, 0, st>>>(c->dp, R, five, ctr, s.all_list.as<unsigned>(), s.pair_work.as<unsigned>(),
                                                        s.pair_primer.as<unsigned>(), (unsigned)s.pair_cap, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>());
         CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_A], st));
-        launch_sw_pairs(c, st, true, R, nullptr, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>());
+        launch_sw_pairs(c, st, true, R, nullptr, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), (unsigned)s.pair_cap);
         launch_sw_all(c, st, true, R, s.all_list.as<unsigned>(), &ctr->n_all, s.fin.as<Fin>(), ctr, 0);
         CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_B], st));
         launch_finalize_pairs(c, st, R, nullptr, nullptr, (unsigned)R.n, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(),
@@ -410,7 +411,15 @@ int idp_match_batch(idp_ctx *c, const idp_reads *reads, int32_t n_reads, idp_res
         if (!s.busy) return IDP_OK;
         CUDA_TRY(cudaStreamSynchronize(s.stream));
         s.busy = false;
-        if (s.h_ctr->overflow) { set_error("candidate pair buffer overflow in a chunk (raise IDP_CHUNK_READS granularity)"); return IDP_ERR_NOMEM; }
+        for (int attempt = 0; s.h_ctr->overflow; ++attempt) {  // rare: redo this chunk (still resident in the slot) with more room
+            if (attempt >= 6) { set_error("candidate pair buffer overflow persists after %d retries", attempt); return IDP_ERR_NOMEM; }
+            s.pair_cap *= 4;
+            int rc2 = enqueue_chain(c, s, s.stream, s.R, s.five.as<idp_result>(), do3 ? s.three.as<idp_result>() : nullptr);
+            if (rc2) return rc2;
+            CUDA_TRY(cudaMemcpyAsync(five + s.chunk_begin, s.five.p, s.chunk_n * sizeof(idp_result), cudaMemcpyDeviceToHost, s.stream));
+            if (do3) CUDA_TRY(cudaMemcpyAsync(three + s.chunk_begin, s.three.p, s.chunk_n * sizeof(idp_result), cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(cudaStreamSynchronize(s.stream));
+        }
         add_timings(c, s, first);
         first = false;
         for (int i = 0; i < 160; ++i) total_metrics[i] += (int64_t)s.h_ctr->metrics[i];
@@ -459,6 +468,7 @@ int idp_match_batch(idp_ctx *c, const idp_reads *reads, int32_t n_reads, idp_res
             R.ref_idx = s.ref_idx.as<int32_t>(); R.ustart = s.ustart.as<int32_t>(); R.uend = s.uend.as<int32_t>();
             c->last.h2d_bytes += cn * 12;
         }
+        s.R = R; s.chunk_begin = b; s.chunk_n = cn;
         if ((rc = enqueue_chain(c, s, st, R, s.five.as<idp_result>(), do3 ? s.three.as<idp_result>() : nullptr))) return rc;
         CUDA_TRY(cudaMemcpyAsync(five + b, s.five.p, cn * sizeof(idp_result), cudaMemcpyDeviceToHost, st));
         c->last.d2h_bytes += cn * (int64_t)sizeof(idp_result);

@@ -490,22 +490,29 @@ constexpr int32_t kScoreMissing = INT32_MIN;  // pair touched a base pair the sc
 template <int NQ, bool LOCAL, bool SMAT>
 __global__ void __launch_bounds__(128) sw_pairs_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
                                                        Counters *ctr, const unsigned int *__restrict__ pair_work,
-                                                       const unsigned int *__restrict__ pair_primer, int *__restrict__ pair_score) {
+                                                       const unsigned int *__restrict__ pair_primer, int *__restrict__ pair_score,
+                                                       unsigned int pair_cap) {
     __shared__ int32_t smat_s[256];
     if (SMAT) { for (int i = threadIdx.x; i < 256; i += blockDim.x) smat_s[i] = P.smat[i]; __syncthreads(); }
-    const unsigned n_pairs = ctr->n_pairs;
+    // after an overflow the counter runs past the buffer and slots below pair_cap may hold stale entries: clamp and
+    // range-check (the batch is redone with a larger buffer, nothing reads these scores)
+    const unsigned n_pairs = min(ctr->n_pairs, pair_cap);
+    const unsigned n_work = work_read ? ctr->n_fall : (unsigned)R.n;
     unsigned long long cells = 0;
     for (unsigned base = blockIdx.x * blockDim.x; base < n_pairs; base += gridDim.x * blockDim.x) {
         const unsigned t = base + threadIdx.x;
-        const bool active = t < n_pairs;
+        bool active = t < n_pairs;
         int n = 0, m = 0, p = 0;
         Oriented T{nullptr, 0, false};
         if (active) {
             const unsigned w = pair_work[t];
-            const int r = work_read ? (int)work_read[w] : (int)w;
             p = (int)pair_primer[t];
-            n = __ldg(&P.pinfo[p]).w;
-            T = make_target(P, R, r, n, LOCAL, m);
+            active = w < n_work && (unsigned)p < (unsigned)P.n_primers;
+            if (active) {
+                const int r = work_read ? (int)work_read[w] : (int)w;
+                n = __ldg(&P.pinfo[p]).w;
+                T = make_target(P, R, r, n, LOCAL, m);
+            }
         }
         const int n_warp_max = __reduce_max_sync(0xffffffffu, n);
         if (active) {

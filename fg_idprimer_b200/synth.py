@@ -153,14 +153,15 @@ def make_reads(panel: Panel, n_pairs: int, seed: int, indel_frac: float = 0.0, m
     truth = np.empty(2 * n_pairs, dtype=np.int32)
     truth[0::2] = a1; truth[1::2] = a2
     truth[0::2][off] = -1; truth[1::2][off] = -1
-    rnd = ACGT[rng.integers(0, 4, codes.shape)]
     codes[np.repeat(off, 2)] = 0
-    pad = codes == 0
-    codes[pad] = rnd[pad]                                    # beyond the amplicon / off-target: iid bases
-    deg = _POPC[codes] > 1                                   # instantiate degenerate positions
+    rnd = np.left_shift(np.uint8(1), rng.integers(0, 4, codes.shape, dtype=np.uint8))   # iid A/C/G/T codes
+    np.copyto(codes, rnd, where=(codes == 0))                # beyond the amplicon / off-target: iid bases
+    del rnd
+    deg = (codes & (codes - 1)) != 0                         # more than one bit set: instantiate degenerate positions
     if deg.any():
         idx = np.nonzero(deg)
         codes[idx] = _MEMBER[codes[idx], rng.integers(0, 12, len(idx[0]))]
+    del deg
     total = codes.size
     k = rng.binomial(total, sub_rate)                        # substitutions
     pos = rng.integers(0, total, k)

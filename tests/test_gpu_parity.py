@@ -249,7 +249,7 @@ def test_scoring_matrix():
         if i % 50 == 0:
             s[9] = "K"   # a read base the matrix has no entry for -> the reference would throw (status 4)
         recs.append(H.Rec("".join(s), True, False))
-    got5, _, _, _ = run_both(primers, H.recs_to_arrays(recs), scoring_matrix=sm, gap_open=-4, gap_extend=-1, min_alignment_score_rate=0.1)
+    got5, _, _, _ = run_both(primers, H.recs_to_arrays(recs), scoring_matrix=sm, gap_open=-4, gap_extend=-1, min_alignment_score_rate=0.0)
     assert (got5["status"] == 4).any() and (got5["type"] == L.GAPPED).any()
 
 
