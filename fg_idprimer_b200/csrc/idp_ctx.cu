@@ -75,7 +75,7 @@ struct idp_ctx {
     int device = 0, sm_count = 148;
     DevPanel dp{};
     DevBuf b_pmask, b_pinfo, b_positive, b_loc_key[2], b_loc_primer[2], b_mate_off, b_mate_idx, b_smat;
-    DevBuf b_keys[2], b_offcnt[2], b_postings[2];
+    DevBuf b_keys[2], b_offcnt[2], b_postings[2], b_heads[2], b_direct[2];
     Slot slots[kSlots];
     cudaStream_t user_stream = nullptr;
     idp_timings last{};
@@ -110,6 +110,7 @@ static int upload_panel(idp_ctx *c) {
         k.k = h.k > 0 ? h.k : -1;
         k.window = p.max_primer_length;
         k.slot_mask = 0; k.shift = 63; k.keys = nullptr; k.off_cnt = nullptr; k.postings = nullptr;
+        k.heads = nullptr; k.direct = nullptr; k.n_postings = 0;
         if (h.k > 0) {
             std::vector<OffCnt> oc(h.keys.size());
             for (size_t i = 0; i < oc.size(); ++i) oc[i] = OffCnt{h.off[i], h.cnt[i]};
@@ -120,6 +121,9 @@ static int upload_panel(idp_ctx *c) {
             while ((size_t(1) << bits) < h.keys.size()) ++bits;
             k.slot_mask = (uint32_t)h.keys.size() - 1; k.shift = 64 - bits;
             k.keys = c->b_keys[w].as<uint64_t>(); k.off_cnt = c->b_offcnt[w].as<OffCnt>(); k.postings = c->b_postings[w].as<uint32_t>();
+            if ((rc = upload(h.heads, c->b_heads[w]))) return rc;
+            k.heads = c->b_heads[w].as<uint2>(); k.n_postings = (uint32_t)h.postings.size();
+            if (!h.direct.empty()) { if ((rc = upload(h.direct, c->b_direct[w]))) return rc; k.direct = c->b_direct[w].as<uint32_t>(); }
         }
     }
     if ((rc = upload(p.mate_off, c->b_mate_off))) return rc;
@@ -138,9 +142,40 @@ static int upload_panel(idp_ctx *c) {
 }
 
 template <int RW>
-static void launch_scan(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp_result *five, unsigned *fall, Counters *ctr) {
-    const int grid = (R.n + 255) / 256;
-    scan_kernel<RW><<<grid, 256, 0, st>>>(c->dp, R, five, fall, ctr);
+static int launch_scan(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp_result *five, unsigned *fall, Counters *ctr) {
+    // shared-memory plan: the read tile first, then as much of the panel side as fits in half an SM (two CTAs per SM)
+    ScanLaunch S{};
+    const DevKmerIndex &ix = c->dp.kidx[0];
+    const size_t budget = 110 * 1024;
+    size_t used = 0;
+    S.stride = R.fixed_len > 0 ? (uint32_t)((R.fixed_len + 1) >> 1) : 0;
+    // per-warp tiles of 32 reads: 32 * stride must stay a multiple of 16 bytes for the TMA bulk copy (it is: 32 * stride)
+    S.stage_tile = R.fixed_len > 0 && (reinterpret_cast<uintptr_t>(R.seq4) & 15) == 0 && S.stride <= 1024;
+    if (S.stage_tile) {
+        S.tile_smem_bytes = (uint32_t)((32 * (size_t)S.stride + 4 * RW + 16 + 15) & ~size_t(15));
+        used = (size_t)S.tile_smem_bytes * (kScanThreads / 32);
+    }
+    auto place = [&](size_t bytes, bool wanted) -> uint32_t {
+        bytes = (bytes + 15) & ~size_t(15);
+        if (!wanted || bytes == 0 || used + bytes > budget) return 0xFFFFFFFFu;
+        const uint32_t off = (uint32_t)used;
+        used += bytes;
+        return off;
+    };
+    S.direct_entries = ix.direct ? (1u << (2 * ix.k)) : 0;
+    S.off_direct = place((size_t)S.direct_entries * 4, ix.direct != nullptr);
+    S.off_pinfo = place((size_t)c->dp.n_primers * sizeof(int4), true);
+    S.off_pmask = place((size_t)c->dp.n_primers * c->dp.ww * 4, true);
+    S.off_heads = place((size_t)ix.n_postings * 8, ix.k > 0);
+    const int n_tiles = (R.n + kScanThreads - 1) / kScanThreads;
+    const int grid = std::max(1, std::min(n_tiles, 2 * c->sm_count));
+    if (used > budget) { S.stage_tile = 0; used = 0; }
+    if (cudaFuncSetAttribute(scan_kernel<RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(scan_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return IDP_ERR_CUDA;
+    }
+    scan_kernel<RW><<<grid, kScanThreads, used, st>>>(c->dp, R, S, five, fall, ctr);
+    return IDP_OK;
 }
 
 template <bool LOCAL, bool SMAT>
@@ -213,12 +248,13 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
     CUDA_TRY(cudaEventRecord(s.ev[EV_START], st));
     if (n > 0) {
         switch (c->rw) {
-            case 4: launch_scan<4>(c, st, R, five, fall, ctr); break;
-            case 5: launch_scan<5>(c, st, R, five, fall, ctr); break;
-            case 8: launch_scan<8>(c, st, R, five, fall, ctr); break;
-            case 16: launch_scan<16>(c, st, R, five, fall, ctr); break;
-            default: launch_scan<32>(c, st, R, five, fall, ctr); break;
+            case 4: rc = launch_scan<4>(c, st, R, five, fall, ctr); break;
+            case 5: rc = launch_scan<5>(c, st, R, five, fall, ctr); break;
+            case 8: rc = launch_scan<8>(c, st, R, five, fall, ctr); break;
+            case 16: rc = launch_scan<16>(c, st, R, five, fall, ctr); break;
+            default: rc = launch_scan<32>(c, st, R, five, fall, ctr); break;
         }
+        if (rc) return rc;
         ++s.launches;
     }
     CUDA_TRY(cudaEventRecord(s.ev[EV_SCAN], st));
@@ -338,7 +374,7 @@ void idp_ctx_destroy(idp_ctx *c) {
     }
     for (DevBuf *b : {&c->b_pmask, &c->b_pinfo, &c->b_positive, &c->b_loc_key[0], &c->b_loc_key[1], &c->b_loc_primer[0], &c->b_loc_primer[1],
                       &c->b_mate_off, &c->b_mate_idx, &c->b_smat, &c->b_keys[0], &c->b_keys[1], &c->b_offcnt[0], &c->b_offcnt[1],
-                      &c->b_postings[0], &c->b_postings[1]}) b->release();
+                      &c->b_postings[0], &c->b_postings[1], &c->b_heads[0], &c->b_heads[1], &c->b_direct[0], &c->b_direct[1]}) b->release();
     delete c;
 }
 

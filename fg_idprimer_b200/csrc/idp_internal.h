@@ -29,6 +29,9 @@ struct DevKmerIndex {
     const uint64_t *keys;      // 0 = empty slot (a real key never has a zero nibble)
     const OffCnt *off_cnt;      // postings offset / count per slot
     const uint32_t *postings;  // primer indices in the iteration order of the reference's Set[Primer]
+    const uint2 *heads;        // per posting {id | (accept+1) << 24, mask of the first 8 primer bases}
+    const uint32_t *direct;    // NULL, or 4^k entries (2 bits per base, all-ACGT k-mers): posting offset | count << 20
+    uint32_t n_postings;
 };
 
 // ---- device view of the panel ----
@@ -62,6 +65,8 @@ struct KmerIndexHost {
     std::vector<uint64_t> keys;
     std::vector<uint32_t> off, cnt;   // per slot
     std::vector<uint32_t> postings;
+    std::vector<uint32_t> heads;      // 2 words per posting (scan kernel), see build_kmer_index
+    std::vector<uint32_t> direct;     // 4^k entries, off | cnt << 20; empty when not applicable
     std::unordered_map<std::string, std::pair<uint32_t, uint32_t>> by_string;  // kmer -> (offset, count)
 };
 

@@ -72,6 +72,13 @@ struct Oriented {
     int len;
     bool rc;
     __device__ __forceinline__ uint32_t nib(int j) const { return rc ? comp_nib(stored_nib(s, len - 1 - j)) : stored_nib(s, j); }
+    // same through a generic pointer (the bases may sit in shared memory)
+    __device__ __forceinline__ uint32_t nib_generic(int j) const {
+        const int i = rc ? len - 1 - j : j;
+        const uint32_t b = s[i >> 1];
+        const uint32_t v = (i & 1) ? (b & 15u) : (b >> 4);
+        return rc ? comp_nib(v) : v;
+    }
 };
 // sequencing order (PM:39-45): raw when unmapped or positive strand, else reverse complement
 __device__ __forceinline__ bool seq_order_is_rc(uint16_t fl) { return !(fl & IDP_F_UNMAPPED) && (fl & IDP_F_REVERSE); }
@@ -87,169 +94,6 @@ __device__ __forceinline__ idp_result none_result() {
     r.primer = -1; r.type = IDP_NONE; r.status = 0; r.multi = 0; r.reserved = 0;
     r.mm = 0; r.next_mm = 0; r.raw_score = 0; r.raw_next = 0; r.q_len = 0; r.q_len_next = 0; r.t_start = 0; r.t_end = 0;
     return r;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Kernel A+B: scan.  One thread per read.
-// ---------------------------------------------------------------------------------------------------------------
-struct Best2 {  // getBestUngappedAlignment (PM:237-248) as a running stable top-2 on key = mm / Primer.length
-    int bp = -1, bmm = 0, sp = -1, smm = 0;
-    double bkey = 0.0, skey = 0.0;
-    __device__ __forceinline__ void offer(int p, int mm, double key) {
-        if (bp < 0 || key < bkey) { sp = bp; smm = bmm; skey = bkey; bp = p; bmm = mm; bkey = key; }
-        else if (sp < 0 || key < skey) { sp = p; smm = mm; skey = key; }
-    }
-};
-
-template <int RW>
-struct ScanCtx {
-    uint32_t win[RW];  // read prefix in sequencing order, base i in nibble i, zero beyond the read
-    int len;
-    unsigned long long compares;
-};
-
-// numMismatches + mismatchAlign (PM:128-147).  Returns true and mm when the rate test passes.
-template <int RW>
-__device__ __forceinline__ bool mismatch_align(const DevPanel &P, ScanCtx<RW> &c, int p, int &mm_out) {
-    const int4 info = __ldg(&P.pinfo[p]);  // {Primer.length, cap, accept, sequence.length}
-    const uint32_t *pm = P.pmask + (size_t)p * P.ww;
-    int total = 0;
-#pragma unroll
-    for (int w = 0; w < RW; ++w) {
-        if (w < P.ww) {
-            uint32_t x = c.win[w] & ~__ldg(&pm[w]);  // read mask not a subset of primer mask (PM:143)
-            x |= x >> 1;
-            x |= x >> 2;
-            total += __popc(x & 0x11111111u);
-        }
-    }
-    c.compares += (unsigned)min(c.len, info.w);
-    int cap, acc;
-    if (c.len >= info.x) { cap = info.y; acc = info.z; }
-    else {  // short read: length = min(bases.length, primer.length) in the JVM's double arithmetic (PM:130-134)
-        const int length = c.len;
-        const double max_mismatches = (double)length * P.max_mismatch_rate;
-        const double capd = floor(max_mismatches) + 1.0;
-        cap = capd > 1e9 ? 1000000000 : (int)capd;
-        const int mm = min(total, cap);
-        mm_out = mm;
-        return __ddiv_rn((double)mm, (double)length) <= P.max_mismatch_rate;
-    }
-    const int mm = min(total, cap);  // the while loop stops counting once count > maxMismatches (PM:142)
-    mm_out = mm;
-    return mm <= acc;
-}
-
-template <int RW>
-__global__ void __launch_bounds__(256) scan_kernel(DevPanel P, DevReads R, idp_result *__restrict__ five,
-                                                   unsigned int *__restrict__ fall, Counters *__restrict__ ctr) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = r < R.n;
-    bool need_gapped = false;
-    ScanCtx<RW> c;
-    c.compares = 0;
-    if (active) {
-        const uint16_t fl = R.flags[r];
-        const uint8_t *s;
-        read_geom(R, r, s, c.len);
-        Oriented o{s, c.len, seq_order_is_rc(fl)};
-        // basesInSequencingOrder (PM:39-45), only the prefix the matchers can look at
-        const int nb = min(c.len, P.window_bases);
-#pragma unroll
-        for (int w = 0; w < RW; ++w) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                const int i = w * 8 + b;
-                if (i < nb) v |= o.nib(i) << (4 * b);
-            }
-            c.win[w] = v;
-        }
-        idp_result res = none_result();
-        // ---- LocationBasedPrimerMatcher.find (PM:194-213) ----
-        if (!(fl & IDP_F_UNMAPPED)) {
-            const int strand = (fl & IDP_F_REVERSE) ? 1 : 0;
-            const int nl = P.n_loc[strand];
-            if (nl > 0) {
-                const int pos = strand ? R.uend[r] : R.ustart[r];  // PM:180, 186
-                const int ref = R.ref_idx[r];
-                if (ref >= 0) {
-                    const int64_t lo = ((int64_t)ref << 32) | (uint32_t)max(pos - P.slop, 0);
-                    const int64_t hi = ((int64_t)ref << 32) | (uint32_t)(pos + P.slop);
-                    const int64_t *keys = P.loc_sortkey[strand];
-                    int a = 0, b = nl;
-                    while (a < b) { const int m = (a + b) >> 1; if (__ldg(&keys[m]) < lo) a = m + 1; else b = m; }
-                    // exactly one primer within slop, else "well I give up" (PM:198-206)
-                    if (a < nl && __ldg(&keys[a]) <= hi && !(a + 1 < nl && __ldg(&keys[a + 1]) <= hi)) {
-                        const int p = __ldg(&P.loc_primer[strand][a]);
-                        int mm;
-                        if (mismatch_align<RW>(P, c, p, mm)) { res.primer = p; res.type = IDP_LOCATION; res.mm = mm; }
-                    }
-                }
-            }
-        }
-        // ---- UngappedAlignmentBasedPrimerMatcher.find (PM:230-248) ----
-        if (res.type == IDP_NONE) {
-            Best2 best;
-            const DevKmerIndex &ix = P.kidx[0];
-            if (ix.k <= 0) {  // PM:100: every primer, file order
-                for (int p = 0; p < P.n_primers; ++p) {
-                    int mm;
-                    if (mismatch_align<RW>(P, c, p, mm)) best.offer(p, mm, __ddiv_rn((double)mm, (double)__ldg(&P.pinfo[p]).x));
-                }
-            } else if (c.len >= ix.k) {  // PM:108-116
-                const int end = min(ix.window, c.len) - ix.k + 1;
-                const uint64_t kmask = ix.k >= 16 ? ~0ull : ((1ull << (4 * ix.k)) - 1ull);
-                uint64_t key = 0;
-#pragma unroll
-                for (int i = 0; i < RW * 8; ++i) {
-                    key = ((key << 4) | ((c.win[i >> 3] >> (4 * (i & 7))) & 15u)) & kmask;
-                    const int start = i - (ix.k - 1);
-                    if (start >= 0 && start < end && key != 0) {
-                        uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> ix.shift);
-                        for (;;) {
-                            const uint64_t kk = __ldg(&ix.keys[h]);
-                            if (kk == key) {
-                                const OffCnt oc = ix.off_cnt[h];
-                                for (uint32_t j = 0; j < oc.cnt; ++j) {
-                                    const int p = (int)__ldg(&ix.postings[oc.off + j]);
-                                    // .distinct (PM:114): a primer already holding a top-2 slot is skipped; one that lost
-                                    // before loses again (strict comparisons), so no visited set is needed
-                                    if (p == best.bp || p == best.sp) continue;
-                                    int mm;
-                                    if (mismatch_align<RW>(P, c, p, mm)) best.offer(p, mm, __ddiv_rn((double)mm, (double)__ldg(&P.pinfo[p]).x));
-                                }
-                                break;
-                            }
-                            if (kk == 0) break;
-                            h = (h + 1) & ix.slot_mask;
-                        }
-                    }
-                }
-            }
-            if (best.bp >= 0) {
-                res.primer = best.bp; res.type = IDP_UNGAPPED; res.mm = best.bmm;
-                res.next_mm = best.sp >= 0 ? best.smm : IDP_NEXT_NA;               // PM:244-245
-                if (!(res.mm <= res.next_mm)) res.status = IDP_STATUS_REQ_MM_LE_NEXT;  // PMa:102
-            }
-        }
-        need_gapped = res.type == IDP_NONE;
-        write_result(&five[r], res);
-    }
-    // fall-through list (IP:444-450), warp-aggregated append
-    const unsigned ballot = __ballot_sync(0xffffffffu, need_gapped);
-    if (ballot) {
-        const int lane = threadIdx.x & 31;
-        unsigned base = 0;
-        if (lane == __ffs(ballot) - 1) base = atomicAdd(&ctr->n_fall, __popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
-        if (need_gapped) fall[base + __popc(ballot & ((1u << lane) - 1u))] = (unsigned)r;
-    }
-    // statistics: base comparisons, one atomic per warp
-    unsigned long long cmp = c.compares;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) cmp += __shfl_xor_sync(0xffffffffu, cmp, d);
-    if ((threadIdx.x & 31) == 0 && cmp) atomicAdd(&ctr->base_compares, cmp);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -770,3 +614,5 @@ __global__ void __launch_bounds__(256) metrics_kernel(DevReads R, const idp_resu
 }
 
 }  // namespace idp
+
+#include "idp_scan.cuh"

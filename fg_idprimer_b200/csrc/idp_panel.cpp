@@ -189,6 +189,32 @@ static bool build_kmer_index(const idp_panel &p, int k, KmerIndexHost &out) {
         out.cnt[h] = (uint32_t)order.size();
     }
     if (out.postings.empty()) out.postings.push_back(0);
+    // head-filtered postings for the scan kernel: {primer id | (accept threshold + 1) << 24, first 8 bases of the mask}
+    out.heads.resize(out.postings.size() * 2);
+    for (size_t j = 0; j < out.postings.size(); ++j) {
+        const uint32_t id = out.postings[j];
+        const int acc1 = std::min(p.acc_full[id] + 1, 255);
+        out.heads[2 * j] = id | ((uint32_t)acc1 << 24);
+        out.heads[2 * j + 1] = p.pmask[(size_t)id * p.ww];
+    }
+    // direct-address table over the 4^k all-ACGT k-mers (2 bits per base): entry = posting offset (20 bits) | count (12 bits)
+    if (k <= 7 && out.postings.size() < (1u << 20) && p.n < (1 << 20)) {
+        bool fits = true;
+        std::vector<uint32_t> direct((size_t)1 << (2 * k), 0);
+        for (auto &kv : out.by_string) {
+            uint32_t code = 0;
+            bool acgt = true;
+            for (char c : kv.first) {
+                const char *at = strchr("ACGT", c);
+                if (!at || !c) { acgt = false; break; }
+                code = (code << 2) | (uint32_t)(at - "ACGT");
+            }
+            if (!acgt) continue;
+            if (kv.second.second >= (1u << 12)) { fits = false; break; }
+            direct[code] = kv.second.first | (kv.second.second << 20);
+        }
+        if (fits) out.direct.swap(direct);
+    }
     return true;
 }
 

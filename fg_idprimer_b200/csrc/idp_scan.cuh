@@ -1,0 +1,330 @@
+// Kernel A+B: k-mer prefilter + location + ungapped IUPAC scan (included at the end of idp_kernels.cuh).
+//
+//   basesInSequencingOrder (PM:39-45) . LocationBasedPrimerMatcher.find (PM:194-213) . getPrimersForAlignmentTasks
+//   (PM:98-116) . mismatchAlign / numMismatches (PM:128-147) . getBestUngappedAlignment (PM:237-248)
+//
+// Persistent CTAs of kScanThreads threads walk tiles of kScanThreads reads.  A tile's packed bases (75 B per 150 bp
+// read) are brought into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier); two CTAs per SM overlap one
+// tile's copy with the other's compute.  The panel side lives in shared memory as far as it fits: a direct-address
+// table over the 4^k all-ACGT k-mers, posting lists whose entries carry the first 8 primer bases and the accept
+// threshold (a candidate is rejected from one 8-byte entry in the common case), the primer masks and thresholds.
+#pragma once
+
+namespace idp {
+
+constexpr int kScanThreads = 512;
+
+struct ScanLaunch {
+    int32_t stage_tile;        // 1: reads are fixed-length and 16-byte aligned: tiles are staged into shared memory by TMA
+    uint32_t stride;           // bytes per read when fixed-length
+    uint32_t tile_smem_bytes;  // shared-memory bytes reserved for the tile (incl. slack), multiple of 16
+    // byte offsets into dynamic shared memory, or 0xFFFFFFFF when the structure stays in global memory
+    uint32_t off_direct, off_heads, off_pmask, off_pinfo;
+    uint32_t direct_entries;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+// 8 BAM bytes-order nibbles (first base in the HIGH nibble of each byte) -> base i in nibble i
+__device__ __forceinline__ uint32_t nibswap(uint32_t x) { return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu); }
+// 1 in the low bit of every nibble that is non-zero
+__device__ __forceinline__ uint32_t nib_nonzero(uint32_t x) {
+    x |= x >> 1;
+    x |= x >> 2;
+    return x & 0x11111111u;
+}
+
+struct Best2 {  // getBestUngappedAlignment (PM:237-248) as a running stable top-2 on key = mm / Primer.length
+    int bp = -1, bmm = 0, sp = -1, smm = 0;
+    double bkey = 0.0, skey = 0.0;
+    __device__ __forceinline__ void offer(int p, int mm, double key) {
+        if (bp < 0 || key < bkey) { sp = bp; smm = bmm; skey = bkey; bp = p; bmm = mm; bkey = key; }
+        else if (sp < 0 || key < skey) { sp = p; smm = mm; skey = key; }
+    }
+};
+
+template <int RW>
+struct ScanCtx {
+    uint32_t win[RW];  // read prefix in sequencing order, base i in nibble i, zero beyond the read
+    int len;
+    unsigned compares;
+    const uint32_t *pmask;  // generic pointers: shared or global
+    const int4 *pinfo;
+};
+
+// numMismatches + mismatchAlign (PM:128-147).  Returns true and mm when the rate test passes.
+template <int RW>
+__device__ __forceinline__ bool mismatch_align(const DevPanel &P, ScanCtx<RW> &c, int p, int &mm_out, int &plen_out) {
+    const int4 info = c.pinfo[p];  // {Primer.length, cap, accept, sequence.length}
+    const uint32_t *pm = c.pmask + (size_t)p * P.ww;
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < RW; ++w)
+        if (w < P.ww) total += __popc(nib_nonzero(c.win[w] & ~pm[w]));  // read mask not a subset of primer mask (PM:143)
+    c.compares += (unsigned)min(c.len, info.w);
+    plen_out = info.x;
+    if (c.len >= info.x) {
+        const int mm = min(total, info.y);  // the while loop stops counting once count > maxMismatches (PM:142)
+        mm_out = mm;
+        return mm <= info.z;
+    }
+    // short read: length = min(bases.length, primer.length), in the JVM's double arithmetic (PM:130-134)
+    const int length = c.len;
+    const double max_mismatches = (double)length * P.max_mismatch_rate;
+    const double capd = floor(max_mismatches) + 1.0;
+    const int mm = min(total, capd > 1e9 ? 1000000000 : (int)capd);
+    mm_out = mm;
+    return __ddiv_rn((double)mm, (double)length) <= P.max_mismatch_rate;
+}
+
+template <int RW>
+__device__ __noinline__ void offer_candidate(const DevPanel &P, ScanCtx<RW> &c, Best2 &best, int p) {
+    // .distinct (PM:114): a primer already holding a top-2 slot is skipped; one that lost before loses again (strict
+    // comparisons), so no visited set is needed
+    if (p == best.bp || p == best.sp) return;
+    int mm, plen;
+    if (mismatch_align<RW>(P, c, p, mm, plen)) best.offer(p, mm, __ddiv_rn((double)mm, (double)plen));
+}
+
+// Candidates that survive the 8-base head filter wait here and are evaluated after the k-mer loop, all lanes together
+// (in first-hit order, which is the order the reference visits them in).
+template <int RW>
+struct Pending {
+    int q0 = -1, q1 = -1, q2 = -1, q3 = -1;
+    __device__ __forceinline__ void flush(const DevPanel &P, ScanCtx<RW> &c, Best2 &best) {
+        if (q0 >= 0) offer_candidate<RW>(P, c, best, q0);
+        if (q1 >= 0) offer_candidate<RW>(P, c, best, q1);
+        if (q2 >= 0) offer_candidate<RW>(P, c, best, q2);
+        if (q3 >= 0) offer_candidate<RW>(P, c, best, q3);
+        q0 = q1 = q2 = q3 = -1;
+    }
+    __device__ __forceinline__ void push(const DevPanel &P, ScanCtx<RW> &c, Best2 &best, int p) {
+        if (p == q0 || p == q1 || p == q2 || p == q3) return;
+        if (q3 >= 0) flush(P, c, best);
+        if (q0 < 0) q0 = p; else if (q1 < 0) q1 = p; else if (q2 < 0) q2 = p; else q3 = p;
+    }
+};
+
+// posting list walk: the 8-byte head rejects a candidate whose first 8 bases already exceed the accept threshold
+// (exact: the full count can only be larger, and a short read's threshold can only be smaller)
+template <int RW>
+__device__ __forceinline__ void walk_postings(const DevPanel &P, ScanCtx<RW> &c, Best2 &best, Pending<RW> &pend, const uint2 *heads,
+                                              uint32_t off, uint32_t cnt) {
+    for (uint32_t j = 0; j < cnt; ++j) {
+        const uint2 h = heads[off + j];
+        const uint32_t acc1 = h.x >> 24;
+        const uint32_t partial = __popc(nib_nonzero(c.win[0] & ~h.y));
+        if (partial < acc1 || acc1 == 255u) pend.push(P, c, best, (int)(h.x & 0xFFFFFu));
+    }
+    c.compares += 8u * cnt;
+}
+
+template <int RW>
+__global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(DevPanel P, DevReads R, ScanLaunch S, idp_result *__restrict__ five,
+                                                               unsigned int *__restrict__ fall, Counters *__restrict__ ctr) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t tile_bar[kScanThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const DevKmerIndex &ix = P.kidx[0];
+    // ---- panel-side tables into shared memory (once per persistent CTA) ----
+    const uint32_t *direct = ix.direct;
+    const uint2 *heads = ix.heads;
+    ScanCtx<RW> c;
+    c.pmask = P.pmask;
+    c.pinfo = P.pinfo;
+    if (S.off_direct != 0xFFFFFFFFu) {
+        uint32_t *d = reinterpret_cast<uint32_t *>(smem + S.off_direct);
+        for (uint32_t i = tid; i < S.direct_entries; i += blockDim.x) d[i] = ix.direct[i];
+        direct = d;
+    }
+    if (S.off_heads != 0xFFFFFFFFu) {
+        uint2 *d = reinterpret_cast<uint2 *>(smem + S.off_heads);
+        for (uint32_t i = tid; i < ix.n_postings; i += blockDim.x) d[i] = ix.heads[i];
+        heads = d;
+    }
+    if (S.off_pmask != 0xFFFFFFFFu) {
+        uint32_t *d = reinterpret_cast<uint32_t *>(smem + S.off_pmask);
+        for (int i = tid; i < P.n_primers * P.ww; i += blockDim.x) d[i] = P.pmask[i];
+        c.pmask = d;
+    }
+    if (S.off_pinfo != 0xFFFFFFFFu) {
+        int4 *d = reinterpret_cast<int4 *>(smem + S.off_pinfo);
+        for (int i = tid; i < P.n_primers; i += blockDim.x) d[i] = P.pinfo[i];
+        c.pinfo = d;
+    }
+    if (S.stage_tile && lane == 0) {
+        mbar_init(&tile_bar[wib], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // ---- every warp walks its own 32-read tiles: no CTA-wide barrier from here on ----
+    unsigned char *wtile = smem + (size_t)wib * S.tile_smem_bytes;
+    uint32_t parity = 0;
+    const int n_wtiles = (R.n + 31) / 32;
+    const int warps_total = gridDim.x * (kScanThreads / 32);
+    unsigned long long compares_total = 0;
+    for (int wt = blockIdx.x * (kScanThreads / 32) + wib; wt < n_wtiles; wt += warps_total) {
+        const int r = wt * 32 + lane;
+        const bool active = r < R.n;
+        if (S.stage_tile) {
+            // this warp's 32 reads (2400 B for 150 bp): one TMA bulk copy + a tail shorter than 16 bytes
+            const size_t g0 = (size_t)wt * 32 * S.stride;
+            const uint32_t bytes = (uint32_t)min(32, R.n - wt * 32) * S.stride;
+            const uint32_t bulk = bytes & ~15u;
+            __syncwarp();  // all lanes are done reading the previous tile
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&tile_bar[wib], bulk);
+                if (bulk) tma_load_1d(wtile, R.seq4 + g0, bulk, &tile_bar[wib]);
+            }
+            if (lane < (int)(bytes - bulk)) wtile[bulk + lane] = R.seq4[g0 + bulk + lane];
+            mbar_wait(&tile_bar[wib], parity);
+            parity ^= 1u;
+            __syncwarp();  // tail bytes visible
+        }
+        bool need_gapped = false;
+        c.compares = 0;
+        if (active) {
+            const uint16_t fl = R.flags[r];
+            const uint8_t *s;
+            read_geom(R, r, s, c.len);
+            const bool rc = seq_order_is_rc(fl);
+            const uint8_t *sp = S.stage_tile ? wtile + (size_t)lane * S.stride : s;  // generic pointer: shared or global
+            // ---- basesInSequencingOrder (PM:39-45), only the prefix the matchers can look at ----
+            if (!rc && ((c.len + 1) >> 1) >= 4 * RW + 4) {
+                const uintptr_t a = reinterpret_cast<uintptr_t>(sp);
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+                const int sh = (int)(a & 3) * 8;
+                uint32_t prev = wp[0];
+#pragma unroll
+                for (int w = 0; w < RW; ++w) {
+                    const uint32_t next = wp[w + 1];
+                    c.win[w] = nibswap(__funnelshift_r(prev, next, sh));
+                    prev = next;
+                }
+                if (c.len < RW * 8) {
+#pragma unroll
+                    for (int w = 0; w < RW; ++w) {
+                        const int rem = c.len - w * 8;
+                        if (rem < 8) c.win[w] = rem <= 0 ? 0u : (c.win[w] & ((1u << (4 * rem)) - 1u));
+                    }
+                }
+            } else {
+                Oriented o{sp, c.len, rc};
+                const int nb = min(c.len, RW * 8);
+#pragma unroll
+                for (int w = 0; w < RW; ++w) {
+                    uint32_t v = 0;
+                    for (int b = 0; b < 8; ++b) {
+                        const int i = w * 8 + b;
+                        if (i < nb) v |= o.nib_generic(i) << (4 * b);
+                    }
+                    c.win[w] = v;
+                }
+            }
+            idp_result res = none_result();
+            // ---- LocationBasedPrimerMatcher.find (PM:194-213) ----
+            if (!(fl & IDP_F_UNMAPPED) && R.ref_idx != nullptr) {
+                const int strand = (fl & IDP_F_REVERSE) ? 1 : 0;
+                const int nl = P.n_loc[strand];
+                const int pos = strand ? R.uend[r] : R.ustart[r];  // PM:180, 186
+                const int ref = R.ref_idx[r];
+                if (nl > 0 && ref >= 0 && pos + P.slop >= 1) {
+                    const int64_t lo = ((int64_t)ref << 32) | (uint32_t)max(pos - P.slop, 0);
+                    const int64_t hi = ((int64_t)ref << 32) | (uint32_t)(pos + P.slop);
+                    const int64_t *keys = P.loc_sortkey[strand];
+                    int a = 0, b = nl;
+                    while (a < b) { const int m = (a + b) >> 1; if (__ldg(&keys[m]) < lo) a = m + 1; else b = m; }
+                    // exactly one primer within slop, else "well I give up" (PM:198-206)
+                    if (a < nl && __ldg(&keys[a]) <= hi && !(a + 1 < nl && __ldg(&keys[a + 1]) <= hi)) {
+                        const int p = __ldg(&P.loc_primer[strand][a]);
+                        int mm, plen;
+                        if (mismatch_align<RW>(P, c, p, mm, plen)) { res.primer = p; res.type = IDP_LOCATION; res.mm = mm; }
+                    }
+                }
+            }
+            // ---- UngappedAlignmentBasedPrimerMatcher.find (PM:230-248) ----
+            if (res.type == IDP_NONE) {
+                Best2 best;
+                if (ix.k <= 0) {  // PM:100: every primer, file order
+                    for (int p = 0; p < P.n_primers; ++p) {
+                        int mm, plen;
+                        if (mismatch_align<RW>(P, c, p, mm, plen)) best.offer(p, mm, __ddiv_rn((double)mm, (double)plen));
+                    }
+                } else if (c.len >= ix.k) {  // PM:108-116
+                    const int n_bases = min(ix.window, c.len);  // k-mers start at 0 .. n_bases - k
+                    Pending<RW> pend;
+                    uint32_t sr[RW];  // shift register over the window: the next base is always the low nibble of sr[0]
+#pragma unroll
+                    for (int w = 0; w < RW; ++w) sr[w] = c.win[w];
+                    const uint64_t kmask4 = ix.k >= 16 ? ~0ull : ((1ull << (4 * ix.k)) - 1ull);
+                    const uint32_t kmask2 = ix.k >= 16 ? ~0u : ((1u << (2 * ix.k)) - 1u);
+                    uint64_t key4 = 0;
+                    uint32_t key2 = 0;
+                    int bad = 0;  // > 0 while the current k-mer holds a nibble that is not exactly one of A/C/G/T
+                    for (int i = 0; i < n_bases; ++i) {
+                        const uint32_t nib = sr[0] & 15u;
+#pragma unroll
+                        for (int w = 0; w < RW - 1; ++w) sr[w] = __funnelshift_r(sr[w], sr[w + 1], 4);
+                        sr[RW - 1] >>= 4;
+                        key4 = ((key4 << 4) | nib) & kmask4;
+                        key2 = ((key2 << 2) | ((0x30210u >> (2 * nib)) & 3u)) & kmask2;  // A,C,G,T (1,2,4,8) -> 0..3
+                        bad = max(bad - 1, 0);
+                        if (__popc(nib) != 1) bad = ix.k;
+                        if (i < ix.k - 1) continue;
+                        if (direct != nullptr && bad == 0) {
+                            const uint32_t e = direct[key2];
+                            if (e) walk_postings<RW>(P, c, best, pend, heads, e & 0xFFFFFu, e >> 20);
+                        } else {  // literal equality of IUPAC letters (PM:113): the full table, keyed by 4 bits per base
+                            OffCnt oc;
+                            if (kmer_lookup(ix, key4, oc)) walk_postings<RW>(P, c, best, pend, direct != nullptr ? ix.heads : heads, oc.off, oc.cnt);
+                        }
+                    }
+                    pend.flush(P, c, best);
+                }
+                if (best.bp >= 0) {
+                    res.primer = best.bp; res.type = IDP_UNGAPPED; res.mm = best.bmm;
+                    res.next_mm = best.sp >= 0 ? best.smm : IDP_NEXT_NA;                   // PM:244-245
+                    if (!(res.mm <= res.next_mm)) res.status = IDP_STATUS_REQ_MM_LE_NEXT;  // PMa:102
+                }
+            }
+            need_gapped = res.type == IDP_NONE;
+            write_result(&five[r], res);
+        }
+        // fall-through list (IP:444-450), warp-aggregated append
+        const unsigned ballot = __ballot_sync(0xffffffffu, need_gapped);
+        if (ballot) {
+            unsigned base = 0;
+            if (lane == __ffs(ballot) - 1) base = atomicAdd(&ctr->n_fall, __popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+            if (need_gapped) fall[base + __popc(ballot & ((1u << lane) - 1u))] = (unsigned)r;
+        }
+        compares_total += c.compares;
+    }
+    // statistics: base comparisons performed (a head-filter rejection counts 8), one atomic per warp
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) compares_total += __shfl_xor_sync(0xffffffffu, compares_total, d);
+    if (lane == 0 && compares_total) atomicAdd(&ctr->base_compares, compares_total);
+}
+
+}  // namespace idp
