@@ -54,7 +54,7 @@ struct Slot {
     // staging for the host-pointer path
     DevBuf seq4, seq_off, len, ref_idx, ustart, uend, flags, five, three;
     // scratch of the chain
-    DevBuf fall, all_list, seg_off, seg_cnt, pair_work, pair_primer, pair_score, fin;
+    DevBuf fall, all_list, seg_off, seg_cnt, pair_work, pair_primer, pair_score, pair_se, fin;
     Counters *d_ctr = nullptr, *h_ctr = nullptr;
     size_t pair_cap = 0;
     bool busy = false;
@@ -133,6 +133,10 @@ static int upload_panel(idp_ctx *c) {
     d.gap_open = p.params.gap_open; d.gap_extend = p.params.gap_extend;
     d.smat = nullptr;
     if (!p.smat16.empty()) { if ((rc = upload(p.smat16, c->b_smat))) return rc; d.smat = c->b_smat.as<int32_t>(); }
+    {   // (score << 12 | start) register traceback: |score| * (rows + columns) must stay below 2^17
+        const long maxabs = std::max<long>({std::labs(d.match_score), std::labs(d.mismatch_score), std::labs((long)d.gap_open + d.gap_extend), std::labs(d.gap_extend)});
+        d.packed_trace_ok = d.smat == nullptr && maxabs * (kMaxPrimerBases + kMaxReadLen + 1) < (1L << 17);
+    }
     d.slop = p.params.slop; d.three_prime = p.params.three_prime;
     d.max_mismatch_rate = p.params.max_mismatch_rate; d.min_alignment_score_rate = p.params.min_alignment_score_rate;
     const int wb = p.window_bases;
@@ -178,21 +182,29 @@ static int launch_scan(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp
     return IDP_OK;
 }
 
+// the pair kernel also produces the traceback-equivalent (start, end) when the packed register variant applies
+static bool pairs_trace(const idp_ctx *c) { return c->nq > 0 && c->dp.packed_trace_ok && c->dp.smat == nullptr; }
+
 template <bool LOCAL, bool SMAT>
 static void launch_sw_pairs_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, const unsigned *work_read, Counters *ctr,
-                              const unsigned *pw, const unsigned *pp, int *ps, unsigned cap) {
+                              const unsigned *pw, const unsigned *pp, int *ps, unsigned *pse, unsigned cap) {
     const int grid = c->sm_count * 8;
+    if (!SMAT && pairs_trace(c)) {
+        if (c->nq == 32) sw_pairs_kernel<32, LOCAL, false, true><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, pse, cap);
+        else sw_pairs_kernel<64, LOCAL, false, true><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, pse, cap);
+        return;
+    }
     switch (c->nq) {
-        case 32: sw_pairs_kernel<32, LOCAL, SMAT><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, cap); break;
-        case 64: sw_pairs_kernel<64, LOCAL, SMAT><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, cap); break;
-        default: sw_pairs_kernel<0, LOCAL, SMAT><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, cap); break;
+        case 32: sw_pairs_kernel<32, LOCAL, SMAT, false><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, pse, cap); break;
+        case 64: sw_pairs_kernel<64, LOCAL, SMAT, false><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, pse, cap); break;
+        default: sw_pairs_kernel<0, LOCAL, SMAT, false><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, pse, cap); break;
     }
 }
 static void launch_sw_pairs(const idp_ctx *c, cudaStream_t st, bool local, const DevReads &R, const unsigned *work_read, Counters *ctr,
-                            const unsigned *pw, const unsigned *pp, int *ps, unsigned cap) {
+                            const unsigned *pw, const unsigned *pp, int *ps, unsigned *pse, unsigned cap) {
     const bool smat = c->dp.smat != nullptr;
-    if (local) { if (smat) launch_sw_pairs_t<true, true>(c, st, R, work_read, ctr, pw, pp, ps, cap); else launch_sw_pairs_t<true, false>(c, st, R, work_read, ctr, pw, pp, ps, cap); }
-    else { if (smat) launch_sw_pairs_t<false, true>(c, st, R, work_read, ctr, pw, pp, ps, cap); else launch_sw_pairs_t<false, false>(c, st, R, work_read, ctr, pw, pp, ps, cap); }
+    if (local) { if (smat) launch_sw_pairs_t<true, true>(c, st, R, work_read, ctr, pw, pp, ps, pse, cap); else launch_sw_pairs_t<true, false>(c, st, R, work_read, ctr, pw, pp, ps, pse, cap); }
+    else { if (smat) launch_sw_pairs_t<false, true>(c, st, R, work_read, ctr, pw, pp, ps, pse, cap); else launch_sw_pairs_t<false, false>(c, st, R, work_read, ctr, pw, pp, ps, pse, cap); }
 }
 
 template <bool LOCAL, bool SMAT>
@@ -215,16 +227,18 @@ static void launch_sw_all(const idp_ctx *c, cudaStream_t st, bool local, const D
 
 static void launch_finalize_pairs(const idp_ctx *c, cudaStream_t st, const DevReads &R, const unsigned *work_read, const unsigned *n_work_ptr,
                                   unsigned n_work_fixed, const unsigned *seg_off, const int *seg_cnt, const unsigned *pp, const int *ps,
-                                  idp_result *out, Counters *ctr, int three) {
+                                  const unsigned *pse, idp_result *out, Counters *ctr, int three) {
     const int grid = c->sm_count * 8;
-    if (c->dp.max_seq_len <= 64) finalize_pairs_kernel<64><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, n_work_fixed, seg_off, seg_cnt, pp, ps, out, ctr, three);
-    else finalize_pairs_kernel<kMaxPrimerBases><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, n_work_fixed, seg_off, seg_cnt, pp, ps, out, ctr, three);
+    if (!pairs_trace(c)) pse = nullptr;
+    if (c->dp.max_seq_len <= 64) finalize_pairs_kernel<64, 0><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, n_work_fixed, seg_off, seg_cnt, pp, ps, pse, out, ctr, three);
+    else finalize_pairs_kernel<kMaxPrimerBases, 0><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, n_work_fixed, seg_off, seg_cnt, pp, ps, pse, out, ctr, three);
 }
 static void launch_finalize_all(const idp_ctx *c, cudaStream_t st, const DevReads &R, const unsigned *work_read, const unsigned *n_work_ptr,
                                 const Fin *fin, idp_result *out, int three) {
     const int grid = c->sm_count * 8;
-    if (c->dp.max_seq_len <= 64) finalize_all_kernel<64><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, three);
-    else finalize_all_kernel<kMaxPrimerBases><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, three);
+    if (c->nq == 32) finalize_all_kernel<64, 32><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, three);
+    else if (c->nq == 64) finalize_all_kernel<64, 64><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, three);
+    else finalize_all_kernel<kMaxPrimerBases, 0><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, three);
 }
 
 // Enqueue the whole matcher chain for reads already on the device.  Nothing here waits on the host.
@@ -237,7 +251,7 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
     if (k_gapped || do3) {
         if (s.pair_cap < 2 * n + 4096) s.pair_cap = 2 * n + 4096;
         if ((rc = s.seg_off.ensure(n * 4)) || (rc = s.seg_cnt.ensure(n * 4)) || (rc = s.pair_work.ensure(s.pair_cap * 4)) ||
-            (rc = s.pair_primer.ensure(s.pair_cap * 4)) || (rc = s.pair_score.ensure(s.pair_cap * 4))) return rc;
+            (rc = s.pair_primer.ensure(s.pair_cap * 4)) || (rc = s.pair_score.ensure(s.pair_cap * 4)) || (rc = s.pair_se.ensure(s.pair_cap * 4))) return rc;
     }
     if (!k_gapped || do3) { if ((rc = s.fin.ensure(n * sizeof(Fin)))) return rc; }
     if (do3) { if ((rc = s.all_list.ensure(n * 4))) return rc; }
@@ -266,10 +280,10 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
             cand5_kernel<<<c->sm_count * 4, 256, smem, st>>>(c->dp, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(),
                                                             (unsigned)s.pair_cap, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>());
             CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st));
-            launch_sw_pairs(c, st, false, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), (unsigned)s.pair_cap);
+            launch_sw_pairs(c, st, false, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), (unsigned)s.pair_cap);
             CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st));
             launch_finalize_pairs(c, st, R, fall, &ctr->n_fall, 0u, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(),
-                                  s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), five, ctr, 0);
+                                  s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), five, ctr, 0);
             s.launches += 3;
         } else {
             CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st));
@@ -286,11 +300,11 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
         cand3_kernel<<<(R.n + 255) / 256, 256, 0, st>>>(c->dp, R, five, ctr, s.all_list.as<unsigned>(), s.pair_work.as<unsigned>(),
                                                        s.pair_primer.as<unsigned>(), (unsigned)s.pair_cap, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>());
         CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_A], st));
-        launch_sw_pairs(c, st, true, R, nullptr, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), (unsigned)s.pair_cap);
+        launch_sw_pairs(c, st, true, R, nullptr, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), (unsigned)s.pair_cap);
         launch_sw_all(c, st, true, R, s.all_list.as<unsigned>(), &ctr->n_all, s.fin.as<Fin>(), ctr, 0);
         CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_B], st));
         launch_finalize_pairs(c, st, R, nullptr, nullptr, (unsigned)R.n, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(),
-                              s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), three, ctr, 1);
+                              s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), three, ctr, 1);
         launch_finalize_all(c, st, R, s.all_list.as<unsigned>(), &ctr->n_all, s.fin.as<Fin>(), three, 1);
         s.launches += 5;
     } else { CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_A], st)); CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_B], st)); }
@@ -366,7 +380,7 @@ void idp_ctx_destroy(idp_ctx *c) {
     cudaDeviceSynchronize();
     for (Slot &s : c->slots) {
         for (DevBuf *b : {&s.seq4, &s.seq_off, &s.len, &s.ref_idx, &s.ustart, &s.uend, &s.flags, &s.five, &s.three, &s.fall, &s.all_list,
-                          &s.seg_off, &s.seg_cnt, &s.pair_work, &s.pair_primer, &s.pair_score, &s.fin}) b->release();
+                          &s.seg_off, &s.seg_cnt, &s.pair_work, &s.pair_primer, &s.pair_score, &s.pair_se, &s.fin}) b->release();
         if (s.d_ctr) cudaFree(s.d_ctr);
         if (s.h_ctr) cudaFreeHost(s.h_ctr);
         for (auto &e : s.ev) if (e) cudaEventDestroy(e);

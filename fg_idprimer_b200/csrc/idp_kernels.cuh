@@ -124,40 +124,48 @@ __global__ void __launch_bounds__(256) cand5_kernel(DevPanel P, DevReads R, cons
     __syncwarp();
     const DevKmerIndex &ix = P.kidx[1];
     const unsigned n_work = ctr->n_fall;
-    const uint64_t kmask = ix.k >= 16 ? ~0ull : ((1ull << (4 * ix.k)) - 1ull);
     for (unsigned w = blockIdx.x * warps_per_block + wib; w < n_work; w += gridDim.x * warps_per_block) {
         const int r = (int)fall[w];
         const uint16_t fl = R.flags[r];
         const uint8_t *s; int len;
         read_geom(R, r, s, len);
         Oriented o{s, len, seq_order_is_rc(fl)};
-        const int end = len >= ix.k ? min(ix.window, len) - ix.k + 1 : 0;
+        const int end = len >= ix.k ? min(ix.window, len) - ix.k + 1 : 0;  // k-mers start at 0 .. end-1 (PM:110)
         unsigned base = 0, count = 0;
         for (int pass = 0; pass < 2; ++pass) {
             unsigned emitted = 0;
-            uint64_t key = 0;
-            for (int i = 0; i < end + ix.k - 1; ++i) {
-                key = ((key << 4) | o.nib(i)) & kmask;
-                if (i < ix.k - 1) continue;
-                OffCnt oc;
-                if (!kmer_lookup(ix, key, oc)) continue;
-                for (uint32_t j0 = 0; j0 < oc.cnt; j0 += 32) {
-                    const uint32_t j = j0 + lane;
-                    bool fresh = false;
-                    uint32_t p = 0;
-                    if (j < oc.cnt) {
-                        p = __ldg(&ix.postings[oc.off + j]);
-                        const uint32_t bit = 1u << (p & 31);
-                        if (pass == 0) fresh = !(atomicOr(&bitmap[p >> 5], bit) & bit);
-                        else fresh = (atomicAnd(&bitmap[p >> 5], ~bit) & bit) != 0;
+            for (int p0 = 0; p0 < end; p0 += 32) {
+                // every lane looks up the k-mer starting at its own position: one table latency per 32 positions
+                const int pos = p0 + lane;
+                OffCnt oc{0u, 0u};
+                if (pos < end) {
+                    uint64_t key = 0;
+                    for (int t = 0; t < ix.k; ++t) key = (key << 4) | o.nib(pos + t);
+                    if (!kmer_lookup(ix, key, oc)) oc.cnt = 0;
+                }
+                unsigned hits = __ballot_sync(0xffffffffu, oc.cnt > 0);
+                while (hits) {  // positions in ascending order = the order the reference visits them in
+                    const int src = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const uint32_t off = __shfl_sync(0xffffffffu, oc.off, src), cnt = __shfl_sync(0xffffffffu, oc.cnt, src);
+                    for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+                        const uint32_t j = j0 + lane;
+                        bool fresh = false;
+                        uint32_t p = 0;
+                        if (j < cnt) {
+                            p = __ldg(&ix.postings[off + j]);
+                            const uint32_t bit = 1u << (p & 31);
+                            if (pass == 0) fresh = !(atomicOr(&bitmap[p >> 5], bit) & bit);
+                            else fresh = (atomicAnd(&bitmap[p >> 5], ~bit) & bit) != 0;
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, fresh);
+                        if (pass == 1 && fresh && count != 0xffffffffu) {
+                            const unsigned at = base + emitted + __popc(m & ((1u << lane) - 1u));
+                            pair_work[at] = w;
+                            pair_primer[at] = p;
+                        }
+                        emitted += __popc(m);
                     }
-                    const unsigned m = __ballot_sync(0xffffffffu, fresh);
-                    if (pass == 1 && fresh && count != 0xffffffffu) {
-                        const unsigned at = base + emitted + __popc(m & ((1u << lane) - 1u));
-                        pair_work[at] = w;
-                        pair_primer[at] = p;
-                    }
-                    emitted += __popc(m);
                 }
             }
             if (pass == 0) {
@@ -318,6 +326,65 @@ __device__ int sw_score_generic(const DevPanel &P, const int32_t *__restrict__ s
     return best;
 }
 
+// Register-resident variant that also carries where each path started: every value is (score << 12) | start, so one
+// integer compare orders scores and the winner's start rides along.  Requires |scores| * (rows + columns) < 2^17
+// (DevPanel::packed_trace_ok) and targets shorter than 4096.  Tie rules are those of sw_trace() below.
+//   a.score >= b.score  <=>  (a | 0xFFF) >= b          a.score > b.score  <=>  a > (b | 0xFFF)
+struct TracedReg { int score, t_start, t_end; };
+
+template <int NQ, bool LOCAL>
+__device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint32_t *__restrict__ qwords, int n, int n_warp_max,
+                                                 const Oriented &T, int m) {
+    TracedReg out{0, 1, 0};
+    if (m == 0) { out.score = LOCAL ? 0 : P.gap_open + n * P.gap_extend; return out; }
+    const int oe = (P.gap_open + P.gap_extend) * 4096, e = P.gap_extend * 4096, ma = P.match_score * 4096, mi = P.mismatch_score * 4096;
+    constexpr int NEG = -(1 << 30);  // score -2^18
+    uint32_t q[(NQ + 7) / 8];
+#pragma unroll
+    for (int w = 0; w < (NQ + 7) / 8; ++w) q[w] = w < P.ww ? __ldg(&qwords[w]) : 0u;
+    int D[NQ], L[NQ], M[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        if (LOCAL) { D[i] = 0; L[i] = 0; M[i] = 0; }
+        else { D[i] = NEG; L[i] = NEG; M[i] = (P.gap_open + (i + 1) * P.gap_extend) * 4096; }  // Up(i,0), start 0
+    }
+    int best = NEG, bi = 0, bj = 0;
+    for (int j = 1; j <= m; ++j) {
+        const uint32_t t = T.nib(j - 1);
+        int mdiag = j - 1, d_up = j, u_up = j;  // row 0: score 0, path starts at this column
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            if (i >= n_warp_max) break;
+            if (i < n) {
+                const uint32_t qc = (q[i >> 3] >> (4 * (i & 7))) & 15u;
+                int dn = mdiag + (qc == t ? ma : mi);
+                if (LOCAL && dn < 0) dn = j;  // clamp at zero: the path (re)starts after this cell
+                int un, ln;
+                { const int a = d_up + oe, b = u_up + e; un = ((a | 0xFFF) >= b) ? a : b; }  // Diagonal preferred over extending Up
+                { const int a = D[i] + oe, b = L[i] + e; ln = ((a | 0xFFF) >= b) ? a : b; }  // Diagonal preferred over extending Left
+                int mn = dn;                                                                  // Diagonal, then Left, then Up
+                if (ln > (mn | 0xFFF)) mn = ln;
+                if (un > (mn | 0xFFF)) mn = un;
+                mdiag = M[i];
+                D[i] = dn; L[i] = ln; M[i] = mn;
+                d_up = dn; u_up = un;
+                if (LOCAL) {
+                    // best cell: lowest row, then lowest column.  Left/Up values never win: each is bounded by a Diagonal
+                    // value of a cell scanned earlier (gap scores are <= 0), and ties go to the earlier cell.
+                    const int ds = dn >> 12, bs = best >> 12;
+                    if (ds > bs || (ds == bs && i + 1 < bi)) { best = dn; bi = i + 1; bj = j; }
+                } else if (i == n - 1) {
+                    // last row, columns ascending, Diagonal / Left / Up, strict '>': Left(n,j) <= an earlier Diagonal(n,j')
+                    if (dn > (best | 0xFFF)) { best = dn; bj = j; }
+                    if (un > (best | 0xFFF)) { best = un; bj = j; }
+                }
+            }
+        }
+    }
+    out.score = best >> 12; out.t_start = (best & 0xFFF) + 1; out.t_end = bj;
+    return out;
+}
+
 // the target of one (read, primer) task: 5' = read prefix of |primer|+slop bases in sequencing order (PM:292-293);
 // 3' = reverse complement of the whole read in sequencing order (IP:502-506)
 __device__ __forceinline__ Oriented make_target(const DevPanel &P, const DevReads &R, int r, int primer_seq_len, bool three_prime, int &m) {
@@ -331,11 +398,11 @@ __device__ __forceinline__ Oriented make_target(const DevPanel &P, const DevRead
 
 constexpr int32_t kScoreMissing = INT32_MIN;  // pair touched a base pair the scoring matrix has no entry for
 
-template <int NQ, bool LOCAL, bool SMAT>
+template <int NQ, bool LOCAL, bool SMAT, bool TRACE>
 __global__ void __launch_bounds__(128) sw_pairs_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
                                                        Counters *ctr, const unsigned int *__restrict__ pair_work,
                                                        const unsigned int *__restrict__ pair_primer, int *__restrict__ pair_score,
-                                                       unsigned int pair_cap) {
+                                                       unsigned int *__restrict__ pair_se, unsigned int pair_cap) {
     __shared__ int32_t smat_s[256];
     if (SMAT) { for (int i = threadIdx.x; i < 256; i += blockDim.x) smat_s[i] = P.smat[i]; __syncthreads(); }
     // after an overflow the counter runs past the buffer and slots below pair_cap may hold stale entries: clamp and
@@ -362,7 +429,11 @@ __global__ void __launch_bounds__(128) sw_pairs_kernel(DevPanel P, DevReads R, c
         if (active) {
             bool missing = false;
             int sc;
-            if (NQ > 0) sc = sw_score<(NQ > 0 ? NQ : 8), LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, n_warp_max, T, m, missing);
+            if (TRACE) {  // few candidates per read: carry the start column too, so no second alignment is needed
+                const TracedReg tr = sw_trace_reg<(NQ > 0 ? NQ : 8), LOCAL>(P, P.pmask + (size_t)p * P.ww, n, n_warp_max, T, m);
+                sc = tr.score;
+                pair_se[t] = ((unsigned)tr.t_start & 0xFFFFu) | ((unsigned)tr.t_end << 16);
+            } else if (NQ > 0) sc = sw_score<(NQ > 0 ? NQ : 8), LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, n_warp_max, T, m, missing);
             else sc = sw_score_generic<LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, T, m, missing);
             pair_score[t] = missing ? kScoreMissing : sc;
             cells += (unsigned long long)n * (unsigned long long)m;
@@ -515,17 +586,30 @@ __device__ Traced sw_trace(const DevPanel &P, const uint32_t *__restrict__ qword
     return out;
 }
 
-// getBestGappedAlignment (PM:305-328) + GappedAlignmentPrimerMatch requires (PMa:113-114) + the score-rate filter (IP:464-469)
-template <int TN>
-__device__ void finish_gapped(const DevPanel &P, const DevReads &R, int r, const Fin &f, bool three_prime, idp_result *__restrict__ out) {
+// getBestGappedAlignment (PM:305-328) + GappedAlignmentPrimerMatch requires (PMa:113-114) + the score-rate filter (IP:464-469).
+// `pre` (score, start, end) is the winner's traceback-equivalent when a kernel already produced it, else it is computed here:
+// NQ > 0 selects the register-resident re-alignment, otherwise the generic one with TN rows in local memory.
+template <int TN, int NQ>
+__device__ void finish_gapped(const DevPanel &P, const DevReads &R, int r, const Fin &f, bool three_prime, const TracedReg *pre,
+                              idp_result *__restrict__ out) {
     idp_result res = none_result();
     if (f.count > 0) {
         if (f.raw == kScoreMissing) res.status = IDP_STATUS_SCORE_MISSING;
         else if (!(f.count == 1 && f.raw < 0)) {  // PM:314
-            int m;
-            const int n = __ldg(&P.pinfo[f.primer]).w;
-            Oriented T = make_target(P, R, r, n, three_prime, m);
-            const Traced tr = sw_trace<TN>(P, P.pmask + (size_t)f.primer * P.ww, n, T, m, three_prime ? IDP_MODE_LOCAL : IDP_MODE_GLOCAL);
+            TracedReg tr;
+            if (pre) tr = *pre;
+            else {
+                int m;
+                const int n = __ldg(&P.pinfo[f.primer]).w;
+                Oriented T = make_target(P, R, r, n, three_prime, m);
+                const uint32_t *qw = P.pmask + (size_t)f.primer * P.ww;
+                if (NQ > 0 && P.packed_trace_ok) {
+                    tr = three_prime ? sw_trace_reg<(NQ > 0 ? NQ : 8), true>(P, qw, n, n, T, m) : sw_trace_reg<(NQ > 0 ? NQ : 8), false>(P, qw, n, n, T, m);
+                } else {
+                    const Traced g = sw_trace<TN>(P, qw, n, T, m, three_prime ? IDP_MODE_LOCAL : IDP_MODE_GLOCAL);
+                    tr.score = g.score; tr.t_start = g.t_start; tr.t_end = g.t_end;
+                }
+            }
             res.primer = f.primer; res.type = IDP_GAPPED; res.multi = f.count > 1;
             res.raw_score = tr.score; res.q_len = f.qlen;
             res.raw_next = f.count > 1 ? f.raw_next : 0; res.q_len_next = f.count > 1 ? f.qlen_next : 0;
@@ -538,17 +622,17 @@ __device__ void finish_gapped(const DevPanel &P, const DevReads &R, int r, const
             if (!(rate >= P.min_alignment_score_rate)) { const uint8_t st = res.status; res = none_result(); res.status = st; }
         }
     }
-    // a read that reached the gapped stage keeps a require-failure recorded by the ungapped stage (none can exist: it had no match)
     write_result(&out[r], res);
 }
 
 // pair mode: one thread per work item picks the best two of its segment, then finishes
-template <int TN>
+template <int TN, int NQ>
 __global__ void __launch_bounds__(128) finalize_pairs_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
                                                              const unsigned int *__restrict__ n_work_ptr, unsigned int n_work_fixed,
                                                              const unsigned int *__restrict__ seg_off, const int *__restrict__ seg_cnt,
                                                              const unsigned int *__restrict__ pair_primer, const int *__restrict__ pair_score,
-                                                             idp_result *__restrict__ out, Counters *__restrict__ ctr_out, int three_prime) {
+                                                             const unsigned int *__restrict__ pair_se, idp_result *__restrict__ out,
+                                                             Counters *__restrict__ ctr_out, int three_prime) {
     const unsigned n_work = n_work_ptr ? *n_work_ptr : n_work_fixed;
     unsigned long long aligned = 0;
     for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
@@ -557,6 +641,7 @@ __global__ void __launch_bounds__(128) finalize_pairs_kernel(DevPanel P, DevRead
         const int r = work_read ? (int)work_read[w] : (int)w;
         Fin f;
         f.count = cnt; f.primer = -1; f.raw = 0; f.raw_next = 0; f.qlen = 0; f.qlen_next = 0;
+        TracedReg pre{0, 1, 0};
         if (cnt > 0) {
             GBest2 g;
             bool missing = false;
@@ -569,8 +654,9 @@ __global__ void __launch_bounds__(128) finalize_pairs_kernel(DevPanel P, DevRead
             f.primer = g.b_primer; f.raw = missing ? kScoreMissing : g.b_score; f.qlen = (int16_t)g.b_qlen;
             f.raw_next = g.s_ord >= 0 ? g.s_score : 0; f.qlen_next = (int16_t)(g.s_ord >= 0 ? g.s_qlen : 0);
             aligned += (unsigned)cnt;
+            if (pair_se) { const unsigned se = pair_se[o + g.b_ord]; pre.score = g.b_score; pre.t_start = (int)(se & 0xFFFFu); pre.t_end = (int)(se >> 16); }
         }
-        finish_gapped<TN>(P, R, r, f, three_prime != 0, out);
+        finish_gapped<TN, NQ>(P, R, r, f, three_prime != 0, pair_se ? &pre : nullptr, out);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) aligned += __shfl_xor_sync(0xffffffffu, aligned, d);
@@ -578,13 +664,13 @@ __global__ void __launch_bounds__(128) finalize_pairs_kernel(DevPanel P, DevRead
 }
 
 // all-primers mode: sw_all_kernel left one Fin per work item
-template <int TN>
+template <int TN, int NQ>
 __global__ void __launch_bounds__(128) finalize_all_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
                                                            const unsigned int *__restrict__ n_work_ptr, const Fin *__restrict__ fin,
                                                            idp_result *__restrict__ out, int three_prime) {
     const unsigned n_work = *n_work_ptr;
     for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x)
-        finish_gapped<TN>(P, R, (int)work_read[w], fin[w], three_prime != 0, out);
+        finish_gapped<TN, NQ>(P, R, (int)work_read[w], fin[w], three_prime != 0, nullptr, out);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
