@@ -75,7 +75,7 @@ struct idp_ctx {
     int device = 0, sm_count = 148;
     DevPanel dp{};
     DevBuf b_pmask, b_pinfo, b_positive, b_loc_key[2], b_loc_primer[2], b_mate_off, b_mate_idx, b_smat;
-    DevBuf b_keys[2], b_offcnt[2], b_postings[2], b_heads[2], b_direct[2];
+    DevBuf b_keys[2], b_offcnt[2], b_postings[2], b_heads[2], b_direct[2], b_bsmm, b_bsacc;
     Slot slots[kSlots];
     cudaStream_t user_stream = nullptr;
     idp_timings last{};
@@ -126,6 +126,9 @@ static int upload_panel(idp_ctx *c) {
             if (!h.direct.empty()) { if ((rc = upload(h.direct, c->b_direct[w]))) return rc; k.direct = c->b_direct[w].as<uint32_t>(); }
         }
     }
+    if ((rc = upload(p.bs_mm, c->b_bsmm)) || (rc = upload(p.bs_acc, c->b_bsacc))) return rc;
+    d.bs_mm = c->b_bsmm.as<uint32_t>(); d.bs_acc = c->b_bsacc.as<uint2>(); d.bs_groups = (p.n + 31) / 32;
+    d.bs_ok = p.acc_max <= 1 && p.window_bases <= 64;
     if ((rc = upload(p.mate_off, c->b_mate_off))) return rc;
     if ((rc = upload(p.mate_idx, c->b_mate_idx))) return rc;
     d.mate_off = c->b_mate_off.as<int32_t>(); d.mate_idx = c->b_mate_idx.as<int32_t>();
@@ -145,19 +148,21 @@ static int upload_panel(idp_ctx *c) {
     return IDP_OK;
 }
 
-template <int RW>
-static int launch_scan(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp_result *five, unsigned *fall, Counters *ctr) {
-    // shared-memory plan: the read tile first, then as much of the panel side as fits in half an SM (two CTAs per SM)
+template <int RW, bool FAST>
+static int launch_scan_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp_result *five, unsigned *fall, Counters *ctr) {
+    // shared-memory plan: the per-warp read tiles first (two buffers each), then as much of the panel side as fits in half
+    // an SM (two CTAs per SM)
     ScanLaunch S{};
     const DevKmerIndex &ix = c->dp.kidx[0];
     const size_t budget = 110 * 1024;
     size_t used = 0;
     S.stride = R.fixed_len > 0 ? (uint32_t)((R.fixed_len + 1) >> 1) : 0;
-    // per-warp tiles of 32 reads: 32 * stride must stay a multiple of 16 bytes for the TMA bulk copy (it is: 32 * stride)
-    S.stage_tile = R.fixed_len > 0 && (reinterpret_cast<uintptr_t>(R.seq4) & 15) == 0 && S.stride <= 1024;
+    // a warp tile is 32 reads: 32 * stride bytes, always a multiple of 16 as the TMA bulk copy requires
+    S.stage_tile = R.fixed_len > 0 && (reinterpret_cast<uintptr_t>(R.seq4) & 15) == 0;
     if (S.stage_tile) {
         S.tile_smem_bytes = (uint32_t)((32 * (size_t)S.stride + 4 * RW + 16 + 15) & ~size_t(15));
-        used = (size_t)S.tile_smem_bytes * (kScanThreads / 32);
+        used = (size_t)S.tile_smem_bytes * 2 * kScanWarps;
+        if (used > budget - 16 * 1024) { S.stage_tile = 0; S.tile_smem_bytes = 0; used = 0; }
     }
     auto place = [&](size_t bytes, bool wanted) -> uint32_t {
         bytes = (bytes + 15) & ~size_t(15);
@@ -167,19 +172,25 @@ static int launch_scan(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp
         return off;
     };
     S.direct_entries = ix.direct ? (1u << (2 * ix.k)) : 0;
-    S.off_direct = place((size_t)S.direct_entries * 4, ix.direct != nullptr);
+    S.off_bsacc = place((size_t)c->dp.bs_groups * sizeof(uint2), FAST);
+    S.off_bsmm = place((size_t)c->dp.bs_groups * kBsPositions * 16 * 4, FAST);
+    S.off_direct = place((size_t)S.direct_entries * 4, !FAST && ix.direct != nullptr);
     S.off_pinfo = place((size_t)c->dp.n_primers * sizeof(int4), true);
     S.off_pmask = place((size_t)c->dp.n_primers * c->dp.ww * 4, true);
-    S.off_heads = place((size_t)ix.n_postings * 8, ix.k > 0);
+    S.off_heads = place((size_t)ix.n_postings * 8, !FAST && ix.k > 0);
     const int n_tiles = (R.n + kScanThreads - 1) / kScanThreads;
     const int grid = std::max(1, std::min(n_tiles, 2 * c->sm_count));
-    if (used > budget) { S.stage_tile = 0; used = 0; }
-    if (cudaFuncSetAttribute(scan_kernel<RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) {
+    if (cudaFuncSetAttribute(scan_kernel<RW, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) {
         set_error("cudaFuncSetAttribute(scan_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
         return IDP_ERR_CUDA;
     }
-    scan_kernel<RW><<<grid, kScanThreads, used, st>>>(c->dp, R, S, five, fall, ctr);
+    scan_kernel<RW, FAST><<<grid, kScanThreads, used, st>>>(c->dp, R, S, five, fall, ctr);
     return IDP_OK;
+}
+template <int RW>
+static int launch_scan(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp_result *five, unsigned *fall, Counters *ctr) {
+    if (RW <= 8 && c->dp.bs_ok && !getenv("IDP_SCAN_EXACT_WALK")) return launch_scan_t<(RW <= 8 ? RW : 8), true>(c, st, R, five, fall, ctr);
+    return launch_scan_t<RW, false>(c, st, R, five, fall, ctr);
 }
 
 // the pair kernel also produces the traceback-equivalent (start, end) when the packed register variant applies
@@ -388,7 +399,7 @@ void idp_ctx_destroy(idp_ctx *c) {
     }
     for (DevBuf *b : {&c->b_pmask, &c->b_pinfo, &c->b_positive, &c->b_loc_key[0], &c->b_loc_key[1], &c->b_loc_primer[0], &c->b_loc_primer[1],
                       &c->b_mate_off, &c->b_mate_idx, &c->b_smat, &c->b_keys[0], &c->b_keys[1], &c->b_offcnt[0], &c->b_offcnt[1],
-                      &c->b_postings[0], &c->b_postings[1], &c->b_heads[0], &c->b_heads[1], &c->b_direct[0], &c->b_direct[1]}) b->release();
+                      &c->b_postings[0], &c->b_postings[1], &c->b_heads[0], &c->b_heads[1], &c->b_direct[0], &c->b_direct[1], &c->b_bsmm, &c->b_bsacc}) b->release();
     delete c;
 }
 

@@ -50,6 +50,12 @@ struct DevPanel {
     const int32_t *loc_primer[2];
     int32_t n_loc[2];
     DevKmerIndex kidx[2];      // 0: ungapped matcher (-k), 1: gapped matcher (-K)
+    // bit-sliced ungapped filter: primers in groups of 32 (file order); bs_mm[(g*16 + i)*16 + nib] has bit b set when read
+    // code `nib` at position i mismatches primer 32g+b (PM:143); bs_acc[g] = {primers accepting >= 0 mismatches, >= 1 mismatch}
+    const uint32_t *bs_mm;
+    const uint2 *bs_acc;
+    int32_t bs_groups;
+    int32_t bs_ok;             // every primer accepts at most one mismatch, so two bit planes decide the filter
     // pair_id groups for 3' matching (IP:496): opposite-strand primers of the same pair, file order
     const int32_t *mate_off;   // [n+1]
     const int32_t *mate_idx;
@@ -87,5 +93,7 @@ struct idp_panel {
     std::vector<int32_t> loc_primer[2];
     std::vector<int32_t> mate_off, mate_idx;
     std::vector<int32_t> smat16;              // 16*16 nibble scoring table or empty
+    std::vector<uint32_t> bs_mm, bs_acc;      // bit-sliced filter tables (see DevPanel)
+    int32_t acc_max = -1;
     idp::KmerIndexHost kidx[2];
 };

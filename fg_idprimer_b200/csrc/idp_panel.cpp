@@ -305,6 +305,23 @@ int idp_panel_create(const idp_primer *primers, int32_t n, const idp_params *par
         for (int mm = 0; mm <= p->seq_len[i]; ++mm) { if (mm / (double)length <= rate) acc = mm; else break; }
         p->acc_full.push_back(acc);
     }
+    // bit-sliced filter over the first 16 bases, 32 primers per word
+    {
+        const int groups = (n + 31) / 32;
+        p->bs_mm.assign((size_t)groups * 16 * 16, 0);
+        p->bs_acc.assign((size_t)groups * 2, 0);
+        for (int i = 0; i < n; ++i) {
+            const int g = i / 32, b = i % 32;
+            p->acc_max = std::max(p->acc_max, p->acc_full[i]);
+            if (p->acc_full[i] >= 0) p->bs_acc[2 * g] |= 1u << b;
+            if (p->acc_full[i] >= 1) p->bs_acc[2 * g + 1] |= 1u << b;
+            for (int pos = 0; pos < 16; ++pos) {
+                const uint32_t mask = pos < p->seq_len[i] ? (uint32_t)base_to_nibble((unsigned char)p->sequence[i][pos]) : 0xFu;
+                for (uint32_t nib = 0; nib < 16; ++nib)
+                    if (nib & ~mask) p->bs_mm[((size_t)g * 16 + pos) * 16 + nib] |= 1u << b;
+            }
+        }
+    }
     // location matcher (PM:162-172): one sorted array per strand
     for (int strand = 0; strand < 2; ++strand) {  // 0 = positive, 1 = negative
         std::vector<int> ids;

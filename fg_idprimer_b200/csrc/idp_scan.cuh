@@ -3,23 +3,32 @@
 //   basesInSequencingOrder (PM:39-45) . LocationBasedPrimerMatcher.find (PM:194-213) . getPrimersForAlignmentTasks
 //   (PM:98-116) . mismatchAlign / numMismatches (PM:128-147) . getBestUngappedAlignment (PM:237-248)
 //
-// Persistent CTAs of kScanThreads threads walk tiles of kScanThreads reads.  A tile's packed bases (75 B per 150 bp
-// read) are brought into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier); two CTAs per SM overlap one
-// tile's copy with the other's compute.  The panel side lives in shared memory as far as it fits: a direct-address
-// table over the 4^k all-ACGT k-mers, posting lists whose entries carry the first 8 primer bases and the accept
-// threshold (a candidate is rejected from one 8-byte entry in the common case), the primer masks and thresholds.
+// Persistent CTAs; every warp walks its own tiles of 32 reads.  A tile's packed bases (2400 B for 150 bp reads) arrive in
+// shared memory by one TMA bulk copy (cp.async.bulk + mbarrier), double-buffered per warp, so no CTA-wide barrier exists
+// after the prologue.  The panel side sits in shared memory as far as it fits.
+//
+// Two ways to find the accepted primers of a read, both exact:
+//  * bit-sliced (DevPanel::bs_ok: every primer tolerates at most one mismatch): the read's first 16 bases index precomputed
+//    32-primer mismatch bit-vectors; two bit planes (seen one / seen two mismatches) decide 32 primers per instruction with no
+//    divergence.  The few survivors get the full mismatchAlign.  The k-mer rule is then applied to what was ACCEPTED: no
+//    accepted primer -> no match whatever the candidates were; one -> it only has to be a candidate (a run of k equal
+//    letters on the diagonal proves it, else an exact membership walk); two or more -> the exact walk below decides order.
+//  * exact walk (any thresholds): read k-mers in order, posting lists in the reference's Set iteration order, an 8-byte
+//    posting head rejects most candidates, survivors are evaluated after the loop in first-hit order.
 #pragma once
 
 namespace idp {
 
 constexpr int kScanThreads = 512;
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kBsPositions = 16;
 
 struct ScanLaunch {
     int32_t stage_tile;        // 1: reads are fixed-length and 16-byte aligned: tiles are staged into shared memory by TMA
     uint32_t stride;           // bytes per read when fixed-length
-    uint32_t tile_smem_bytes;  // shared-memory bytes reserved for the tile (incl. slack), multiple of 16
+    uint32_t tile_smem_bytes;  // shared-memory bytes of one warp tile buffer (incl. slack), multiple of 16
     // byte offsets into dynamic shared memory, or 0xFFFFFFFF when the structure stays in global memory
-    uint32_t off_direct, off_heads, off_pmask, off_pinfo;
+    uint32_t off_direct, off_heads, off_pmask, off_pinfo, off_bsmm, off_bsacc;
     uint32_t direct_entries;
 };
 
@@ -53,6 +62,12 @@ __device__ __forceinline__ uint32_t nib_nonzero(uint32_t x) {
     x |= x >> 2;
     return x & 0x11111111u;
 }
+// bits 0,4,...,28 -> bits 0..7
+__device__ __forceinline__ uint32_t gather_nibble_bits(uint32_t z) {
+    z = (z | (z >> 3)) & 0x03030303u;
+    z = (z | (z >> 6)) & 0x000F000Fu;
+    return (z | (z >> 12)) & 0xFFu;
+}
 
 struct Best2 {  // getBestUngappedAlignment (PM:237-248) as a running stable top-2 on key = mm / Primer.length
     int bp = -1, bmm = 0, sp = -1, smm = 0;
@@ -68,7 +83,7 @@ struct ScanCtx {
     uint32_t win[RW];  // read prefix in sequencing order, base i in nibble i, zero beyond the read
     int len;
     unsigned compares;
-    const uint32_t *pmask;  // generic pointers: shared or global
+    const uint32_t *pmask;  // shared or global
     const int4 *pinfo;
 };
 
@@ -139,25 +154,99 @@ __device__ __forceinline__ void walk_postings(const DevPanel &P, ScanCtx<RW> &c,
     c.compares += 8u * cnt;
 }
 
+// The reference's candidate walk (PM:108-116) with the accept test applied on the fly: read k-mers left to right, each
+// k-mer's primers in Set iteration order, first occurrence wins ties.
 template <int RW>
+__device__ __noinline__ void kmer_scan_exact(const DevPanel &P, ScanCtx<RW> &c, Best2 &best, const uint32_t *direct, const uint2 *heads) {
+    const DevKmerIndex &ix = P.kidx[0];
+    const int n_bases = min(ix.window, c.len);  // k-mers start at 0 .. n_bases - k
+    Pending<RW> pend;
+    uint32_t sr[RW];  // shift register over the window: the next base is always the low nibble of sr[0]
+#pragma unroll
+    for (int w = 0; w < RW; ++w) sr[w] = c.win[w];
+    const uint64_t kmask4 = ix.k >= 16 ? ~0ull : ((1ull << (4 * ix.k)) - 1ull);
+    const uint32_t kmask2 = ix.k >= 16 ? ~0u : ((1u << (2 * ix.k)) - 1u);
+    uint64_t key4 = 0;
+    uint32_t key2 = 0;
+    int bad = 0;  // > 0 while the current k-mer holds a nibble that is not exactly one of A/C/G/T
+    for (int i = 0; i < n_bases; ++i) {
+        const uint32_t nib = sr[0] & 15u;
+#pragma unroll
+        for (int w = 0; w < RW - 1; ++w) sr[w] = __funnelshift_r(sr[w], sr[w + 1], 4);
+        sr[RW - 1] >>= 4;
+        key4 = ((key4 << 4) | nib) & kmask4;
+        key2 = ((key2 << 2) | ((0x30210u >> (2 * nib)) & 3u)) & kmask2;  // A,C,G,T (1,2,4,8) -> 0..3
+        bad = max(bad - 1, 0);
+        if (__popc(nib) != 1) bad = ix.k;
+        if (i < ix.k - 1) continue;
+        if (direct != nullptr && bad == 0) {
+            const uint32_t e = direct[key2];
+            if (e) walk_postings<RW>(P, c, best, pend, heads, e & 0xFFFFFu, e >> 20);
+        } else {  // literal equality of IUPAC letters (PM:113): the full table, keyed by 4 bits per base
+            OffCnt oc;
+            if (kmer_lookup(ix, key4, oc)) walk_postings<RW>(P, c, best, pend, direct != nullptr ? ix.heads : heads, oc.off, oc.cnt);
+        }
+    }
+    pend.flush(P, c, best);
+}
+
+// Is primer p among getPrimersForAlignmentTasksWithCommonKmer(read) (PM:108-116)?  Exact, by walking the read's k-mers.
+template <int RW>
+__device__ __noinline__ bool kmer_member_exact(const DevPanel &P, const ScanCtx<RW> &c, int p) {
+    const DevKmerIndex &ix = P.kidx[0];
+    const int n_bases = min(ix.window, c.len);
+    const uint64_t kmask4 = ix.k >= 16 ? ~0ull : ((1ull << (4 * ix.k)) - 1ull);
+    uint64_t key4 = 0;
+    for (int i = 0; i < n_bases; ++i) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int w = 0; w < RW; ++w) if ((i >> 3) == w) word = c.win[w];
+        key4 = ((key4 << 4) | ((word >> (4 * (i & 7))) & 15u)) & kmask4;
+        OffCnt oc;
+        if (i >= ix.k - 1 && kmer_lookup(ix, key4, oc))
+            for (uint32_t j = 0; j < oc.cnt; ++j) if ((int)__ldg(&ix.postings[oc.off + j]) == p) return true;
+    }
+    return false;
+}
+
+// A run of k literally equal letters at the same offset in read and primer (inside both the search window and the primer)
+// proves that the primer shares a k-mer with the read.  Nibble codes are letters: equal code <=> equal letter.
+template <int RW>
+__device__ __forceinline__ bool diagonal_kmer(const DevPanel &P, const ScanCtx<RW> &c, int p, int seq_len, int k, int n_bases) {
+    const uint32_t *pm = c.pmask + (size_t)p * P.ww;
+    uint64_t eq = 0;
+#pragma unroll
+    for (int w = 0; w < RW; ++w)
+        if (w < P.ww && w < 8) eq |= (uint64_t)gather_nibble_bits(~nib_nonzero(c.win[w] ^ pm[w]) & 0x11111111u) << (8 * w);
+    const int lim = min(min(n_bases, seq_len), 64);
+    if (lim < k) return false;
+    if (lim < 64) eq &= (1ull << lim) - 1ull;
+    uint64_t run = eq;
+    for (int t = 1; t < k; ++t) run &= eq >> t;
+    return run != 0ull;
+}
+
+template <int RW, bool FAST>
 __global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(DevPanel P, DevReads R, ScanLaunch S, idp_result *__restrict__ five,
                                                                unsigned int *__restrict__ fall, Counters *__restrict__ ctr) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ __align__(8) uint64_t tile_bar[kScanThreads / 32];
+    __shared__ __align__(8) uint64_t tile_bar[kScanWarps][2];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const DevKmerIndex &ix = P.kidx[0];
     // ---- panel-side tables into shared memory (once per persistent CTA) ----
     const uint32_t *direct = ix.direct;
     const uint2 *heads = ix.heads;
+    const uint32_t *bs_mm = P.bs_mm;
+    const uint2 *bs_acc = P.bs_acc;
     ScanCtx<RW> c;
     c.pmask = P.pmask;
     c.pinfo = P.pinfo;
-    if (S.off_direct != 0xFFFFFFFFu) {
+    if (!FAST && S.off_direct != 0xFFFFFFFFu) {
         uint32_t *d = reinterpret_cast<uint32_t *>(smem + S.off_direct);
         for (uint32_t i = tid; i < S.direct_entries; i += blockDim.x) d[i] = ix.direct[i];
         direct = d;
     }
-    if (S.off_heads != 0xFFFFFFFFu) {
+    if (!FAST && S.off_heads != 0xFFFFFFFFu) {
         uint2 *d = reinterpret_cast<uint2 *>(smem + S.off_heads);
         for (uint32_t i = tid; i < ix.n_postings; i += blockDim.x) d[i] = ix.heads[i];
         heads = d;
@@ -172,34 +261,49 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(DevPanel P, DevRe
         for (int i = tid; i < P.n_primers; i += blockDim.x) d[i] = P.pinfo[i];
         c.pinfo = d;
     }
+    if (FAST && S.off_bsmm != 0xFFFFFFFFu) {
+        uint32_t *d = reinterpret_cast<uint32_t *>(smem + S.off_bsmm);
+        for (int i = tid; i < P.bs_groups * kBsPositions * 16; i += blockDim.x) d[i] = P.bs_mm[i];
+        bs_mm = d;
+    }
+    if (FAST && S.off_bsacc != 0xFFFFFFFFu) {
+        uint2 *d = reinterpret_cast<uint2 *>(smem + S.off_bsacc);
+        for (int i = tid; i < P.bs_groups; i += blockDim.x) d[i] = P.bs_acc[i];
+        bs_acc = d;
+    }
     if (S.stage_tile && lane == 0) {
-        mbar_init(&tile_bar[wib], 1);
+        mbar_init(&tile_bar[wib][0], 1);
+        mbar_init(&tile_bar[wib][1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     // ---- every warp walks its own 32-read tiles: no CTA-wide barrier from here on ----
-    unsigned char *wtile = smem + (size_t)wib * S.tile_smem_bytes;
-    uint32_t parity = 0;
+    unsigned char *wbuf[2] = {smem + (size_t)(2 * wib) * S.tile_smem_bytes, smem + (size_t)(2 * wib + 1) * S.tile_smem_bytes};
+    uint32_t phase[2] = {0u, 0u};
     const int n_wtiles = (R.n + 31) / 32;
-    const int warps_total = gridDim.x * (kScanThreads / 32);
+    const int warps_total = gridDim.x * kScanWarps;
     unsigned long long compares_total = 0;
-    for (int wt = blockIdx.x * (kScanThreads / 32) + wib; wt < n_wtiles; wt += warps_total) {
+    auto issue_tile = [&](int wt, int b) {  // this warp's 32 reads: one TMA bulk copy + a tail shorter than 16 bytes
+        const size_t g0 = (size_t)wt * 32 * S.stride;
+        const uint32_t bytes = (uint32_t)min(32, R.n - wt * 32) * S.stride;
+        const uint32_t bulk = bytes & ~15u;
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&tile_bar[wib][b], bulk);
+            if (bulk) tma_load_1d(wbuf[b], R.seq4 + g0, bulk, &tile_bar[wib][b]);
+        }
+        if (lane < (int)(bytes - bulk)) wbuf[b][bulk + lane] = R.seq4[g0 + bulk + lane];
+    };
+    int cur = 0;
+    const int wt0 = blockIdx.x * kScanWarps + wib;
+    if (S.stage_tile && wt0 < n_wtiles) issue_tile(wt0, 0);
+    for (int wt = wt0; wt < n_wtiles; wt += warps_total) {
         const int r = wt * 32 + lane;
         const bool active = r < R.n;
         if (S.stage_tile) {
-            // this warp's 32 reads (2400 B for 150 bp): one TMA bulk copy + a tail shorter than 16 bytes
-            const size_t g0 = (size_t)wt * 32 * S.stride;
-            const uint32_t bytes = (uint32_t)min(32, R.n - wt * 32) * S.stride;
-            const uint32_t bulk = bytes & ~15u;
-            __syncwarp();  // all lanes are done reading the previous tile
-            if (lane == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&tile_bar[wib], bulk);
-                if (bulk) tma_load_1d(wtile, R.seq4 + g0, bulk, &tile_bar[wib]);
-            }
-            if (lane < (int)(bytes - bulk)) wtile[bulk + lane] = R.seq4[g0 + bulk + lane];
-            mbar_wait(&tile_bar[wib], parity);
-            parity ^= 1u;
+            if (wt + warps_total < n_wtiles) issue_tile(wt + warps_total, cur ^ 1);  // prefetch; that buffer was released below
+            mbar_wait(&tile_bar[wib][cur], phase[cur]);
+            phase[cur] ^= 1u;
             __syncwarp();  // tail bytes visible
         }
         bool need_gapped = false;
@@ -209,7 +313,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(DevPanel P, DevRe
             const uint8_t *s;
             read_geom(R, r, s, c.len);
             const bool rc = seq_order_is_rc(fl);
-            const uint8_t *sp = S.stage_tile ? wtile + (size_t)lane * S.stride : s;  // generic pointer: shared or global
+            const uint8_t *sp = S.stage_tile ? wbuf[cur] + (size_t)lane * S.stride : s;  // shared or global
             // ---- basesInSequencingOrder (PM:39-45), only the prefix the matchers can look at ----
             if (!rc && ((c.len + 1) >> 1) >= 4 * RW + 4) {
                 const uintptr_t a = reinterpret_cast<uintptr_t>(sp);
@@ -264,43 +368,66 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(DevPanel P, DevRe
                 }
             }
             // ---- UngappedAlignmentBasedPrimerMatcher.find (PM:230-248) ----
-            if (res.type == IDP_NONE) {
+            if (res.type == IDP_NONE && !(ix.k > 0 && c.len < ix.k)) {  // PM:109: a read shorter than k has no candidates
                 Best2 best;
-                if (ix.k <= 0) {  // PM:100: every primer, file order
+                if (FAST) {
+                    // survivors of the 16-base bit-sliced filter, ascending primer index (file order)
+                    uint32_t nx[kBsPositions];
+#pragma unroll
+                    for (int i = 0; i < kBsPositions; ++i) nx[i] = (i >> 3) < RW ? ((c.win[(i >> 3) < RW ? (i >> 3) : 0] >> (4 * (i & 7))) & 15u) : 0u;
+                    int n_acc = 0, a_p = -1, a_mm = 0, a_plen = 1, a_seq = 0;
+                    int q0 = -1, q1 = -1, q2 = -1, q3 = -1;
+                    auto evaluate = [&](int p) {
+                        int mm, plen;
+                        if (mismatch_align<RW>(P, c, p, mm, plen)) {
+                            if (ix.k <= 0) best.offer(p, mm, __ddiv_rn((double)mm, (double)plen));  // PM:100: file order
+                            else if (n_acc == 0) { a_p = p; a_mm = mm; a_plen = plen; a_seq = c.pinfo[p].w; }
+                            ++n_acc;
+                        }
+                    };
+                    auto flush = [&]() {
+                        if (q0 >= 0) evaluate(q0);
+                        if (q1 >= 0) evaluate(q1);
+                        if (q2 >= 0) evaluate(q2);
+                        if (q3 >= 0) evaluate(q3);
+                        q0 = q1 = q2 = q3 = -1;
+                    };
+                    for (int g = 0; g < P.bs_groups; ++g) {
+                        const uint32_t *row = bs_mm + (size_t)g * (kBsPositions * 16);
+                        uint32_t ones = 0, twos = 0;
+#pragma unroll
+                        for (int i = 0; i < kBsPositions; ++i) {
+                            const uint32_t v = row[i * 16 + nx[i]];
+                            twos |= ones & v;
+                            ones |= v;
+                        }
+                        const uint2 a = bs_acc[g];
+                        uint32_t surv = a.x & ~twos & (~ones | a.y);  // at most acc (0 or 1) mismatches in the first 16 bases
+                        while (surv) {
+                            const int p = g * 32 + __ffs(surv) - 1;
+                            surv &= surv - 1;
+                            if (q3 >= 0) flush();
+                            if (q0 < 0) q0 = p; else if (q1 < 0) q1 = p; else if (q2 < 0) q2 = p; else q3 = p;
+                        }
+                    }
+                    c.compares += (unsigned)(P.n_primers * kBsPositions);
+                    flush();
+                    if (ix.k > 0) {
+                        if (n_acc == 1) {
+                            const int n_bases = min(ix.window, c.len);
+                            if (diagonal_kmer<RW>(P, c, a_p, a_seq, ix.k, n_bases) || kmer_member_exact<RW>(P, c, a_p))
+                                best.offer(a_p, a_mm, __ddiv_rn((double)a_mm, (double)a_plen));
+                        } else if (n_acc >= 2) {
+                            kmer_scan_exact<RW>(P, c, best, ix.direct, ix.heads);  // ties: the reference's candidate order decides
+                        }
+                    }
+                } else if (ix.k <= 0) {  // PM:100: every primer, file order
                     for (int p = 0; p < P.n_primers; ++p) {
                         int mm, plen;
                         if (mismatch_align<RW>(P, c, p, mm, plen)) best.offer(p, mm, __ddiv_rn((double)mm, (double)plen));
                     }
-                } else if (c.len >= ix.k) {  // PM:108-116
-                    const int n_bases = min(ix.window, c.len);  // k-mers start at 0 .. n_bases - k
-                    Pending<RW> pend;
-                    uint32_t sr[RW];  // shift register over the window: the next base is always the low nibble of sr[0]
-#pragma unroll
-                    for (int w = 0; w < RW; ++w) sr[w] = c.win[w];
-                    const uint64_t kmask4 = ix.k >= 16 ? ~0ull : ((1ull << (4 * ix.k)) - 1ull);
-                    const uint32_t kmask2 = ix.k >= 16 ? ~0u : ((1u << (2 * ix.k)) - 1u);
-                    uint64_t key4 = 0;
-                    uint32_t key2 = 0;
-                    int bad = 0;  // > 0 while the current k-mer holds a nibble that is not exactly one of A/C/G/T
-                    for (int i = 0; i < n_bases; ++i) {
-                        const uint32_t nib = sr[0] & 15u;
-#pragma unroll
-                        for (int w = 0; w < RW - 1; ++w) sr[w] = __funnelshift_r(sr[w], sr[w + 1], 4);
-                        sr[RW - 1] >>= 4;
-                        key4 = ((key4 << 4) | nib) & kmask4;
-                        key2 = ((key2 << 2) | ((0x30210u >> (2 * nib)) & 3u)) & kmask2;  // A,C,G,T (1,2,4,8) -> 0..3
-                        bad = max(bad - 1, 0);
-                        if (__popc(nib) != 1) bad = ix.k;
-                        if (i < ix.k - 1) continue;
-                        if (direct != nullptr && bad == 0) {
-                            const uint32_t e = direct[key2];
-                            if (e) walk_postings<RW>(P, c, best, pend, heads, e & 0xFFFFFu, e >> 20);
-                        } else {  // literal equality of IUPAC letters (PM:113): the full table, keyed by 4 bits per base
-                            OffCnt oc;
-                            if (kmer_lookup(ix, key4, oc)) walk_postings<RW>(P, c, best, pend, direct != nullptr ? ix.heads : heads, oc.off, oc.cnt);
-                        }
-                    }
-                    pend.flush(P, c, best);
+                } else {
+                    kmer_scan_exact<RW>(P, c, best, direct, heads);
                 }
                 if (best.bp >= 0) {
                     res.primer = best.bp; res.type = IDP_UNGAPPED; res.mm = best.bmm;
@@ -320,8 +447,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(DevPanel P, DevRe
             if (need_gapped) fall[base + __popc(ballot & ((1u << lane) - 1u))] = (unsigned)r;
         }
         compares_total += c.compares;
+        __syncwarp();  // all lanes are done with this tile buffer: the next iteration may overwrite it
+        cur ^= 1;
     }
-    // statistics: base comparisons performed (a head-filter rejection counts 8), one atomic per warp
+    // statistics: base comparisons performed, one atomic per warp
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) compares_total += __shfl_xor_sync(0xffffffffu, compares_total, d);
     if (lane == 0 && compares_total) atomicAdd(&ctr->base_compares, compares_total);

@@ -312,3 +312,63 @@ def test_large_batch_properties():
     panel_o = O.Panel(_synth_primers(panel), _opts_to_oracle(opts))
     want5, _, _, _ = panel_o.process_batch(reads.oracle_arrays(lo, hi), n_threads=8)
     assert_same(five[lo:hi], want5, "prefix")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the bit-sliced fast path of the scan kernel (all accept thresholds <= 1) against the oracle and against the exact walk
+# ------------------------------------------------------------------------------------------------------------------
+def test_fast_filter_ties_and_iupac_dense_primers():
+    rng = np.random.default_rng(21)
+    base = "ACGTTGCAAGGCTTACGATCGGATTC"
+    primers = []
+    for i in range(20):   # near-duplicates: several primers accept the same read -> candidate order decides
+        s = list(base[: 20 + i % 6])
+        if i % 4:
+            j = int(rng.integers(0, len(s)))
+            s[j] = "ACGT"[("ACGT".index(s[j]) + 1 + i % 3) % 4]
+        primers.append(H.Primer(f"d{i}", f"d{i}+", "".join(s), True))
+        primers.append(H.Primer(f"d{i}", f"d{i}-", H.revcomp("".join(s)), False))
+    for i in range(10):   # IUPAC letter every few bases: accepted by mismatch count, but no literal k-mer on the diagonal
+        s = list("".join("ACGT"[x] for x in rng.integers(0, 4, 22)))
+        for j in range(2 + i % 3, 22, 4 + i % 3):
+            s[j] = {"A": "R", "C": "Y", "G": "R", "T": "Y"}[s[j]]
+        primers.append(H.Primer(f"u{i}", f"u{i}+", "".join(s), True))
+        primers.append(H.Primer(f"u{i}", f"u{i}-", "".join("ACGT"[x] for x in rng.integers(0, 4, 21)), False))
+    inst = {"R": "AG", "Y": "CT"}
+    recs = []
+    for i in range(1500):
+        p = primers[int(rng.integers(0, len(primers)))]
+        s = [inst[ch][int(rng.integers(0, 2))] if ch in inst else ch for ch in p.sequence]
+        s += ["ACGT"[x] for x in rng.integers(0, 4, 30)]
+        if rng.random() < 0.5:
+            s[int(rng.integers(0, 20))] = "ACGTN"[int(rng.integers(0, 5))]
+        if rng.random() < 0.1:
+            s = s[: int(rng.integers(3, 25))]
+        recs.append(H.Rec("".join(s), True, False))
+    arrays = H.recs_to_arrays(recs)
+    for k in (None, 4, 6, 8):
+        for rate in (0.0, 0.05):
+            got5, _, _, _ = run_both(primers, arrays, max_mismatch_rate=rate, ungapped_kmer_length=k, gapped_kmer_length=10)
+            assert (got5["type"] == L.UNGAPPED).any()
+
+
+@pytest.mark.parametrize("name,n_pairs", [("c2", 300_000), ("c3", 100_000), ("c5", 100_000)])
+def test_fast_filter_equals_exact_walk(name, n_pairs):
+    import os
+    panel, reads, opts = synth.workload(name, n_pairs)
+    batch = idp.ReadBatch(reads.seq4().reshape(-1), reads.flags, fixed_len=150, ref_idx=reads.ref_idx, unclipped_start=reads.ustart,
+                          unclipped_end=reads.uend)
+    out = []
+    for exact in (False, True):
+        if exact:
+            os.environ["IDP_SCAN_EXACT_WALK"] = "1"
+        try:
+            with idp.IdentifyPrimers(panel.primers, ref_names=panel.ref_names, **opts) as tool:
+                five, three = tool.process_batch(batch)
+                out.append((five.copy(), None if three is None else three.copy(), tool.metric_counter.copy(), tool.num_alignments))
+        finally:
+            os.environ.pop("IDP_SCAN_EXACT_WALK", None)
+    assert np.array_equal(out[0][0].view(np.uint8), out[1][0].view(np.uint8))
+    if out[0][1] is not None:
+        assert np.array_equal(out[0][1].view(np.uint8), out[1][1].view(np.uint8))
+    assert np.array_equal(out[0][2], out[1][2]) and out[0][3] == out[1][3]
