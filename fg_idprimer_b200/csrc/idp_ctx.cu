@@ -74,7 +74,7 @@ struct idp_ctx {
     const idp_panel *panel = nullptr;
     int device = 0, sm_count = 148;
     DevPanel dp{};
-    DevBuf b_pmask, b_pinfo, b_positive, b_loc_key[2], b_loc_primer[2], b_mate_off, b_mate_idx, b_smat;
+    DevBuf b_qbot, b_bylen, b_pmask, b_pinfo, b_positive, b_loc_key[2], b_loc_primer[2], b_mate_off, b_mate_idx, b_smat;
     DevBuf b_keys[2], b_offcnt[2], b_postings[2], b_heads[2], b_direct[2], b_bsmm, b_bsacc;
     Slot slots[kSlots];
     cudaStream_t user_stream = nullptr;
@@ -145,6 +145,27 @@ static int upload_panel(idp_ctx *c) {
     const int wb = p.window_bases;
     c->rw = wb <= 32 ? 4 : wb <= 40 ? 5 : wb <= 64 ? 8 : wb <= 128 ? 16 : 32;
     c->nq = p.max_seq_len <= 32 ? 32 : p.max_seq_len <= 64 ? 64 : 0;
+    d.qbot = nullptr;
+    if (c->nq > 0) {  // primers bottom-aligned in nq rows for the register-resident aligners
+        const int words = c->nq / 8;
+        std::vector<uint32_t> qbot((size_t)p.n * words, 0u);
+        for (int i = 0; i < p.n; ++i) {
+            const int off = c->nq - p.seq_len[i];
+            for (int b = 0; b < p.seq_len[i]; ++b) {
+                const uint32_t nib = (p.pmask[(size_t)i * p.ww + b / 8] >> (4 * (b % 8))) & 15u;
+                qbot[(size_t)i * words + (off + b) / 8] |= nib << (4 * ((off + b) % 8));
+            }
+        }
+        if ((rc = upload(qbot, c->b_qbot))) return rc;
+        d.qbot = c->b_qbot.as<uint32_t>();
+    }
+    {
+        std::vector<uint32_t> order(p.n);
+        for (int i = 0; i < p.n; ++i) order[i] = (uint32_t)i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return p.seq_len[a] < p.seq_len[b]; });
+        if ((rc = upload(order, c->b_bylen))) return rc;
+        d.by_len = c->b_bylen.as<uint32_t>();
+    }
     return IDP_OK;
 }
 
@@ -288,7 +309,7 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
         if (k_gapped) {
             const int words = (p.n + 31) / 32;
             const size_t smem = (size_t)8 * words * 4;
-            cand5_kernel<<<c->sm_count * 4, 256, smem, st>>>(c->dp, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(),
+            cand5_kernel<<<c->sm_count * 8, 256, smem, st>>>(c->dp, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(),
                                                             (unsigned)s.pair_cap, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>());
             CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st));
             launch_sw_pairs(c, st, false, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), (unsigned)s.pair_cap);
@@ -397,7 +418,7 @@ void idp_ctx_destroy(idp_ctx *c) {
         for (auto &e : s.ev) if (e) cudaEventDestroy(e);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
-    for (DevBuf *b : {&c->b_pmask, &c->b_pinfo, &c->b_positive, &c->b_loc_key[0], &c->b_loc_key[1], &c->b_loc_primer[0], &c->b_loc_primer[1],
+    for (DevBuf *b : {&c->b_qbot, &c->b_bylen, &c->b_pmask, &c->b_pinfo, &c->b_positive, &c->b_loc_key[0], &c->b_loc_key[1], &c->b_loc_primer[0], &c->b_loc_primer[1],
                       &c->b_mate_off, &c->b_mate_idx, &c->b_smat, &c->b_keys[0], &c->b_keys[1], &c->b_offcnt[0], &c->b_offcnt[1],
                       &c->b_postings[0], &c->b_postings[1], &c->b_heads[0], &c->b_heads[1], &c->b_direct[0], &c->b_direct[1], &c->b_bsmm, &c->b_bsacc}) b->release();
     delete c;

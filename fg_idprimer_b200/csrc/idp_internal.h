@@ -41,6 +41,8 @@ struct DevPanel {
     int32_t window_bases;      // leading read bases the scan kernel looks at
     int32_t max_seq_len;
     const uint32_t *pmask;     // [n][ww] IUPAC masks, base i in nibble i, padded with 0xF
+    const uint32_t *qbot;      // [n][nq/8] the same letters bottom-aligned in nq (32 or 64) rows, zero above; NULL if nq == 0
+    const uint32_t *by_len;    // [n] primer indices sorted by sequence length (stable)
     // [n] {Primer.length (PR:206), early-exit cap of numMismatches and largest accepted mismatch count when the read
     //      is at least Primer.length long (PM:130-134), primer.sequence.length}
     const int4 *pinfo;

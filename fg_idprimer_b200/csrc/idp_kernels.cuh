@@ -66,6 +66,21 @@ __device__ __forceinline__ uint32_t stored_nib(const uint8_t *s, int i) {
 // htsjdk 2.16 SequenceUtil.complement touches only A<->T, C<->G (nibbles 1<->8, 2<->4); every other code is kept (PM:42)
 __device__ __forceinline__ uint32_t comp_nib(uint32_t x) { return (uint32_t)(0xFEDCBA9176523480ull >> (4 * x)) & 15u; }
 
+// 8 BAM bytes-order nibbles (first base in the HIGH nibble of each byte) -> base i in nibble i
+__device__ __forceinline__ uint32_t nibswap(uint32_t x) { return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu); }
+// 1 in the low bit of every nibble that is non-zero
+__device__ __forceinline__ uint32_t nib_nonzero(uint32_t x) {
+    x |= x >> 1;
+    x |= x >> 2;
+    return x & 0x11111111u;
+}
+// bits 0,4,...,28 -> bits 0..7
+__device__ __forceinline__ uint32_t gather_nibble_bits(uint32_t z) {
+    z = (z | (z >> 3)) & 0x03030303u;
+    z = (z | (z >> 6)) & 0x000F000Fu;
+    return (z | (z >> 12)) & 0xFFu;
+}
+
 // a read viewed in a given orientation: forward = as stored, rc = reverse-complemented
 struct Oriented {
     const uint8_t *s;
@@ -76,6 +91,24 @@ struct Oriented {
     __device__ __forceinline__ uint32_t nib_generic(int j) const {
         const int i = rc ? len - 1 - j : j;
         const uint32_t b = s[i >> 1];
+        const uint32_t v = (i & 1) ? (b & 15u) : (b >> 4);
+        return rc ? comp_nib(v) : v;
+    }
+};
+// sequential access to an oriented read through a one-word cache: one 32-bit load per 8 bases instead of a byte load per base
+struct TargetStream {
+    const uint8_t *s;
+    int len;
+    bool rc;
+    const uint32_t *curp;
+    uint32_t word;
+    __device__ __forceinline__ explicit TargetStream(const Oriented &o) : s(o.s), len(o.len), rc(o.rc), curp(nullptr), word(0) {}
+    __device__ __forceinline__ uint32_t nib(int j) {
+        const int i = rc ? len - 1 - j : j;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(s) + (uintptr_t)(i >> 1);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+        if (wp != curp) { curp = wp; word = __ldg(wp); }
+        const uint32_t b = (word >> (8 * (int)(a & 3))) & 0xFFu;
         const uint32_t v = (i & 1) ? (b & 15u) : (b >> 4);
         return rc ? comp_nib(v) : v;
     }
@@ -132,17 +165,20 @@ __global__ void __launch_bounds__(256) cand5_kernel(DevPanel P, DevReads R, cons
         Oriented o{s, len, seq_order_is_rc(fl)};
         const int end = len >= ix.k ? min(ix.window, len) - ix.k + 1 : 0;  // k-mers start at 0 .. end-1 (PM:110)
         unsigned base = 0, count = 0;
+        OffCnt cached{0u, 0u};  // with at most 32 k-mer positions (the usual case) the second pass reuses the first pass's lookups
         for (int pass = 0; pass < 2; ++pass) {
             unsigned emitted = 0;
             for (int p0 = 0; p0 < end; p0 += 32) {
                 // every lane looks up the k-mer starting at its own position: one table latency per 32 positions
                 const int pos = p0 + lane;
                 OffCnt oc{0u, 0u};
-                if (pos < end) {
+                if (pass == 1 && end <= 32) oc = cached;
+                else if (pos < end) {
                     uint64_t key = 0;
                     for (int t = 0; t < ix.k; ++t) key = (key << 4) | o.nib(pos + t);
                     if (!kmer_lookup(ix, key, oc)) oc.cnt = 0;
                 }
+                cached = oc;
                 unsigned hits = __ballot_sync(0xffffffffu, oc.cnt > 0);
                 while (hits) {  // positions in ascending order = the order the reference visits them in
                     const int src = __ffs(hits) - 1;
@@ -176,6 +212,7 @@ __global__ void __launch_bounds__(256) cand5_kernel(DevPanel P, DevReads R, cons
                     if (lane == 0) { atomicAdd(&ctr->overflow, 1u); seg_off[w] = 0; seg_cnt[w] = -1; }
                     count = 0xffffffffu;
                 } else if (lane == 0) { seg_off[w] = base; seg_cnt[w] = (int)count; }
+                if (count == 0) break;  // no candidate set any bit: nothing to clear, nothing to emit
             }
             __syncwarp();
         }
@@ -264,8 +301,9 @@ __device__ __forceinline__ int sw_score(const DevPanel &P, const int32_t *__rest
         else { D[i] = kNegInf; L[i] = kNegInf; M[i] = P.gap_open + (i + 1) * P.gap_extend; }  // Up(i,0)
     }
     int best = LOCAL ? 0 : kNegInf;
+    TargetStream ts(T);
     for (int j = 0; j < m; ++j) {
-        const uint32_t t = T.nib(j);
+        const uint32_t t = ts.nib(j);
         int mdiag = 0, d_up = 0, u_up = 0;  // row 0 is all zero in Glocal and Local
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {
@@ -326,59 +364,156 @@ __device__ int sw_score_generic(const DevPanel &P, const int32_t *__restrict__ s
     return best;
 }
 
-// Register-resident variant that also carries where each path started: every value is (score << 12) | start, so one
-// integer compare orders scores and the winner's start rides along.  Requires |scores| * (rows + columns) < 2^17
-// (DevPanel::packed_trace_ok) and targets shorter than 4096.  Tie rules are those of sw_trace() below.
+// ---------------------------------------------------------------------------------------------------------------
+// Fast register-resident variants (default byte-equality scorer).  The query occupies the LAST n of NQ register rows
+// (DevPanel::qbot holds every primer bottom-aligned), so the last query row is always row NQ-1 and rows above the
+// query simply are not executed: the unrolled rows are entered through a switch at the warp's longest query, shorter
+// queries skip their leading rows by predicate.  Per column one SIMD compare produces the match mask of all rows.
+// ---------------------------------------------------------------------------------------------------------------
+#define IDP_ROWS8(b) IDP_ROW((b) + 0) IDP_ROW((b) + 1) IDP_ROW((b) + 2) IDP_ROW((b) + 3) IDP_ROW((b) + 4) IDP_ROW((b) + 5) IDP_ROW((b) + 6) IDP_ROW((b) + 7)
+#define IDP_ROWS32 IDP_ROWS8(0) IDP_ROWS8(8) IDP_ROWS8(16) IDP_ROWS8(24)
+#define IDP_ROWS64 IDP_ROWS32 IDP_ROWS8(32) IDP_ROWS8(40) IDP_ROWS8(48) IDP_ROWS8(56)
+// Rows [lo, hi) are "ragged": some lanes' queries start below them.  They run branch-free (a lane whose query has not
+// started keeps its three carried values by select), because a divergent branch inside the fall-through switch would
+// keep the lanes apart until the end of the column.  Rows [hi, NQ) belong to every lane's query and run plain.
+// lo = NQ - (longest query in the warp), hi = NQ - (shortest); both are warp-uniform.
+#define IDP_SWITCH_ROWS(NQ_, first)                     \
+    if constexpr ((NQ_) == 32) { switch (first) { IDP_ROWS32 default: break; } } \
+    else { switch (first) { IDP_ROWS64 default: break; } }
+
+template <int NQ, bool LOCAL>
+__device__ __forceinline__ int sw_score_fast(const DevPanel &P, const uint32_t *__restrict__ qbot, int n, int lo, int hi, const Oriented &T, int m) {
+    static_assert(NQ == 32 || NQ == 64, "row count");
+    const int oe = P.gap_open + P.gap_extend, e = P.gap_extend, ma = P.match_score, mi = P.mismatch_score;
+    if (m == 0) return LOCAL ? 0 : P.gap_open + n * P.gap_extend;
+    const int off = NQ - n;
+    uint32_t q[NQ / 8];
+#pragma unroll
+    for (int w = 0; w < NQ / 8; ++w) q[w] = __ldg(&qbot[w]);
+    int D[NQ], L[NQ], M[NQ];
+#pragma unroll
+    for (int r = 0; r < NQ; ++r) {
+        if (LOCAL) { D[r] = 0; L[r] = 0; M[r] = 0; }
+        else { D[r] = kNegInf; L[r] = kNegInf; M[r] = P.gap_open + (r - off + 1) * P.gap_extend; }  // Up(i,0), i = r-off+1
+    }
+    int best = LOCAL ? 0 : kNegInf;
+    TargetStream ts(T);
+    for (int j = 0; j < m; ++j) {
+        uint32_t t = ts.nib(j);
+        asm volatile("" : "+r"(t));  // keep the base in a register: do not re-derive it inside every row
+        const uint32_t trep = t * 0x11111111u;
+        uint32_t ne[NQ / 8];          // low bit of nibble r%8 of ne[r/8] is set when query row r differs from t
+#pragma unroll
+        for (int w = 0; w < NQ / 8; ++w) ne[w] = nib_nonzero(q[w] ^ trep);
+        int mdiag = 0, d_up = 0, u_up = 0;  // row 0 is all zero in Glocal and Local
+#define IDP_CELL(r)                                                                    \
+            int dn = mdiag + ((ne[(r) >> 3] & (1u << (4 * ((r) & 7)))) ? mi : ma);      \
+            if (LOCAL) dn = max(dn, 0);                                                \
+            const int un = __viaddmax_s32(d_up, oe, u_up + e);                         \
+            const int ln = __viaddmax_s32(D[(r)], oe, L[(r)] + e);                     \
+            const int mold = M[(r)];                                                   \
+            M[(r)] = __vimax3_s32(dn, ln, un);                                         \
+            D[(r)] = dn; L[(r)] = ln;
+#define IDP_ROW(r)                                                                     \
+    case (r): {                                                                        \
+        if ((r) >= hi) break;                                                          \
+        const bool act = (r) >= off;                                                   \
+        IDP_CELL(r)                                                                    \
+        mdiag = act ? mold : mdiag; d_up = act ? dn : d_up; u_up = act ? un : u_up;    \
+        if (LOCAL) best = max(best, act ? dn : 0);                                     \
+    }
+        IDP_SWITCH_ROWS(NQ, lo)
+#undef IDP_ROW
+#define IDP_ROW(r)                                                                     \
+    case (r): {                                                                        \
+        IDP_CELL(r)                                                                    \
+        mdiag = mold; d_up = dn; u_up = un;                                            \
+        if (LOCAL) best = max(best, dn);                                               \
+    }
+        IDP_SWITCH_ROWS(NQ, hi)
+#undef IDP_ROW
+#undef IDP_CELL
+        if (!LOCAL) best = max(best, M[NQ - 1]);  // last query row, this column (Glocal end cell: best over the last row)
+    }
+    return best;
+}
+
+// Same, carrying where each path started: every value is (score << 12) | start, so one integer compare orders scores and
+// the winner's start rides along.  Requires |scores| * (rows + columns) < 2^17 (DevPanel::packed_trace_ok) and targets
+// shorter than 4096.  Tie rules are those of sw_trace() below.
 //   a.score >= b.score  <=>  (a | 0xFFF) >= b          a.score > b.score  <=>  a > (b | 0xFFF)
 struct TracedReg { int score, t_start, t_end; };
 
 template <int NQ, bool LOCAL>
-__device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint32_t *__restrict__ qwords, int n, int n_warp_max,
-                                                 const Oriented &T, int m) {
+__device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint32_t *__restrict__ qbot, int n, int lo, int hi, const Oriented &T, int m) {
+    static_assert(NQ == 32 || NQ == 64, "row count");
     TracedReg out{0, 1, 0};
     if (m == 0) { out.score = LOCAL ? 0 : P.gap_open + n * P.gap_extend; return out; }
     const int oe = (P.gap_open + P.gap_extend) * 4096, e = P.gap_extend * 4096, ma = P.match_score * 4096, mi = P.mismatch_score * 4096;
     constexpr int NEG = -(1 << 30);  // score -2^18
-    uint32_t q[(NQ + 7) / 8];
+    const int off = NQ - n;
+    uint32_t q[NQ / 8];
 #pragma unroll
-    for (int w = 0; w < (NQ + 7) / 8; ++w) q[w] = w < P.ww ? __ldg(&qwords[w]) : 0u;
+    for (int w = 0; w < NQ / 8; ++w) q[w] = __ldg(&qbot[w]);
     int D[NQ], L[NQ], M[NQ];
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) {
-        if (LOCAL) { D[i] = 0; L[i] = 0; M[i] = 0; }
-        else { D[i] = NEG; L[i] = NEG; M[i] = (P.gap_open + (i + 1) * P.gap_extend) * 4096; }  // Up(i,0), start 0
+    for (int r = 0; r < NQ; ++r) {
+        if (LOCAL) { D[r] = 0; L[r] = 0; M[r] = 0; }
+        else { D[r] = NEG; L[r] = NEG; M[r] = (P.gap_open + (r - off + 1) * P.gap_extend) * 4096; }  // Up(i,0), start 0
     }
     int best = NEG, bi = 0, bj = 0;
+    TargetStream ts(T);
     for (int j = 1; j <= m; ++j) {
-        const uint32_t t = T.nib(j - 1);
-        int mdiag = j - 1, d_up = j, u_up = j;  // row 0: score 0, path starts at this column
+        uint32_t t = ts.nib(j - 1);
+        asm volatile("" : "+r"(t));
+        const uint32_t trep = t * 0x11111111u;
+        uint32_t ne[NQ / 8];
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            if (i >= n_warp_max) break;
-            if (i < n) {
-                const uint32_t qc = (q[i >> 3] >> (4 * (i & 7))) & 15u;
-                int dn = mdiag + (qc == t ? ma : mi);
-                if (LOCAL && dn < 0) dn = j;  // clamp at zero: the path (re)starts after this cell
-                int un, ln;
-                { const int a = d_up + oe, b = u_up + e; un = ((a | 0xFFF) >= b) ? a : b; }  // Diagonal preferred over extending Up
-                { const int a = D[i] + oe, b = L[i] + e; ln = ((a | 0xFFF) >= b) ? a : b; }  // Diagonal preferred over extending Left
-                int mn = dn;                                                                  // Diagonal, then Left, then Up
-                if (ln > (mn | 0xFFF)) mn = ln;
-                if (un > (mn | 0xFFF)) mn = un;
-                mdiag = M[i];
-                D[i] = dn; L[i] = ln; M[i] = mn;
-                d_up = dn; u_up = un;
-                if (LOCAL) {
-                    // best cell: lowest row, then lowest column.  Left/Up values never win: each is bounded by a Diagonal
-                    // value of a cell scanned earlier (gap scores are <= 0), and ties go to the earlier cell.
-                    const int ds = dn >> 12, bs = best >> 12;
-                    if (ds > bs || (ds == bs && i + 1 < bi)) { best = dn; bi = i + 1; bj = j; }
-                } else if (i == n - 1) {
-                    // last row, columns ascending, Diagonal / Left / Up, strict '>': Left(n,j) <= an earlier Diagonal(n,j')
-                    if (dn > (best | 0xFFF)) { best = dn; bj = j; }
-                    if (un > (best | 0xFFF)) { best = un; bj = j; }
-                }
+        for (int w = 0; w < NQ / 8; ++w) ne[w] = nib_nonzero(q[w] ^ trep);
+        int mdiag = j - 1, d_up = j, u_up = j;  // row 0: score 0, path starts at this column
+#define IDP_CELL(r)                                                                                                            \
+            int dn = mdiag + ((ne[(r) >> 3] & (1u << (4 * ((r) & 7)))) ? mi : ma);                                              \
+            if (LOCAL) dn = dn < 0 ? j : dn; /* clamp at zero: the path (re)starts after this cell */                          \
+            int un, ln;                                                                                                        \
+            { const int a = d_up + oe, b = u_up + e; un = ((a | 0xFFF) >= b) ? a : b; } /* Diagonal over extending Up */       \
+            { const int a = D[(r)] + oe, b = L[(r)] + e; ln = ((a | 0xFFF) >= b) ? a : b; } /* Diagonal over extending Left */ \
+            int mn = dn; /* Diagonal, then Left, then Up */                                                                    \
+            mn = (ln > (mn | 0xFFF)) ? ln : mn;                                                                                \
+            mn = (un > (mn | 0xFFF)) ? un : mn;                                                                                \
+            const int mold = M[(r)];                                                                                           \
+            D[(r)] = dn; L[(r)] = ln; M[(r)] = mn;
+        // Local best cell: lowest row, then lowest column; Left/Up values never win (each is bounded by a Diagonal value of a
+        // cell scanned earlier, gap scores being <= 0, and ties go to the earlier cell)
+#define IDP_BEST(r, cond)                                                                      \
+            if (LOCAL) {                                                                       \
+                const int ds = dn >> 12, bs = best >> 12;                                      \
+                const bool better = (cond) && (ds > bs || (ds == bs && (r) + 1 < bi));         \
+                best = better ? dn : best; bi = better ? (r) + 1 : bi; bj = better ? j : bj;   \
             }
+#define IDP_ROW(r)                                                                     \
+    case (r): {                                                                        \
+        if ((r) >= hi) break;                                                          \
+        const bool act = (r) >= off;                                                   \
+        IDP_CELL(r)                                                                    \
+        mdiag = act ? mold : mdiag; d_up = act ? dn : d_up; u_up = act ? un : u_up;    \
+        IDP_BEST(r, act)                                                               \
+    }
+        IDP_SWITCH_ROWS(NQ, lo)
+#undef IDP_ROW
+#define IDP_ROW(r)                                                                     \
+    case (r): {                                                                        \
+        IDP_CELL(r)                                                                    \
+        mdiag = mold; d_up = dn; u_up = un;                                            \
+        IDP_BEST(r, true)                                                              \
+    }
+        IDP_SWITCH_ROWS(NQ, hi)
+#undef IDP_ROW
+#undef IDP_CELL
+#undef IDP_BEST
+        if (!LOCAL) {
+            // last row, columns ascending, Diagonal / Left / Up, strict '>': Left(n,j) never exceeds an earlier Diagonal(n,j')
+            if (d_up > (best | 0xFFF)) { best = d_up; bj = j; }
+            if (u_up > (best | 0xFFF)) { best = u_up; bj = j; }
         }
     }
     out.score = best >> 12; out.t_start = (best & 0xFFF) + 1; out.t_end = bj;
@@ -399,7 +534,7 @@ __device__ __forceinline__ Oriented make_target(const DevPanel &P, const DevRead
 constexpr int32_t kScoreMissing = INT32_MIN;  // pair touched a base pair the scoring matrix has no entry for
 
 template <int NQ, bool LOCAL, bool SMAT, bool TRACE>
-__global__ void __launch_bounds__(128) sw_pairs_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
+__global__ void __launch_bounds__(128, 4) sw_pairs_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
                                                        Counters *ctr, const unsigned int *__restrict__ pair_work,
                                                        const unsigned int *__restrict__ pair_primer, int *__restrict__ pair_score,
                                                        unsigned int *__restrict__ pair_se, unsigned int pair_cap) {
@@ -426,14 +561,17 @@ __global__ void __launch_bounds__(128) sw_pairs_kernel(DevPanel P, DevReads R, c
             }
         }
         const int n_warp_max = __reduce_max_sync(0xffffffffu, n);
+        const int n_warp_min = __reduce_min_sync(0xffffffffu, active ? n : n_warp_max);
+        constexpr int NQF = NQ == 64 ? 64 : 32;
         if (active) {
             bool missing = false;
             int sc;
             if (TRACE) {  // few candidates per read: carry the start column too, so no second alignment is needed
-                const TracedReg tr = sw_trace_reg<(NQ > 0 ? NQ : 8), LOCAL>(P, P.pmask + (size_t)p * P.ww, n, n_warp_max, T, m);
+                const TracedReg tr = sw_trace_reg<NQF, LOCAL>(P, P.qbot + (size_t)p * (NQF / 8), n, NQF - n_warp_max, NQF - n_warp_min, T, m);
                 sc = tr.score;
                 pair_se[t] = ((unsigned)tr.t_start & 0xFFFFu) | ((unsigned)tr.t_end << 16);
-            } else if (NQ > 0) sc = sw_score<(NQ > 0 ? NQ : 8), LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, n_warp_max, T, m, missing);
+            } else if (NQ > 0 && !SMAT) sc = sw_score_fast<NQF, LOCAL>(P, P.qbot + (size_t)p * (NQF / 8), n, NQF - n_warp_max, NQF - n_warp_min, T, m);
+            else if (NQ > 0) sc = sw_score<(NQ > 0 ? NQ : 8), LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, n_warp_max, T, m, missing);
             else sc = sw_score_generic<LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, T, m, missing);
             pair_score[t] = missing ? kScoreMissing : sc;
             cells += (unsigned long long)n * (unsigned long long)m;
@@ -474,7 +612,7 @@ struct GBest2 {
 // Every primer is a candidate (no -K, or 3' with no 5' match anywhere): one block per read, threads stride the panel
 // in file order, the best two are reduced on chip.  Nothing per-pair ever touches HBM.
 template <int NQ, bool LOCAL, bool SMAT>
-__global__ void __launch_bounds__(128) sw_all_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
+__global__ void __launch_bounds__(128, 4) sw_all_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
                                                      const unsigned int *__restrict__ n_work_ptr, Fin *__restrict__ fin,
                                                      Counters *__restrict__ ctr_out, int count_as_5p) {
     __shared__ int32_t smat_s[256];
@@ -487,17 +625,22 @@ __global__ void __launch_bounds__(128) sw_all_kernel(DevPanel P, DevReads R, con
         const int r = (int)work_read[w];
         GBest2 g;
         bool any_missing = false;
+        constexpr int NQF = NQ == 64 ? 64 : 32;
         for (int p0 = 0; p0 < P.n_primers; p0 += blockDim.x) {
-            const int p = p0 + threadIdx.x;
-            const bool active = p < P.n_primers;
+            // primers are visited sorted by length so that a warp's alignments have (nearly) the same number of rows;
+            // ties are still broken by the primer's position in the file (the ordinal offered below)
+            const bool active = p0 + (int)threadIdx.x < P.n_primers;
+            const int p = active ? (int)__ldg(&P.by_len[p0 + threadIdx.x]) : 0;
             int n = 0, m = 0;
             Oriented T{nullptr, 0, false};
             if (active) { n = __ldg(&P.pinfo[p]).w; T = make_target(P, R, r, n, LOCAL, m); }
             const int n_warp_max = __reduce_max_sync(0xffffffffu, n);
+            const int n_warp_min = __reduce_min_sync(0xffffffffu, active ? n : n_warp_max);
             if (active) {
                 bool missing = false;
                 int sc;
-                if (NQ > 0) sc = sw_score<(NQ > 0 ? NQ : 8), LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, n_warp_max, T, m, missing);
+                if (NQ > 0 && !SMAT) sc = sw_score_fast<NQF, LOCAL>(P, P.qbot + (size_t)p * (NQF / 8), n, NQF - n_warp_max, NQF - n_warp_min, T, m);
+                else if (NQ > 0) sc = sw_score<(NQ > 0 ? NQ : 8), LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, n_warp_max, T, m, missing);
                 else sc = sw_score_generic<LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, T, m, missing);
                 any_missing |= missing;
                 g.offer(p, p, sc, n);
@@ -604,7 +747,9 @@ __device__ void finish_gapped(const DevPanel &P, const DevReads &R, int r, const
                 Oriented T = make_target(P, R, r, n, three_prime, m);
                 const uint32_t *qw = P.pmask + (size_t)f.primer * P.ww;
                 if (NQ > 0 && P.packed_trace_ok) {
-                    tr = three_prime ? sw_trace_reg<(NQ > 0 ? NQ : 8), true>(P, qw, n, n, T, m) : sw_trace_reg<(NQ > 0 ? NQ : 8), false>(P, qw, n, n, T, m);
+                    constexpr int NQF = NQ == 64 ? 64 : 32;
+                    const uint32_t *qb = P.qbot + (size_t)f.primer * (NQF / 8);
+                    tr = three_prime ? sw_trace_reg<NQF, true>(P, qb, n, 0, NQF, T, m) : sw_trace_reg<NQF, false>(P, qb, n, 0, NQF, T, m);
                 } else {
                     const Traced g = sw_trace<TN>(P, qw, n, T, m, three_prime ? IDP_MODE_LOCAL : IDP_MODE_GLOCAL);
                     tr.score = g.score; tr.t_start = g.t_start; tr.t_end = g.t_end;

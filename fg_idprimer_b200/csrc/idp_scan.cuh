@@ -54,21 +54,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!done);
 }
 
-// 8 BAM bytes-order nibbles (first base in the HIGH nibble of each byte) -> base i in nibble i
-__device__ __forceinline__ uint32_t nibswap(uint32_t x) { return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu); }
-// 1 in the low bit of every nibble that is non-zero
-__device__ __forceinline__ uint32_t nib_nonzero(uint32_t x) {
-    x |= x >> 1;
-    x |= x >> 2;
-    return x & 0x11111111u;
-}
-// bits 0,4,...,28 -> bits 0..7
-__device__ __forceinline__ uint32_t gather_nibble_bits(uint32_t z) {
-    z = (z | (z >> 3)) & 0x03030303u;
-    z = (z | (z >> 6)) & 0x000F000Fu;
-    return (z | (z >> 12)) & 0xFFu;
-}
-
 struct Best2 {  // getBestUngappedAlignment (PM:237-248) as a running stable top-2 on key = mm / Primer.length
     int bp = -1, bmm = 0, sp = -1, smm = 0;
     double bkey = 0.0, skey = 0.0;
