@@ -175,6 +175,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the IdentifyPrimers GPU path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("IDP_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
