@@ -175,7 +175,7 @@ static int launch_scan_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, i
     // an SM (two CTAs per SM)
     ScanLaunch S{};
     const DevKmerIndex &ix = c->dp.kidx[0];
-    const size_t budget = 110 * 1024;
+    const size_t budget = (size_t)(224 * 1024 / kScanMinBlocks - 1024);
     size_t used = 0;
     S.stride = R.fixed_len > 0 ? (uint32_t)((R.fixed_len + 1) >> 1) : 0;
     // a warp tile is 32 reads: 32 * stride bytes, always a multiple of 16 as the TMA bulk copy requires
@@ -194,13 +194,13 @@ static int launch_scan_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, i
     };
     S.direct_entries = ix.direct ? (1u << (2 * ix.k)) : 0;
     S.off_bsacc = place((size_t)c->dp.bs_groups * sizeof(uint2), FAST);
-    S.off_bsmm = place((size_t)c->dp.bs_groups * kBsPositions * 16 * 4, FAST);
+    S.off_bsmm = place((size_t)c->dp.bs_groups * kBsStride * 16 * 4, FAST);
     S.off_direct = place((size_t)S.direct_entries * 4, !FAST && ix.direct != nullptr);
     S.off_pinfo = place((size_t)c->dp.n_primers * sizeof(int4), true);
     S.off_pmask = place((size_t)c->dp.n_primers * c->dp.ww * 4, true);
     S.off_heads = place((size_t)ix.n_postings * 8, !FAST && ix.k > 0);
     const int n_tiles = (R.n + kScanThreads - 1) / kScanThreads;
-    const int grid = std::max(1, std::min(n_tiles, 2 * c->sm_count));
+    const int grid = std::max(1, std::min(n_tiles, kScanMinBlocks * c->sm_count));
     if (cudaFuncSetAttribute(scan_kernel<RW, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) {
         set_error("cudaFuncSetAttribute(scan_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
         return IDP_ERR_CUDA;

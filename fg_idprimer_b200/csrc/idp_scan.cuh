@@ -20,8 +20,10 @@
 namespace idp {
 
 constexpr int kScanThreads = 512;
+constexpr int kScanMinBlocks = 2;
 constexpr int kScanWarps = kScanThreads / 32;
-constexpr int kBsPositions = 16;
+constexpr int kBsStride = 16;     // positions per group in the table (host layout)
+constexpr int kBsPositions = 12;  // positions the filter actually looks at
 
 struct ScanLaunch {
     int32_t stage_tile;        // 1: reads are fixed-length and 16-byte aligned: tiles are staged into shared memory by TMA
@@ -212,7 +214,7 @@ __device__ __forceinline__ bool diagonal_kmer(const DevPanel &P, const ScanCtx<R
 }
 
 template <int RW, bool FAST>
-__global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(DevPanel P, DevReads R, ScanLaunch S, idp_result *__restrict__ five,
+__global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(const __grid_constant__ DevPanel P, const __grid_constant__ DevReads R, const __grid_constant__ ScanLaunch S, idp_result *__restrict__ five,
                                                                unsigned int *__restrict__ fall, Counters *__restrict__ ctr) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t tile_bar[kScanWarps][2];
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(DevPanel P, DevRe
     }
     if (FAST && S.off_bsmm != 0xFFFFFFFFu) {
         uint32_t *d = reinterpret_cast<uint32_t *>(smem + S.off_bsmm);
-        for (int i = tid; i < P.bs_groups * kBsPositions * 16; i += blockDim.x) d[i] = P.bs_mm[i];
+        for (int i = tid; i < P.bs_groups * kBsStride * 16; i += blockDim.x) d[i] = P.bs_mm[i];
         bs_mm = d;
     }
     if (FAST && S.off_bsacc != 0xFFFFFFFFu) {
@@ -357,9 +359,6 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(DevPanel P, DevRe
                 Best2 best;
                 if (FAST) {
                     // survivors of the 16-base bit-sliced filter, ascending primer index (file order)
-                    uint32_t nx[kBsPositions];
-#pragma unroll
-                    for (int i = 0; i < kBsPositions; ++i) nx[i] = (i >> 3) < RW ? ((c.win[(i >> 3) < RW ? (i >> 3) : 0] >> (4 * (i & 7))) & 15u) : 0u;
                     int n_acc = 0, a_p = -1, a_mm = 0, a_plen = 1, a_seq = 0;
                     int q0 = -1, q1 = -1, q2 = -1, q3 = -1;
                     auto evaluate = [&](int p) {
@@ -378,11 +377,12 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_kernel(DevPanel P, DevRe
                         q0 = q1 = q2 = q3 = -1;
                     };
                     for (int g = 0; g < P.bs_groups; ++g) {
-                        const uint32_t *row = bs_mm + (size_t)g * (kBsPositions * 16);
+                        const uint32_t *row = bs_mm + (size_t)g * (kBsStride * 16);
                         uint32_t ones = 0, twos = 0;
 #pragma unroll
                         for (int i = 0; i < kBsPositions; ++i) {
-                            const uint32_t v = row[i * 16 + nx[i]];
+                            const uint32_t nib = (c.win[(i >> 3) < RW ? (i >> 3) : 0] >> (4 * (i & 7))) & 15u;
+                            const uint32_t v = row[i * 16 + nib];
                             twos |= ones & v;
                             ones |= v;
                         }
