@@ -381,11 +381,68 @@ __device__ int sw_score_generic(const DevPanel &P, const int32_t *__restrict__ s
     if constexpr ((NQ_) == 32) { switch (first) { IDP_ROWS32 default: break; } } \
     else { switch (first) { IDP_ROWS64 default: break; } }
 
+// Glocal, score only, in "shifted" coordinates X'(i,j) = X(i,j) - extend*(i+j): a gap extension then costs nothing
+// (U'(i,j) = max(D'(i-1,j) + open, U'(i-1,j)), same for Left) and the diagonal move adds s - 2*extend, so a cell is
+// LOP3 + SEL + IADD + 2 x VIADDMNMX + VIMNMX3.  The end cell converts back: M(n,j) = M'(n,j) + extend*(n+j).
+template <int NQ>
+__device__ __forceinline__ int sw_score_glocal_shifted(const DevPanel &P, const uint32_t *__restrict__ qbot, int n, int lo, int hi,
+                                                       const Oriented &T, int m) {
+    const int o = P.gap_open, e = P.gap_extend;
+    int ma = P.match_score - 2 * e, mi = P.mismatch_score - 2 * e;
+    asm volatile("" : "+r"(ma), "+r"(mi));  // live in registers: do not reload and re-derive them from the parameters in every row
+    const int off = NQ - n;
+    uint32_t q[NQ / 8];
+#pragma unroll
+    for (int w = 0; w < NQ / 8; ++w) q[w] = __ldg(&qbot[w]);
+    int D[NQ], L[NQ], M[NQ];
+#pragma unroll
+    for (int r = 0; r < NQ; ++r) { D[r] = kNegInf; L[r] = kNegInf; M[r] = o; }  // Up'(i,0) = open + i*extend - extend*i
+    int best = kNegInf;
+    TargetStream ts(T);
+    for (int j = 1; j <= m; ++j) {
+        uint32_t t = ts.nib(j - 1);
+        asm volatile("" : "+r"(t));
+        const uint32_t trep = t * 0x11111111u;
+        uint32_t ne[NQ / 8];
+#pragma unroll
+        for (int w = 0; w < NQ / 8; ++w) ne[w] = nib_nonzero(q[w] ^ trep);
+        int mdiag = -e * (j - 1), d_up = -e * j, u_up = -e * j;  // row 0 is all zero: shifted by -extend*(0+j)
+#define IDP_CELL(r)                                                                    \
+            const int dn = mdiag + ((ne[(r) >> 3] & (1u << (4 * ((r) & 7)))) ? mi : ma); \
+            const int un = __viaddmax_s32(d_up, o, u_up);                              \
+            const int ln = __viaddmax_s32(D[(r)], o, L[(r)]);                          \
+            const int mold = M[(r)];                                                   \
+            M[(r)] = __vimax3_s32(dn, ln, un);                                         \
+            D[(r)] = dn; L[(r)] = ln;
+#define IDP_ROW(r)                                                                     \
+    case (r): {                                                                        \
+        if ((r) >= hi) break;                                                          \
+        const bool act = (r) >= off;                                                   \
+        IDP_CELL(r)                                                                    \
+        mdiag = act ? mold : mdiag; d_up = act ? dn : d_up; u_up = act ? un : u_up;    \
+    }
+        IDP_SWITCH_ROWS(NQ, lo)
+#undef IDP_ROW
+#define IDP_ROW(r)                                                                     \
+    case (r): {                                                                        \
+        IDP_CELL(r)                                                                    \
+        mdiag = mold; d_up = dn; u_up = un;                                            \
+    }
+        IDP_SWITCH_ROWS(NQ, hi)
+#undef IDP_ROW
+#undef IDP_CELL
+        best = max(best, M[NQ - 1] + e * (n + j));  // last query row, this column, back in true coordinates
+    }
+    return best;
+}
+
 template <int NQ, bool LOCAL>
 __device__ __forceinline__ int sw_score_fast(const DevPanel &P, const uint32_t *__restrict__ qbot, int n, int lo, int hi, const Oriented &T, int m) {
     static_assert(NQ == 32 || NQ == 64, "row count");
-    const int oe = P.gap_open + P.gap_extend, e = P.gap_extend, ma = P.match_score, mi = P.mismatch_score;
     if (m == 0) return LOCAL ? 0 : P.gap_open + n * P.gap_extend;
+    if constexpr (!LOCAL) return sw_score_glocal_shifted<NQ>(P, qbot, n, lo, hi, T, m);
+    int oe = P.gap_open + P.gap_extend, e = P.gap_extend, ma = P.match_score, mi = P.mismatch_score;
+    asm volatile("" : "+r"(oe), "+r"(e), "+r"(ma), "+r"(mi));  // keep the constants in registers across the unrolled rows
     const int off = NQ - n;
     uint32_t q[NQ / 8];
 #pragma unroll
@@ -449,7 +506,8 @@ __device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint3
     static_assert(NQ == 32 || NQ == 64, "row count");
     TracedReg out{0, 1, 0};
     if (m == 0) { out.score = LOCAL ? 0 : P.gap_open + n * P.gap_extend; return out; }
-    const int oe = (P.gap_open + P.gap_extend) * 4096, e = P.gap_extend * 4096, ma = P.match_score * 4096, mi = P.mismatch_score * 4096;
+    int oe = (P.gap_open + P.gap_extend) * 4096, e = P.gap_extend * 4096, ma = P.match_score * 4096, mi = P.mismatch_score * 4096;
+    asm volatile("" : "+r"(oe), "+r"(e), "+r"(ma), "+r"(mi));  // keep the constants in registers across the unrolled rows
     constexpr int NEG = -(1 << 30);  // score -2^18
     const int off = NQ - n;
     uint32_t q[NQ / 8];
