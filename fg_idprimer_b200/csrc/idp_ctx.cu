@@ -54,7 +54,7 @@ struct Slot {
     // staging for the host-pointer path
     DevBuf seq4, seq_off, len, ref_idx, ustart, uend, flags, five, three;
     // scratch of the chain
-    DevBuf fall, all_list, seg_off, seg_cnt, pair_work, pair_primer, pair_score, pair_se, fin;
+    DevBuf fall, spill, all_list, seg_off, seg_cnt, pair_work, pair_primer, pair_score, pair_se, fin;
     Counters *d_ctr = nullptr, *h_ctr = nullptr;
     size_t pair_cap = 0;
     bool busy = false;
@@ -280,6 +280,7 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
     int rc;
     const bool k_gapped = p.kidx[1].k > 0, do3 = p.params.three_prime >= 0;
     if ((rc = s.fall.ensure(n * 4))) return rc;
+    if (k_gapped && (rc = s.spill.ensure(n * 4))) return rc;
     if (k_gapped || do3) {
         if (s.pair_cap < 2 * n + 4096) s.pair_cap = 2 * n + 4096;
         if ((rc = s.seg_off.ensure(n * 4)) || (rc = s.seg_cnt.ensure(n * 4)) || (rc = s.pair_work.ensure(s.pair_cap * 4)) ||
@@ -309,8 +310,11 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
         if (k_gapped) {
             const int words = (p.n + 31) / 32;
             const size_t smem = (size_t)8 * words * 4;
-            cand5_kernel<<<c->sm_count * 8, 256, smem, st>>>(c->dp, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(),
+            cand5_thread_kernel<<<c->sm_count * 8, 256, 0, st>>>(c->dp, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(),
+                                                                  (unsigned)s.pair_cap, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(), s.spill.as<unsigned>());
+            cand5_kernel<<<c->sm_count * 4, 256, smem, st>>>(c->dp, R, fall, s.spill.as<unsigned>(), ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(),
                                                             (unsigned)s.pair_cap, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>());
+            ++s.launches;
             CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st));
             launch_sw_pairs(c, st, false, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), (unsigned)s.pair_cap);
             CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st));
@@ -411,7 +415,7 @@ void idp_ctx_destroy(idp_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (Slot &s : c->slots) {
-        for (DevBuf *b : {&s.seq4, &s.seq_off, &s.len, &s.ref_idx, &s.ustart, &s.uend, &s.flags, &s.five, &s.three, &s.fall, &s.all_list,
+        for (DevBuf *b : {&s.seq4, &s.seq_off, &s.len, &s.ref_idx, &s.ustart, &s.uend, &s.flags, &s.five, &s.three, &s.fall, &s.spill, &s.all_list,
                           &s.seg_off, &s.seg_cnt, &s.pair_work, &s.pair_primer, &s.pair_score, &s.pair_se, &s.fin}) b->release();
         if (s.d_ctr) cudaFree(s.d_ctr);
         if (s.h_ctr) cudaFreeHost(s.h_ctr);

@@ -41,6 +41,8 @@ struct Counters {
     unsigned int n_pairs;         // (read, primer) pairs emitted for sw_pairs_kernel
     unsigned int n_all;           // 3' reads that take every primer
     unsigned int overflow;        // pair buffer too small: number of work items not emitted
+    unsigned int n_spill;         // fall-through reads with more -K candidates than the per-thread list holds
+    unsigned int pad0;
     unsigned long long n_align5;  // alignments performed by the 5' aligner (IP:424)
     unsigned long long n_align3;
     unsigned long long sw_cells;
@@ -130,9 +132,9 @@ __device__ __forceinline__ idp_result none_result() {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Candidate emission for the 5' gapped stage under -K: one warp per fall-through read.  Walks the read's k-mers in
-// order; a per-warp bitmap in shared memory implements `.distinct` (PM:114).  Pass 1 sets bits and counts, pass 2
-// clears them again while emitting, so the bitmap is zero for the next read.
+// Candidate emission for the 5' gapped stage under -K, common case: one THREAD per fall-through read keeps up to
+// kCandLocal distinct candidates in registers (first-hit order, PM:112-114).  Reads with more go to the spill list and
+// are handled by the warp kernel below.  Thousands of independent lookup chains in flight hide the table latency.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool kmer_lookup(const DevKmerIndex &ix, uint64_t key, OffCnt &oc) {
     if (key == 0) return false;
@@ -145,7 +147,76 @@ __device__ __forceinline__ bool kmer_lookup(const DevKmerIndex &ix, uint64_t key
     }
 }
 
+constexpr int kCandLocal = 8;
+
+__global__ void __launch_bounds__(256) cand5_thread_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ fall,
+                                                           Counters *__restrict__ ctr, unsigned int *__restrict__ pair_work,
+                                                           unsigned int *__restrict__ pair_primer, unsigned int pair_cap,
+                                                           unsigned int *__restrict__ seg_off, int *__restrict__ seg_cnt,
+                                                           unsigned int *__restrict__ spill) {
+    const DevKmerIndex &ix = P.kidx[1];
+    const unsigned n_work = ctr->n_fall;
+    const int lane = threadIdx.x & 31;
+    const uint64_t kmask = ix.k >= 16 ? ~0ull : ((1ull << (4 * ix.k)) - 1ull);
+    for (unsigned base = blockIdx.x * blockDim.x; base < n_work; base += gridDim.x * blockDim.x) {
+        const unsigned w = base + threadIdx.x;
+        const bool active = w < n_work;
+        int cand[kCandLocal];
+        int nc = 0;
+        bool spilled = false;
+        if (active) {
+            const int r = (int)fall[w];
+            const uint8_t *s; int len;
+            read_geom(R, r, s, len);
+            TargetStream ts(Oriented{s, len, seq_order_is_rc(R.flags[r])});
+            const int n_bases = len >= ix.k ? min(ix.window, len) : 0;  // k-mers start at 0 .. n_bases - k (PM:110)
+            uint64_t key = 0;
+            for (int i = 0; i < n_bases && !spilled; ++i) {
+                key = ((key << 4) | ts.nib(i)) & kmask;
+                OffCnt oc;
+                if (i < ix.k - 1 || !kmer_lookup(ix, key, oc)) continue;
+                for (uint32_t j = 0; j < oc.cnt; ++j) {
+                    const int p = (int)__ldg(&ix.postings[oc.off + j]);
+                    bool seen = false;
+#pragma unroll
+                    for (int t = 0; t < kCandLocal; ++t) seen |= (t < nc && cand[t] == p);
+                    if (seen) continue;
+                    if (nc == kCandLocal) { spilled = true; break; }
+#pragma unroll
+                    for (int t = 0; t < kCandLocal; ++t) if (t == nc) cand[t] = p;
+                    ++nc;
+                }
+            }
+        }
+        const int count = (active && !spilled) ? nc : 0;
+        int incl = count;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned rbase = 0;
+        if (lane == 31 && total) rbase = atomicAdd(&ctr->n_pairs, (unsigned)total);
+        rbase = __shfl_sync(0xffffffffu, rbase, 31);
+        if (active) {
+            if (spilled) { spill[atomicAdd(&ctr->n_spill, 1u)] = w; }
+            else if ((unsigned long long)rbase + total > pair_cap) { if (count) atomicAdd(&ctr->overflow, 1u); seg_off[w] = 0; seg_cnt[w] = count ? -1 : 0; }
+            else {
+                const unsigned at = rbase + (unsigned)(incl - count);
+                seg_off[w] = at; seg_cnt[w] = count;
+#pragma unroll
+                for (int t = 0; t < kCandLocal; ++t) if (t < count) { pair_work[at + t] = w; pair_primer[at + t] = (unsigned)cand[t]; }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Candidate emission for the 5' gapped stage under -K: one warp per fall-through read.  Walks the read's k-mers in
+// order; a per-warp bitmap in shared memory implements `.distinct` (PM:114).  Pass 1 sets bits and counts, pass 2
+// clears them again while emitting, so the bitmap is zero for the next read.
+// ---------------------------------------------------------------------------------------------------------------
+
 __global__ void __launch_bounds__(256) cand5_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ fall,
+                                                    const unsigned int *__restrict__ spill,
                                                     Counters *__restrict__ ctr, unsigned int *__restrict__ pair_work,
                                                     unsigned int *__restrict__ pair_primer, unsigned int pair_cap,
                                                     unsigned int *__restrict__ seg_off, int *__restrict__ seg_cnt) {
@@ -156,8 +227,9 @@ __global__ void __launch_bounds__(256) cand5_kernel(DevPanel P, DevReads R, cons
     for (int i = lane; i < words; i += 32) bitmap[i] = 0;
     __syncwarp();
     const DevKmerIndex &ix = P.kidx[1];
-    const unsigned n_work = ctr->n_fall;
-    for (unsigned w = blockIdx.x * warps_per_block + wib; w < n_work; w += gridDim.x * warps_per_block) {
+    const unsigned n_work = ctr->n_spill;
+    for (unsigned wi = blockIdx.x * warps_per_block + wib; wi < n_work; wi += gridDim.x * warps_per_block) {
+        const unsigned w = spill[wi];
         const int r = (int)fall[w];
         const uint16_t fl = R.flags[r];
         const uint8_t *s; int len;
