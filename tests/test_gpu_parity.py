@@ -372,3 +372,73 @@ def test_fast_filter_equals_exact_walk(name, n_pairs):
     if out[0][1] is not None:
         assert np.array_equal(out[0][1].view(np.uint8), out[1][1].view(np.uint8))
     assert np.array_equal(out[0][2], out[1][2]) and out[0][3] == out[1][3]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# input layouts: fixed-length batches of odd sizes (TMA tile tails), chunked host path on ragged reads, device pointers
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("read_len,n_reads", [(150, 1), (150, 31), (150, 33), (149, 1001), (151, 777), (36, 513), (21, 64)])
+def test_fixed_length_layouts(read_len, n_reads):
+    panel, reads, opts = synth.workload("c1", 1200)
+    codes = reads.codes[:n_reads, :read_len] if read_len <= 150 else np.concatenate(
+        [reads.codes[:n_reads], reads.codes[n_reads:2 * n_reads, :read_len - 150]], axis=1)
+    flags = np.full(n_reads, H.F_UNMAPPED, dtype=np.uint16)      # fragments
+    arrays = dict(bases=synth.codes_to_ascii(codes).reshape(-1), off=np.arange(n_reads + 1, dtype=np.int64) * read_len,
+                  ref_idx=np.full(n_reads, -1, np.int32), ustart=np.zeros(n_reads, np.int32), uend=np.zeros(n_reads, np.int32), flags=flags)
+    want5, _, want_metrics, want_align = O.Panel(_synth_primers(panel), _opts_to_oracle(opts)).process_batch(arrays, n_threads=4)
+    with idp.IdentifyPrimers(panel.primers, **opts) as tool:
+        got5, _ = tool.process_batch(idp.ReadBatch(synth.pack_fixed(codes).reshape(-1), flags, fixed_len=read_len))
+        assert_same(got5, want5, f"fixed_len={read_len}")
+        assert np.array_equal(tool.metric_counter, want_metrics) and tool.num_alignments == want_align
+
+
+def test_chunked_host_path_on_ragged_mapped_reads():
+    import os
+    panel, reads, opts = synth.workload("c5", 700)
+    rng = np.random.default_rng(3)
+    arr = reads.oracle_arrays()
+    # ragged: trim every read to a random length (mapped minus-strand reads keep their 3' end = sequencing 5' end)
+    lens = rng.integers(12, 151, reads.n)
+    bases, off = [], [0]
+    neg = (reads.flags & H.F_REVERSE) != 0
+    for i in range(reads.n):
+        row = arr["bases"][i * 150:(i + 1) * 150]
+        bases.append(row[150 - lens[i]:] if neg[i] else row[:lens[i]])
+        off.append(off[-1] + int(lens[i]))
+    ustart, uend = arr["ustart"].copy(), arr["uend"].copy()
+    ustart[neg] = uend[neg] - lens[neg] + 1
+    uend[~neg] = ustart[~neg] + lens[~neg] - 1
+    arrays = dict(bases=np.concatenate(bases), off=np.array(off, dtype=np.int64), ref_idx=arr["ref_idx"], ustart=ustart, uend=uend, flags=arr["flags"])
+    want5, want3, want_metrics, want_align = O.Panel(_synth_primers(panel), _opts_to_oracle(opts)).process_batch(arrays, n_threads=4)
+    for chunk in ("37", "256", "100000"):
+        os.environ["IDP_CHUNK_READS"] = chunk
+        try:
+            with idp.IdentifyPrimers(panel.primers, ref_names=panel.ref_names, **opts) as tool:
+                got5, got3 = tool.process_batch(idp.ReadBatch.from_ascii(arrays["bases"], arrays["off"], arrays["flags"], arrays["ref_idx"], ustart, uend))
+                assert_same(got5, want5, f"chunk {chunk} 5'")
+                assert_same(got3, want3, f"chunk {chunk} 3'")
+                assert np.array_equal(tool.metric_counter, want_metrics) and tool.num_alignments == want_align
+        finally:
+            os.environ.pop("IDP_CHUNK_READS", None)
+
+
+def test_device_pointer_entry_with_offsets():
+    import torch
+    panel, reads, opts = synth.workload("c5", 1200)
+    arr = reads.oracle_arrays()
+    want5, want3, want_metrics, want_align = O.Panel(_synth_primers(panel), _opts_to_oracle(opts)).process_batch(arr, n_threads=4)
+    batch = idp.ReadBatch.from_ascii(arr["bases"], arr["off"], arr["flags"], arr["ref_idx"], arr["ustart"], arr["uend"])
+    dev = torch.device("cuda", 0)
+    t = {k: torch.from_numpy(v.view(np.int64) if v.dtype == np.uint64 else (v.view(np.int16) if v.dtype == np.uint16 else v)).to(dev)
+         for k, v in dict(seq4=batch.seq4, seq_off=batch.seq_off, len=batch.len, ref=batch.ref_idx, us=batch.unclipped_start, ue=batch.unclipped_end, fl=batch.flags).items()}
+    f5 = torch.zeros((reads.n, 32), dtype=torch.uint8, device=dev)
+    f3 = torch.zeros((reads.n, 32), dtype=torch.uint8, device=dev)
+    with idp.IdentifyPrimers(panel.primers, ref_names=panel.ref_names, **opts) as tool:
+        tool.set_stream(torch.cuda.current_stream().cuda_stream)
+        metrics, n_align = tool.process_batch_device(reads.n, t["seq4"].data_ptr(), t["fl"].data_ptr(), f5.data_ptr(), f3.data_ptr(),
+                                                     seq_off_ptr=t["seq_off"].data_ptr(), len_ptr=t["len"].data_ptr(), ref_idx_ptr=t["ref"].data_ptr(),
+                                                     ustart_ptr=t["us"].data_ptr(), uend_ptr=t["ue"].data_ptr())
+        torch.cuda.synchronize()
+        assert_same(f5.cpu().numpy().view(L.RESULT_DTYPE).reshape(-1), want5, "device 5'")
+        assert_same(f3.cpu().numpy().view(L.RESULT_DTYPE).reshape(-1), want3, "device 3'")
+        assert np.array_equal(metrics, want_metrics) and n_align == want_align
