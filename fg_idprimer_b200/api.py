@@ -380,6 +380,22 @@ class IdentifyPrimers:
             tags["f5"] = self.info(three, flags)
         return tags
 
+    # ---- downstream classification (scripts/post_process_bam.py:56-78) ----
+    CLASS_NAMES = ["Canonical", "SelfDimer", "CrossDimer", "NonCanonical", "Single", "NoMatch"]
+
+    def classify_primer_pair(self, f5_primer: int, r5_primer: int, min_insert_length: int = 50, max_insert_length: int = 250) -> str:
+        return self.CLASS_NAMES[L.lib().idp_classify_primer_pair(self._panel, f5_primer, r5_primer, min_insert_length, max_insert_length)]
+
+    def classify_templates(self, flags, five, min_insert_length: int = 50, max_insert_length: int = 250):
+        """Per-read class codes and the six match-type counts (one per template whose first record is read 1)."""
+        flags = np.ascontiguousarray(flags, dtype=np.uint16)
+        five = np.ascontiguousarray(five, dtype=L.RESULT_DTYPE)
+        cls = np.zeros(len(flags), dtype=np.uint8)
+        counts = np.zeros(6, dtype=np.int64)
+        L.check(L.lib().idp_classify_templates(self._panel, flags.ctypes.data, five.ctypes.data, len(flags), min_insert_length, max_insert_length,
+                                               cls.ctypes.data, counts.ctypes.data))
+        return cls, dict(zip(self.CLASS_NAMES, counts.tolist()))
+
     # ---- metrics (TemplateTypeMetric.scala:34-56, IdentifyPrimersMetric.scala:34-89) ----
     def summary(self) -> dict:
         out = np.zeros(17, dtype=np.int64)

@@ -406,6 +406,44 @@ void idp_summary_metrics(const int64_t *m, int64_t *o) {  // IdentifyPrimersMetr
     memcpy(o, vals, sizeof vals);
 }
 
+// scripts/post_process_bam.py:56-78
+int idp_classify_primer_pair(const idp_panel *p, int32_t f5, int32_t r5, int32_t min_insert_length, int32_t max_insert_length) {
+    if (!p || f5 >= p->n || r5 >= p->n) return -1;
+    if (f5 < 0 && r5 < 0) return IDP_CLASS_NO_MATCH;
+    if (f5 < 0 || r5 < 0) return IDP_CLASS_SINGLE;
+    if (p->pair_id[f5] != p->pair_id[r5]) {  // from different primer pairs
+        if (p->ref_name[f5] != p->ref_name[r5]) return IDP_CLASS_CROSS_DIMER;
+        const int32_t insert_length = std::max(p->end[f5], p->end[r5]) - std::min(p->start[f5], p->start[r5]) + 1;  // :47-53
+        return (insert_length < min_insert_length || max_insert_length < insert_length) ? IDP_CLASS_CROSS_DIMER : IDP_CLASS_NON_CANONICAL;
+    }
+    if (p->primer_id[f5] == p->primer_id[r5]) return IDP_CLASS_SELF_DIMER;
+    if (p->positive[f5] == p->positive[r5]) return IDP_CLASS_NON_CANONICAL;
+    return IDP_CLASS_CANONICAL;
+}
+
+int idp_classify_templates(const idp_panel *p, const uint16_t *flags, const idp_result *five, int32_t n_reads, int32_t min_insert_length,
+                           int32_t max_insert_length, uint8_t *cls_per_read, int64_t *counts6) {
+    if (!p || !flags || !five || n_reads < 0) { set_error("idp_classify_templates: NULL argument"); return IDP_ERR_ARG; }
+    for (int32_t r = 0; r < n_reads;) {
+        const bool has_r2 = (flags[r] & IDP_F_MATE_NEXT) && r + 1 < n_reads;
+        const int32_t m1 = five[r].type != IDP_NONE ? five[r].primer : -1;
+        const int32_t m2 = has_r2 && five[r + 1].type != IDP_NONE ? five[r + 1].primer : -1;
+        int32_t f5 = m1, r5 = m2;
+        if (has_r2) {  // forward / reverse slots (IP:530-540)
+            bool fwd_is_r1 = true;
+            if (m1 >= 0) fwd_is_r1 = p->positive[m1] != 0;
+            else if (m2 >= 0) fwd_is_r1 = p->positive[m2] == 0;
+            if (!fwd_is_r1) { f5 = m2; r5 = m1; }
+        }
+        const int cls = idp_classify_primer_pair(p, f5, r5, min_insert_length, max_insert_length);
+        if (cls < 0) { set_error("idp_classify_templates: primer index out of range at read %d", r); return IDP_ERR_ARG; }
+        if (cls_per_read) { cls_per_read[r] = (uint8_t)cls; if (has_r2) cls_per_read[r + 1] = (uint8_t)cls; }
+        if (counts6 && (flags[r] & IDP_F_FIRST)) counts6[cls] += 1;  // "do not double-count": only record.is_read1
+        r += has_r2 ? 2 : 1;
+    }
+    return IDP_OK;
+}
+
 void idp_pack_bases(const char *ascii, int32_t n, uint8_t *seq4) {
     for (int32_t i = 0; i < n; i += 2) {
         int hi = base_to_nibble((unsigned char)ascii[i]);

@@ -190,6 +190,20 @@ int    idp_metric_bin(int template_type, int is_fr, int r1_type, int r2_type);
 void   idp_summary_metrics(const int64_t *metrics160, int64_t *out17);  /* IdentifyPrimersMetric.scala:34-89 */
 /* PrimerMatch.info(rec) (PMa:78-88), "none" for no match (IP:242); returns the string length */
 int    idp_format_info(const idp_panel *panel, const idp_result *r, uint16_t read_flags, char *buf, int32_t cap);
+/* Downstream pair classification (scripts/post_process_bam.py:56-78) on the forward / reverse 5' slots of addTagsToPair
+ * (IP:530-540).  idp_classify_primer_pair takes the primers in the f5 / r5 tags (-1 = "none").  idp_classify_templates walks a
+ * batch: cls_per_read[n] (may be NULL) receives the class of each read's template (both reads of a pair get the same value, as
+ * the script tags both records); counts6 (may be NULL) is ADDED to once per template whose first record is read 1
+ * (post_process_bam.py:159).  Pure host functions. */
+#define IDP_CLASS_CANONICAL     0
+#define IDP_CLASS_SELF_DIMER    1
+#define IDP_CLASS_CROSS_DIMER   2
+#define IDP_CLASS_NON_CANONICAL 3
+#define IDP_CLASS_SINGLE        4
+#define IDP_CLASS_NO_MATCH      5
+int    idp_classify_primer_pair(const idp_panel *panel, int32_t f5_primer, int32_t r5_primer, int32_t min_insert_length, int32_t max_insert_length);
+int    idp_classify_templates(const idp_panel *panel, const uint16_t *flags, const idp_result *five, int32_t n_reads,
+                              int32_t min_insert_length, int32_t max_insert_length, uint8_t *cls_per_read, int64_t *counts6);
 /* pack ASCII bases to BAM nibbles / back (htsjdk SAMUtils.bytesToCompressedBases semantics) */
 void   idp_pack_bases(const char *ascii, int32_t n, uint8_t *seq4);
 void   idp_unpack_bases(const uint8_t *seq4, int32_t n, char *ascii);

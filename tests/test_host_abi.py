@@ -142,3 +142,24 @@ def test_panel_validation_errors():
         idp.Primer("1", "x", "ACGU", True)                                      # Primer.scala:194-200
     with pytest.raises(ValueError):
         idp.Primer.validate_primers([good[0], good[0]], False)                  # Primer.scala:146-150
+
+
+def test_downstream_classification_matches_reference_script():
+    """scripts/post_process_bam.py:56-78, golden vectors produced by the reference's own function (tests/golden/gen_classify_golden.py)."""
+    import json
+    g = json.load(open(os.path.join(H.ROOT, "tests", "golden", "classify_golden.json")))
+    primers = [idp.Primer(p["pair_id"], p["primer_id"], p["sequence"], p["positive_strand"], p["ref_name"], p["start"], p["end"]) for p in g["primers"]]
+    tool = idp.IdentifyPrimers(primers, ref_names=["chr1", "chr2", "chr3"], device=None)
+    for c in g["cases"]:
+        assert tool.classify_primer_pair(c["f5"], c["r5"], c["min_insert"], c["max_insert"]) == c["expected"], c
+    # batch walk: slots of addTagsToPair (IdentifyPrimers.scala:530-540), fragments, counting only read-1 records
+    five = np.zeros(7, dtype=L.RESULT_DTYPE)
+    five["primer"] = [1, 0, -1, 3, 5, -1, 2]          # pair (p0_R, p0_F), pair (none, p1_R), fragment p2_R, pair (none, p1_F)
+    five["type"] = [2, 2, 0, 2, 2, 0, 2]
+    flags = np.array([H.F_PAIRED | H.F_FIRST | H.F_MATE_NEXT, H.F_PAIRED | H.F_SECOND, H.F_PAIRED | H.F_FIRST | H.F_MATE_NEXT, H.F_PAIRED | H.F_SECOND,
+                      0, H.F_PAIRED | H.F_FIRST | H.F_MATE_NEXT, H.F_PAIRED | H.F_SECOND], dtype=np.uint16)
+    cls, counts = tool.classify_templates(flags, five)
+    names = [tool.CLASS_NAMES[c] for c in cls]
+    assert names == ["Canonical", "Canonical", "Single", "Single", "Single", "Single", "Single"]
+    assert counts == {"Canonical": 1, "SelfDimer": 0, "CrossDimer": 0, "NonCanonical": 0, "Single": 2, "NoMatch": 0}
+    tool.close()
