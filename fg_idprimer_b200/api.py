@@ -204,6 +204,23 @@ class ReadBatch:
         seq4, boff, lens = cls.pack(bases, off)
         return cls(seq4, flags, boff, lens, ref_idx, unclipped_start, unclipped_end)
 
+    @classmethod
+    def from_bam(cls, bam: bytes):
+        """Uncompressed, queryname-grouped BAM alignment records -> (batch, rec_index); see idp_bam_to_batch."""
+        lib = L.lib()
+        buf = np.frombuffer(bam, dtype=np.uint8)
+        n = C.c_int32(0)
+        nbytes = C.c_uint64(0)
+        L.check(lib.idp_bam_scan(buf.ctypes.data, len(buf), C.byref(n), C.byref(nbytes)))
+        n = n.value
+        seq4 = np.zeros(nbytes.value, dtype=np.uint8)
+        seq_off = np.zeros(n, dtype=np.uint64)
+        length, ref_idx, us, ue, rec = (np.zeros(n, dtype=np.int32) for _ in range(5))
+        flags = np.zeros(n, dtype=np.uint16)
+        L.check(lib.idp_bam_to_batch(buf.ctypes.data, len(buf), seq4.ctypes.data, seq_off.ctypes.data, length.ctypes.data, ref_idx.ctypes.data,
+                                     us.ctypes.data, ue.ctypes.data, flags.ctypes.data, rec.ctypes.data))
+        return cls(seq4, flags, seq_off, length, ref_idx, us, ue), rec
+
     def as_struct(self, keep: list) -> L.IdpReads:
         r = L.IdpReads()
         ptr = lambda a: None if a is None else a.ctypes.data

@@ -204,6 +204,14 @@ int    idp_format_info(const idp_panel *panel, const idp_result *r, uint16_t rea
 int    idp_classify_primer_pair(const idp_panel *panel, int32_t f5_primer, int32_t r5_primer, int32_t min_insert_length, int32_t max_insert_length);
 int    idp_classify_templates(const idp_panel *panel, const uint16_t *flags, const idp_result *five, int32_t n_reads,
                               int32_t min_insert_length, int32_t max_insert_length, uint8_t *cls_per_read, int64_t *counts6);
+/* Host ingest: uncompressed BAM alignment records (the bytes inside the BGZF blocks: block_size-prefixed records, SAMv1 4.2),
+ * queryname-grouped as Bams.templateIterator consumes them (IP:288-289), into the arrays of idp_reads.  The record's own 4-bit
+ * `seq` bytes are copied unchanged; unclipped ends come from the CIGAR (PM:180, 186), IDP_F_FR_PAIR from the mate fields (fgbio
+ * SamRecord.isFrPair), IDP_F_MATE_NEXT from the grouping; secondary / supplementary records are skipped; reads come out R1 then
+ * R2 per template and rec_index[i] (may be NULL) is the ordinal of the BAM record behind read i.  idp_bam_scan sizes the arrays. */
+int    idp_bam_scan(const uint8_t *bam, size_t n_bytes, int32_t *n_reads, uint64_t *seq_bytes);
+int    idp_bam_to_batch(const uint8_t *bam, size_t n_bytes, uint8_t *seq4, uint64_t *seq_off, int32_t *len, int32_t *ref_idx,
+                        int32_t *unclipped_start, int32_t *unclipped_end, uint16_t *flags, int32_t *rec_index);
 /* pack ASCII bases to BAM nibbles / back (htsjdk SAMUtils.bytesToCompressedBases semantics) */
 void   idp_pack_bases(const char *ascii, int32_t n, uint8_t *seq4);
 void   idp_unpack_bases(const uint8_t *seq4, int32_t n, char *ascii);

@@ -442,3 +442,29 @@ def test_device_pointer_entry_with_offsets():
         assert_same(f5.cpu().numpy().view(L.RESULT_DTYPE).reshape(-1), want5, "device 5'")
         assert_same(f3.cpu().numpy().view(L.RESULT_DTYPE).reshape(-1), want3, "device 3'")
         assert np.array_equal(metrics, want_metrics) and n_align == want_align
+
+
+def test_maximum_sizes_and_empty_batch():
+    rng = np.random.default_rng(17)
+    seq = lambda n: "".join("ACGT"[x] for x in rng.integers(0, 4, n))
+    # longest supported primer (256 bases) and reads up to the 4095-base limit, 5' and 3' matching
+    primers = [H.Primer("L", "L+", seq(256), True), H.Primer("L", "L-", seq(255), False), H.Primer("S", "S+", seq(20), True), H.Primer("S", "S-", seq(33), False)]
+    recs = []
+    for i, n in enumerate([4095, 4000, 1000, 300, 256, 255, 40, 20]):
+        p = primers[i % 4]
+        body = list(p.sequence + seq(4095))[:n]
+        if i % 2 and n > 30:
+            del body[11]
+            body.append("A")
+        recs.append(H.Rec("".join(body), True, False))
+        recs.append(H.Rec(H.revcomp(p.sequence)[: max(1, n // 2)] + seq(10), True, False))   # primer at the 3' end of a short read
+    arrays = H.recs_to_arrays(recs)
+    run_both(primers, arrays, max_mismatch_rate=0.02, gapped_kmer_length=12, ungapped_kmer_length=8)
+    run_both(primers, arrays, max_mismatch_rate=0.02, three_prime=3, min_alignment_score_rate=0.0)
+    # an empty batch is legal
+    with idp.IdentifyPrimers([idp.Primer(p.pair_id, p.primer_id, p.sequence, p.positive_strand) for p in primers], three_prime=0) as tool:
+        five, three = tool.process_batch(idp.ReadBatch(np.zeros(0, np.uint8), np.zeros(0, np.uint16), seq_off=np.zeros(0, np.uint64), length=np.zeros(0, np.int32)))
+        assert len(five) == 0 and len(three) == 0 and tool.metric_counter.sum() == 0
+    # beyond the limits the library refuses instead of approximating
+    with pytest.raises(idp.IdpError):
+        idp.IdentifyPrimers([idp.Primer("x", "x+", seq(257), True), idp.Primer("x", "x-", seq(20), False)], device=None)
