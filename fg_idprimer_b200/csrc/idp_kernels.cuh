@@ -7,14 +7,18 @@
 //   results : idp_result (32 B) per read.
 //
 // Kernels (reference function each one covers)
-//   scan_kernel        basesInSequencingOrder (PM:39-45) + LocationBasedPrimerMatcher.find (PM:194-213) +
+//   scan_kernel (idp_scan.cuh)  basesInSequencingOrder (PM:39-45) + LocationBasedPrimerMatcher.find (PM:194-213) +
 //                      getPrimersForAlignmentTasks (PM:98-116) + mismatchAlign / numMismatches (PM:128-147) +
 //                      getBestUngappedAlignment (PM:237-248); reads with no match go to the fall-through list
-//   cand5_kernel       GappedAlignmentBasedPrimerMatcher.toAlignmentTasks candidates under -K (PM:287-296, 108-116)
+//   cand5_thread_kernel / cand5_kernel   GappedAlignmentBasedPrimerMatcher.toAlignmentTasks candidates under -K
+//                      (PM:287-296, 108-116): a thread per read with a register-resident distinct list, a warp per read
+//                      with a shared-memory bitmap for the reads that overflow it
 //   cand3_kernel       matchThreePrime's primersToCheck (IP:490-499)
-//   sw_pairs_kernel    fgbio Aligner.align, score only, one thread per (read, primer) pair (IP:446-448, 509-513)
-//   sw_all_kernel      the same when every primer is a candidate: one block per read, best two kept on chip
-//   finalize_kernel    getBestGappedAlignment (PM:305-328) + traceback of the winner + finalizedGappedAlignment (IP:459-471)
+//   sw_pairs_kernel    fgbio Aligner.align, one thread per (read, primer) pair (IP:446-448, 509-513); the packed variant
+//                      also yields targetStart / targetEnd
+//   sw_all_kernel      the same, score only, when every primer is a candidate: one block per read, best two kept on chip
+//   finalize_*_kernel  getBestGappedAlignment (PM:305-328) + (all-primers path) re-alignment of the winner with start
+//                      tracking + finalizedGappedAlignment (IP:459-471)
 //   metrics_kernel     TemplateType + TemplateTypeMetric counter (TemplateType.scala:52-63, IP:413)
 #pragma once
 #include <cuda_runtime.h>
@@ -356,8 +360,6 @@ __global__ void __launch_bounds__(256) cand3_kernel(DevPanel P, DevReads R, cons
 //   D(i,j) = s(q_i,t_j) + max(D,L,U)(i-1,j-1)      U(i,j) = max(D(i-1,j)+o+e, U(i-1,j)+e)
 //   L(i,j) = max(D(i,j-1)+o+e, L(i,j-1)+e)          M = max(D,L,U) is kept per row for the next column's diagonal
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int score_of(const DevPanel &P, uint32_t q, uint32_t t) { return q == t ? P.match_score : P.mismatch_score; }
-
 template <int NQ, bool LOCAL, bool SMAT>
 __device__ __forceinline__ int sw_score(const DevPanel &P, const int32_t *__restrict__ smat, const uint32_t *__restrict__ qwords, int n,
                                         int n_warp_max, const Oriented &T, int m, bool &missing) {

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
                         if (n_acc == 1) {
                             const int n_bases = min(ix.window, c.len);
                             if (diagonal_kmer<RW>(P, c, a_p, a_seq, ix.k, n_bases) || kmer_member_exact<RW>(P, c, a_p))
-                                best.offer(a_p, a_mm, __ddiv_rn((double)a_mm, (double)a_plen));
+                                best.offer(a_p, a_mm, 0.0);  // the only accepted candidate: its sort key is never compared
                         } else if (n_acc >= 2) {
                             kmer_scan_exact<RW>(P, c, best, ix.direct, ix.heads);  // ties: the reference's candidate order decides
                         }
