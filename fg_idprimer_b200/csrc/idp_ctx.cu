@@ -136,9 +136,9 @@ static int upload_panel(idp_ctx *c) {
     d.gap_open = p.params.gap_open; d.gap_extend = p.params.gap_extend;
     d.smat = nullptr;
     if (!p.smat16.empty()) { if ((rc = upload(p.smat16, c->b_smat))) return rc; d.smat = c->b_smat.as<int32_t>(); }
-    {   // (score << 12 | start) register traceback: |score| * (rows + columns) must stay below 2^17
+    {   // (score << 14 | rank << 12 | start) register traceback: |score| * (rows + columns) must stay below 2^16
         const long maxabs = std::max<long>({std::labs(d.match_score), std::labs(d.mismatch_score), std::labs((long)d.gap_open + d.gap_extend), std::labs(d.gap_extend)});
-        d.packed_trace_ok = d.smat == nullptr && maxabs * (kMaxPrimerBases + kMaxReadLen + 1) < (1L << 17);
+        d.packed_trace_ok = d.smat == nullptr && maxabs * (kMaxPrimerBases + kMaxReadLen + 1) < (1L << 16);
     }
     d.slop = p.params.slop; d.three_prime = p.params.three_prime;
     d.max_mismatch_rate = p.params.max_mismatch_rate; d.min_alignment_score_rate = p.params.min_alignment_score_rate;

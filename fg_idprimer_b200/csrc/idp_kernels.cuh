@@ -569,10 +569,14 @@ __device__ __forceinline__ int sw_score_fast(const DevPanel &P, const uint32_t *
     return best;
 }
 
-// Same, carrying where each path started: every value is (score << 12) | start, so one integer compare orders scores and
-// the winner's start rides along.  Requires |scores| * (rows + columns) < 2^17 (DevPanel::packed_trace_ok) and targets
-// shorter than 4096.  Tie rules are those of sw_trace() below.
-//   a.score >= b.score  <=>  (a | 0xFFF) >= b          a.score > b.score  <=>  a > (b | 0xFFF)
+// Same, carrying where each path started and resolving ties the way an explicit traceback would, in ONE integer per
+// matrix value:      value = (score << 14) | (rank << 12) | start
+// `start` (12 bits) is the target offset at which the path left the free first row / a zero cell.  `rank` (2 bits) is the
+// matrix the value belongs to -- Diagonal 3, Left 2, Up 1 -- so that a plain integer max of two candidates with equal scores
+// picks the one the reference prefers: Diagonal over Left over Up for the diagonal move, a gap opened from Diagonal over an
+// extended gap.  After each max the rank is re-stamped with one LOP3.  Requires |scores| * (rows + columns) < 2^16
+// (DevPanel::packed_trace_ok) and targets shorter than 4096.
+//   a.score > b.score  <=>  a > (b | 0x3FFF)
 struct TracedReg { int score, t_start, t_end; };
 
 template <int NQ, bool LOCAL>
@@ -580,9 +584,11 @@ __device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint3
     static_assert(NQ == 32 || NQ == 64, "row count");
     TracedReg out{0, 1, 0};
     if (m == 0) { out.score = LOCAL ? 0 : P.gap_open + n * P.gap_extend; return out; }
-    int oe = (P.gap_open + P.gap_extend) * 4096, e = P.gap_extend * 4096, ma = P.match_score * 4096, mi = P.mismatch_score * 4096;
+    constexpr int SH = 14, LOW = 0x3FFF, RANK = 0x3000, RD = 0x3000, RL = 0x2000, RU = 0x1000;
+    int oe = (P.gap_open + P.gap_extend) << SH, e = P.gap_extend * (1 << SH), ma = P.match_score << SH, mi = P.mismatch_score * (1 << SH);
+    oe = (P.gap_open + P.gap_extend) * (1 << SH);
     asm volatile("" : "+r"(oe), "+r"(e), "+r"(ma), "+r"(mi));  // keep the constants in registers across the unrolled rows
-    constexpr int NEG = -(1 << 30);  // score -2^18
+    constexpr int NEG = -(1 << 30);  // score -2^16
     const int off = NQ - n;
     uint32_t q[NQ / 8];
 #pragma unroll
@@ -590,8 +596,8 @@ __device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint3
     int D[NQ], L[NQ], M[NQ];
 #pragma unroll
     for (int r = 0; r < NQ; ++r) {
-        if (LOCAL) { D[r] = 0; L[r] = 0; M[r] = 0; }
-        else { D[r] = NEG; L[r] = NEG; M[r] = (P.gap_open + (r - off + 1) * P.gap_extend) * 4096; }  // Up(i,0), start 0
+        if (LOCAL) { D[r] = RD; L[r] = RL; M[r] = RD; }
+        else { D[r] = NEG | RD; L[r] = NEG | RL; M[r] = ((P.gap_open + (r - off + 1) * P.gap_extend) * (1 << SH)) | RU; }  // Up(i,0), start 0
     }
     int best = NEG, bi = 0, bj = 0;
     TargetStream ts(T);
@@ -602,23 +608,20 @@ __device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint3
         uint32_t ne[NQ / 8];
 #pragma unroll
         for (int w = 0; w < NQ / 8; ++w) ne[w] = nib_nonzero(q[w] ^ trep);
-        int mdiag = j - 1, d_up = j, u_up = j;  // row 0: score 0, path starts at this column
-#define IDP_CELL(r)                                                                                                            \
-            int dn = mdiag + ((ne[(r) >> 3] & (1u << (4 * ((r) & 7)))) ? mi : ma);                                              \
-            if (LOCAL) dn = dn < 0 ? j : dn; /* clamp at zero: the path (re)starts after this cell */                          \
-            int un, ln;                                                                                                        \
-            { const int a = d_up + oe, b = u_up + e; un = ((a | 0xFFF) >= b) ? a : b; } /* Diagonal over extending Up */       \
-            { const int a = D[(r)] + oe, b = L[(r)] + e; ln = ((a | 0xFFF) >= b) ? a : b; } /* Diagonal over extending Left */ \
-            int mn = dn; /* Diagonal, then Left, then Up */                                                                    \
-            mn = (ln > (mn | 0xFFF)) ? ln : mn;                                                                                \
-            mn = (un > (mn | 0xFFF)) ? un : mn;                                                                                \
-            const int mold = M[(r)];                                                                                           \
-            D[(r)] = dn; L[(r)] = ln; M[(r)] = mn;
+        int mdiag = j - 1, d_up = RD | j, u_up = RU | j;  // row 0: score 0, path starts at this column
+#define IDP_CELL(r)                                                                                              \
+            int dn = ((mdiag + ((ne[(r) >> 3] & (1u << (4 * ((r) & 7)))) ? mi : ma)) & ~RANK) | RD;               \
+            if (LOCAL) dn = dn < 0 ? (RD | j) : dn; /* clamp at zero: the path (re)starts after this cell */      \
+            const int un = (__viaddmax_s32(d_up, oe, u_up + e) & ~RANK) | RU; /* equal scores: opened from Diagonal */ \
+            const int ln = (__viaddmax_s32(D[(r)], oe, L[(r)] + e) & ~RANK) | RL;                                 \
+            const int mold = M[(r)];                                                                              \
+            M[(r)] = __vimax3_s32(dn, ln, un); /* equal scores: Diagonal, then Left, then Up */                   \
+            D[(r)] = dn; L[(r)] = ln;
         // Local best cell: lowest row, then lowest column; Left/Up values never win (each is bounded by a Diagonal value of a
         // cell scanned earlier, gap scores being <= 0, and ties go to the earlier cell)
 #define IDP_BEST(r, cond)                                                                      \
             if (LOCAL) {                                                                       \
-                const int ds = dn >> 12, bs = best >> 12;                                      \
+                const int ds = dn >> SH, bs = best >> SH;                                      \
                 const bool better = (cond) && (ds > bs || (ds == bs && (r) + 1 < bi));         \
                 best = better ? dn : best; bi = better ? (r) + 1 : bi; bj = better ? j : bj;   \
             }
@@ -644,11 +647,11 @@ __device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint3
 #undef IDP_BEST
         if (!LOCAL) {
             // last row, columns ascending, Diagonal / Left / Up, strict '>': Left(n,j) never exceeds an earlier Diagonal(n,j')
-            if (d_up > (best | 0xFFF)) { best = d_up; bj = j; }
-            if (u_up > (best | 0xFFF)) { best = u_up; bj = j; }
+            if (d_up > (best | LOW)) { best = d_up; bj = j; }
+            if (u_up > (best | LOW)) { best = u_up; bj = j; }
         }
     }
-    out.score = best >> 12; out.t_start = (best & 0xFFF) + 1; out.t_end = bj;
+    out.score = best >> SH; out.t_start = (best & 0xFFF) + 1; out.t_end = bj;
     return out;
 }
 
