@@ -201,12 +201,17 @@ static int launch_scan_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, i
     S.off_heads = place((size_t)ix.n_postings * 8, !FAST && ix.k > 0);
     const int n_tiles = (R.n + kScanThreads - 1) / kScanThreads;
     const int grid = std::max(1, std::min(n_tiles, kScanMinBlocks * c->sm_count));
-    if (cudaFuncSetAttribute(scan_kernel<RW, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(scan_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return IDP_ERR_CUDA;
-    }
-    scan_kernel<RW, FAST><<<grid, kScanThreads, used, st>>>(c->dp, R, S, five, fall, ctr);
-    return IDP_OK;
+    const bool onchip = FAST && S.stage_tile && S.off_bsmm != 0xFFFFFFFFu && S.off_bsacc != 0xFFFFFFFFu;
+    auto launch = [&](auto kernel) -> int {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(scan_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return IDP_ERR_CUDA;
+        }
+        kernel<<<grid, kScanThreads, used, st>>>(c->dp, R, S, five, fall, ctr);
+        return IDP_OK;
+    };
+    if (FAST && onchip) return launch(scan_kernel<RW, FAST, FAST>);
+    return launch(scan_kernel<RW, FAST, false>);
 }
 template <int RW>
 static int launch_scan(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp_result *five, unsigned *fall, Counters *ctr) {

@@ -213,7 +213,9 @@ __device__ __forceinline__ bool diagonal_kmer(const DevPanel &P, const ScanCtx<R
     return run != 0ull;
 }
 
-template <int RW, bool FAST>
+// ONCHIP: the read tiles and the bit-sliced tables are known at compile time to sit in shared memory, so the hot loads are
+// LDS rather than generic loads (the launcher picks it when the shared-memory plan placed all of them)
+template <int RW, bool FAST, bool ONCHIP>
 __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(const __grid_constant__ DevPanel P, const __grid_constant__ DevReads R, const __grid_constant__ ScanLaunch S, idp_result *__restrict__ five,
                                                                unsigned int *__restrict__ fall, Counters *__restrict__ ctr) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -251,12 +253,16 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
     if (FAST && S.off_bsmm != 0xFFFFFFFFu) {
         uint32_t *d = reinterpret_cast<uint32_t *>(smem + S.off_bsmm);
         for (int i = tid; i < P.bs_groups * kBsStride * 16; i += blockDim.x) d[i] = P.bs_mm[i];
-        bs_mm = d;
+        if (!ONCHIP) bs_mm = d;
     }
     if (FAST && S.off_bsacc != 0xFFFFFFFFu) {
         uint2 *d = reinterpret_cast<uint2 *>(smem + S.off_bsacc);
         for (int i = tid; i < P.bs_groups; i += blockDim.x) d[i] = P.bs_acc[i];
-        bs_acc = d;
+        if (!ONCHIP) bs_acc = d;
+    }
+    if (ONCHIP) {  // provably shared pointers
+        bs_mm = reinterpret_cast<const uint32_t *>(smem + S.off_bsmm);
+        bs_acc = reinterpret_cast<const uint2 *>(smem + S.off_bsacc);
     }
     if (S.stage_tile && lane == 0) {
         mbar_init(&tile_bar[wib][0], 1);
@@ -300,12 +306,21 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
             const uint8_t *s;
             read_geom(R, r, s, c.len);
             const bool rc = seq_order_is_rc(fl);
-            const uint8_t *sp = S.stage_tile ? wbuf[cur] + (size_t)lane * S.stride : s;  // shared or global
+            const uint8_t *sp = ONCHIP ? smem + (size_t)(2 * wib + cur) * S.tile_smem_bytes + (size_t)lane * S.stride
+                                       : (S.stage_tile ? wbuf[cur] + (size_t)lane * S.stride : s);  // shared or global
             // ---- basesInSequencingOrder (PM:39-45), only the prefix the matchers can look at ----
             if (!rc && ((c.len + 1) >> 1) >= 4 * RW + 4) {
-                const uintptr_t a = reinterpret_cast<uintptr_t>(sp);
-                const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
-                const int sh = (int)(a & 3) * 8;
+                const uint32_t *wp;
+                int sh;
+                if (ONCHIP) {  // index the shared array itself (16-byte aligned) so the loads stay LDS
+                    const uint32_t bo = (uint32_t)(2 * wib + cur) * S.tile_smem_bytes + (uint32_t)lane * S.stride;
+                    wp = reinterpret_cast<const uint32_t *>(smem) + (bo >> 2);
+                    sh = (int)(bo & 3u) * 8;
+                } else {
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(sp);
+                    wp = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+                    sh = (int)(a & 3) * 8;
+                }
                 uint32_t prev = wp[0];
 #pragma unroll
                 for (int w = 0; w < RW; ++w) {
