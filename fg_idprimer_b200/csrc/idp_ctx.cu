@@ -127,7 +127,7 @@ static int upload_panel(idp_ctx *c) {
         }
     }
     if ((rc = upload(p.bs_mm, c->b_bsmm)) || (rc = upload(p.bs_acc, c->b_bsacc))) return rc;
-    d.bs_mm = c->b_bsmm.as<uint32_t>(); d.bs_acc = c->b_bsacc.as<uint2>(); d.bs_groups = (p.n + 31) / 32;
+    d.bs_mm = c->b_bsmm.as<uint32_t>(); d.bs_acc = c->b_bsacc.as<uint2>(); d.bs_groups = (int)(p.bs_acc.size() / 2);
     d.bs_ok = p.acc_max <= 1 && p.window_bases <= 64;
     if ((rc = upload(p.mate_off, c->b_mate_off))) return rc;
     if ((rc = upload(p.mate_idx, c->b_mate_idx))) return rc;
@@ -185,16 +185,16 @@ static int launch_scan_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, i
         used = (size_t)S.tile_smem_bytes * 2 * kScanWarps;
         if (used > budget - 16 * 1024) { S.stage_tile = 0; S.tile_smem_bytes = 0; used = 0; }
     }
-    auto place = [&](size_t bytes, bool wanted) -> uint32_t {
+    auto place = [&](size_t bytes, bool wanted, size_t align = 16) -> uint32_t {
         bytes = (bytes + 15) & ~size_t(15);
-        if (!wanted || bytes == 0 || used + bytes > budget) return 0xFFFFFFFFu;
-        const uint32_t off = (uint32_t)used;
-        used += bytes;
-        return off;
+        const size_t at = (used + align - 1) & ~(align - 1);
+        if (!wanted || bytes == 0 || at + bytes > budget) return 0xFFFFFFFFu;
+        used = at + bytes;
+        return (uint32_t)at;
     };
     S.direct_entries = ix.direct ? (1u << (2 * ix.k)) : 0;
     S.off_bsacc = place((size_t)c->dp.bs_groups * sizeof(uint2), FAST);
-    S.off_bsmm = place((size_t)c->dp.bs_groups * kBsStride * 16 * 4, FAST);
+    S.off_bsmm = place((size_t)c->dp.bs_groups * kBsStride * 16 * 4, FAST, 64);  // 64-byte aligned: table offsets are OR-ed in
     S.off_direct = place((size_t)S.direct_entries * 4, !FAST && ix.direct != nullptr);
     S.off_pinfo = place((size_t)c->dp.n_primers * sizeof(int4), true);
     S.off_pmask = place((size_t)c->dp.n_primers * c->dp.ww * 4, true);

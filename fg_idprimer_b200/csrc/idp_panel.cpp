@@ -307,7 +307,7 @@ int idp_panel_create(const idp_primer *primers, int32_t n, const idp_params *par
     }
     // bit-sliced filter over the first 16 bases, 32 primers per word
     {
-        const int groups = (n + 31) / 32;
+        const int groups = (((n + 31) / 32) + 1) & ~1;  // an even count: the kernel unrolls 2 / 4 / 6 / 8 groups; a padding group accepts nothing
         p->bs_mm.assign((size_t)groups * 16 * 16, 0);
         p->bs_acc.assign((size_t)groups * 2, 0);
         for (int i = 0; i < n; ++i) {

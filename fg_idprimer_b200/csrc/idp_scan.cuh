@@ -213,6 +213,44 @@ __device__ __forceinline__ bool diagonal_kmer(const DevPanel &P, const ScanCtx<R
     return run != 0ull;
 }
 
+template <int... I, class F>
+__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, I...>, F &&f) { (f(std::integral_constant<int, I>{}), ...); }
+template <int N, class F>
+__device__ __forceinline__ void static_for(F &&f) { static_for_impl(std::make_integer_sequence<int, N>{}, f); }
+
+// The bit-sliced filter for a compile-time number of 32-primer groups, tables in shared memory at a 64-byte aligned address
+// `tab`.  The per-position table offsets (nibble * 4, OR-ed into the aligned base) are formed once per read; every lookup is
+// then one LDS with an immediate offset and the two bit planes cost two LOP3.  Reports the number of survivors and the first
+// one (lowest primer index); the caller re-runs the general loop only when a read has more than one survivor.
+template <int G, int RW>
+__device__ __forceinline__ void bs_filter_fixed(uint32_t tab, uint32_t acc, const uint32_t *win, int &n_surv, uint32_t &first_word, int &first_group) {
+    uint32_t o[kBsPositions];
+#pragma unroll
+    for (int i = 0; i < kBsPositions; ++i) {
+        const uint32_t w = win[(i >> 3) < RW ? (i >> 3) : 0];
+        const int s = 4 * (i & 7);
+        o[i] = ((s == 0 ? (w << 2) : (w >> (s - 2))) & 0x3Cu) | tab;
+    }
+    static_for<G>([&](auto gc) {
+        constexpr int g = decltype(gc)::value;
+        uint32_t ones = 0, twos = 0;
+        static_for<kBsPositions>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            uint32_t v;
+            asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(o[i]), "n"((g * kBsStride + i) * 64));
+            twos |= ones & v;
+            ones |= v;
+        });
+        uint32_t ax, ay;
+        asm("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(ax), "=r"(ay) : "r"(acc), "n"(g * 8));
+        const uint32_t surv = ax & ~twos & (~ones | ay);  // at most acc (0 or 1) mismatches in the positions looked at
+        const bool first = surv != 0u && n_surv == 0;
+        first_word = first ? surv : first_word;
+        first_group = first ? g : first_group;
+        n_surv += __popc(surv);
+    });
+}
+
 // ONCHIP: the read tiles and the bit-sliced tables are known at compile time to sit in shared memory, so the hot loads are
 // LDS rather than generic loads (the launcher picks it when the shared-memory plan placed all of them)
 template <int RW, bool FAST, bool ONCHIP>
@@ -264,6 +302,8 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
         bs_mm = reinterpret_cast<const uint32_t *>(smem + S.off_bsmm);
         bs_acc = reinterpret_cast<const uint2 *>(smem + S.off_bsacc);
     }
+    const uint32_t tab_addr = ONCHIP ? smem_u32(smem) + S.off_bsmm : 0u, acc_addr = ONCHIP ? smem_u32(smem) + S.off_bsacc : 0u;
+    const bool fixed_groups = ONCHIP && (tab_addr & 63u) == 0u && P.bs_groups >= 2 && P.bs_groups <= 8 && (P.bs_groups & 1) == 0;
     if (S.stage_tile && lane == 0) {
         mbar_init(&tile_bar[wib][0], 1);
         mbar_init(&tile_bar[wib][1], 1);
@@ -391,7 +431,20 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
                         if (q3 >= 0) evaluate(q3);
                         q0 = q1 = q2 = q3 = -1;
                     };
-                    for (int g = 0; g < P.bs_groups; ++g) {
+                    int n_surv = 2;  // "unknown": the general loop below decides
+                    if (ONCHIP && fixed_groups) {
+                        uint32_t first_word = 0;
+                        int first_group = 0;
+                        n_surv = 0;
+                        switch (P.bs_groups) {
+                            case 2: bs_filter_fixed<2, RW>(tab_addr, acc_addr, c.win, n_surv, first_word, first_group); break;
+                            case 4: bs_filter_fixed<4, RW>(tab_addr, acc_addr, c.win, n_surv, first_word, first_group); break;
+                            case 6: bs_filter_fixed<6, RW>(tab_addr, acc_addr, c.win, n_surv, first_word, first_group); break;
+                            default: bs_filter_fixed<8, RW>(tab_addr, acc_addr, c.win, n_surv, first_word, first_group); break;
+                        }
+                        if (n_surv == 1) q0 = first_group * 32 + __ffs(first_word) - 1;
+                    }
+                    for (int g = 0; n_surv >= 2 && g < P.bs_groups; ++g) {
                         const uint32_t *row = bs_mm + (size_t)g * (kBsStride * 16);
                         uint32_t ones = 0, twos = 0;
 #pragma unroll
