@@ -58,6 +58,12 @@ struct DevPanel {
     const uint2 *bs_acc;
     int32_t bs_groups;
     int32_t bs_ok;             // every primer accepts at most one mismatch, so two bit planes decide the filter
+    // seed index over the first 2*S read bases (pigeonhole: at most one mismatch => one of the two S-base seeds matches a
+    // primer exactly).  seed_tab[t * seed_slots + hash(seed t)] = count | (primer or offset into seed_list) << 8; the table
+    // holds every read spelling (non-empty submasks of the IUPAC codes) a primer's seed matches without a mismatch
+    const uint32_t *seed_tab;
+    const uint32_t *seed_list;
+    int32_t seed_ok, seed_S, seed_shift, seed_slots;
     // pair_id groups for 3' matching (IP:496): opposite-strand primers of the same pair, file order
     const int32_t *mate_off;   // [n+1]
     const int32_t *mate_idx;
@@ -97,5 +103,7 @@ struct idp_panel {
     std::vector<int32_t> smat16;              // 16*16 nibble scoring table or empty
     std::vector<uint32_t> bs_mm, bs_acc;      // bit-sliced filter tables (see DevPanel)
     int32_t acc_max = -1;
+    std::vector<uint32_t> seed_tab, seed_list;  // seed index (see DevPanel); empty when the panel is not eligible
+    int32_t seed_S = 0, seed_shift = 0, seed_slots = 0;
     idp::KmerIndexHost kidx[2];
 };

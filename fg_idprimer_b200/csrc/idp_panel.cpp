@@ -322,6 +322,67 @@ int idp_panel_create(const idp_primer *primers, int32_t n, const idp_params *par
             }
         }
     }
+    // seed index for the ungapped scan: when every primer tolerates at most one mismatch (PM:130-134), a primer accepted for
+    // a read matches one of the read's two leading S-base seeds without a mismatch.  Each primer seed is entered under every
+    // read spelling it matches (PM:143: the read code must be a non-empty submask of the primer code).
+    {
+        int min_len = INT32_MAX;
+        for (int i = 0; i < n; ++i) min_len = std::min(min_len, p->seq_len[i]);
+        const int S = (min_len >= 16 && n > 512) ? 8 : 6;
+        bool ok = n > 0 && p->acc_max <= 1 && min_len >= 2 * S && n < (1 << 24);
+        std::vector<std::pair<uint32_t, uint32_t>> ent[2];  // (seed key, primer)
+        for (int i = 0; ok && i < n; ++i)
+            for (int t = 0; ok && t < 2; ++t) {
+                uint32_t codes[8];
+                size_t variants = 1;
+                for (int j = 0; j < S; ++j) {
+                    codes[j] = (uint32_t)base_to_nibble((unsigned char)p->sequence[i][t * S + j]) & 15u;
+                    variants *= (size_t(1) << __builtin_popcount(codes[j])) - 1;
+                }
+                if (variants == 0 || variants > 1024) { ok = false; break; }
+                uint32_t sub[8];
+                for (int j = 0; j < S; ++j) sub[j] = codes[j];  // largest submask first
+                for (;;) {
+                    uint32_t key = 0;
+                    for (int j = 0; j < S; ++j) key |= sub[j] << (4 * j);
+                    ent[t].emplace_back(key, (uint32_t)i);
+                    int j = 0;  // odometer over the non-empty submasks of every position
+                    for (; j < S; ++j) {
+                        sub[j] = (sub[j] - 1) & codes[j];
+                        if (sub[j] != 0) break;
+                        sub[j] = codes[j];
+                    }
+                    if (j == S) break;
+                }
+            }
+        const size_t most = std::max(ent[0].size(), ent[1].size());
+        if (ok && most > (size_t(1) << 22)) ok = false;
+        if (ok) {
+            int bits = 10;
+            while ((size_t(1) << bits) < 4 * most) ++bits;
+            const uint32_t slots = 1u << bits;
+            std::vector<uint32_t> tab(2 * (size_t)slots, 0u), list;
+            for (int t = 0; ok && t < 2; ++t) {
+                std::vector<std::vector<uint32_t>> per(slots);
+                for (auto &e : ent[t]) per[(e.first * 0x9E3779B1u) >> (32 - bits)].push_back(e.second);
+                for (uint32_t s = 0; ok && s < slots; ++s) {
+                    auto &v = per[s];
+                    if (v.empty()) continue;
+                    std::sort(v.begin(), v.end());
+                    v.erase(std::unique(v.begin(), v.end()), v.end());
+                    if (v.size() > 255 || list.size() + v.size() >= (size_t(1) << 24)) { ok = false; break; }
+                    if (v.size() == 1) { tab[(size_t)t * slots + s] = 1u | (v[0] << 8); continue; }
+                    tab[(size_t)t * slots + s] = (uint32_t)v.size() | ((uint32_t)list.size() << 8);
+                    list.insert(list.end(), v.begin(), v.end());
+                }
+            }
+            if (ok) {
+                p->seed_tab.swap(tab);
+                p->seed_list.swap(list);
+                p->seed_S = S; p->seed_shift = 32 - bits; p->seed_slots = (int32_t)slots;
+            }
+        }
+    }
     // location matcher (PM:162-172): one sorted array per strand
     for (int strand = 0; strand < 2; ++strand) {  // 0 = positive, 1 = negative
         std::vector<int> ids;

@@ -30,7 +30,7 @@ struct ScanLaunch {
     uint32_t stride;           // bytes per read when fixed-length
     uint32_t tile_smem_bytes;  // shared-memory bytes of one warp tile buffer (incl. slack), multiple of 16
     // byte offsets into dynamic shared memory, or 0xFFFFFFFF when the structure stays in global memory
-    uint32_t off_direct, off_heads, off_pmask, off_pinfo, off_bsmm, off_bsacc;
+    uint32_t off_direct, off_heads, off_pmask, off_pinfo, off_bsmm, off_bsacc, off_seed;
     uint32_t direct_entries;
 };
 
@@ -251,6 +251,45 @@ __device__ __forceinline__ void bs_filter_fixed(uint32_t tab, uint32_t acc, cons
     });
 }
 
+// Seed lookup (DevPanel::seed_ok): the read's two leading S-base seeds are hashed into the panel's seed tables; every
+// listed primer is checked on the first 2*S bases (at most one mismatch) and the survivors are kept in ascending primer
+// order (file order) in s0..s3, INT_MAX = empty.  Exact for every read whose first 2*S codes are non-zero: an accepted
+// primer has at most one mismatch, so it matches one seed without a mismatch and is listed under the read's spelling of
+// it.  Returns false when the read has to take the general loop instead (a zero code in the head: a read shorter than
+// 2*S or the '=' code; or more than four survivors).
+template <int RW>
+__device__ __forceinline__ bool seed_filter(const DevPanel &P, ScanCtx<RW> &c, const uint32_t *tab, int &s0, int &s1, int &s2, int &s3) {
+    const bool six = P.seed_S == 6;
+    const uint32_t w0 = c.win[0];
+    const uint32_t h1 = RW > 1 ? (six ? (c.win[RW > 1 ? 1 : 0] & 0xFFFFu) : c.win[RW > 1 ? 1 : 0]) : 0u;  // head = w0 + h1
+    if (nib_nonzero(w0) != 0x11111111u || nib_nonzero(h1) != (six ? 0x1111u : 0x11111111u)) return false;
+    const uint32_t key0 = six ? (w0 & 0xFFFFFFu) : w0;
+    const uint32_t key1 = six ? ((w0 >> 24) | (h1 << 8)) : h1;
+    s0 = s1 = s2 = s3 = INT_MAX;
+    bool fits = true;
+    unsigned verified = 0;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const uint32_t e = tab[(uint32_t)t * (uint32_t)P.seed_slots + (((t ? key1 : key0) * 0x9E3779B1u) >> P.seed_shift)];
+        const uint32_t cnt = e & 0xFFu, val = e >> 8;
+        for (uint32_t j = 0; j < cnt; ++j) {
+            const int p = cnt == 1u ? (int)val : (int)__ldg(&P.seed_list[val + j]);
+            if (p == s0 || p == s1 || p == s2 || p == s3) continue;
+            const uint32_t *pm = c.pmask + (size_t)p * P.ww;
+            ++verified;
+            if (__popc(nib_nonzero(w0 & ~pm[0])) + __popc(nib_nonzero(h1 & ~pm[1])) > 1) continue;
+            int x = p, y;  // sorted insertion; whatever falls off the end did not fit
+            y = s0; s0 = min(x, y); x = max(x, y);
+            y = s1; s1 = min(x, y); x = max(x, y);
+            y = s2; s2 = min(x, y); x = max(x, y);
+            y = s3; s3 = min(x, y); x = max(x, y);
+            fits = fits && x == INT_MAX;
+        }
+    }
+    c.compares += verified * 2u * (unsigned)P.seed_S;
+    return fits;
+}
+
 // ONCHIP: the read tiles and the bit-sliced tables are known at compile time to sit in shared memory, so the hot loads are
 // LDS rather than generic loads (the launcher picks it when the shared-memory plan placed all of them)
 template <int RW, bool FAST, bool ONCHIP>
@@ -298,6 +337,12 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
         for (int i = tid; i < P.bs_groups; i += blockDim.x) d[i] = P.bs_acc[i];
         if (!ONCHIP) bs_acc = d;
     }
+    const uint32_t *seed_tab = P.seed_tab;
+    if (FAST && P.seed_ok && S.off_seed != 0xFFFFFFFFu) {
+        uint32_t *d = reinterpret_cast<uint32_t *>(smem + S.off_seed);
+        for (int i = tid; i < 2 * P.seed_slots; i += blockDim.x) d[i] = P.seed_tab[i];
+        seed_tab = d;
+    }
     if (ONCHIP) {  // provably shared pointers
         bs_mm = reinterpret_cast<const uint32_t *>(smem + S.off_bsmm);
         bs_acc = reinterpret_cast<const uint2 *>(smem + S.off_bsacc);
@@ -311,8 +356,8 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
     }
     __syncthreads();
     // ---- every warp walks its own 32-read tiles: no CTA-wide barrier from here on ----
-    unsigned char *wbuf[2] = {smem + (size_t)(2 * wib) * S.tile_smem_bytes, smem + (size_t)(2 * wib + 1) * S.tile_smem_bytes};
-    uint32_t phase[2] = {0u, 0u};
+    auto wbuf = [&](int b) { return smem + (size_t)(2 * wib + b) * S.tile_smem_bytes; };  // two tile buffers per warp
+    uint32_t phase = 0u;  // bit b: parity of the next completion of buffer b
     const int n_wtiles = (R.n + 31) / 32;
     const int warps_total = gridDim.x * kScanWarps;
     unsigned long long compares_total = 0;
@@ -323,31 +368,36 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
         if (lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&tile_bar[wib][b], bulk);
-            if (bulk) tma_load_1d(wbuf[b], R.seq4 + g0, bulk, &tile_bar[wib][b]);
+            if (bulk) tma_load_1d(wbuf(b), R.seq4 + g0, bulk, &tile_bar[wib][b]);
         }
-        if (lane < (int)(bytes - bulk)) wbuf[b][bulk + lane] = R.seq4[g0 + bulk + lane];
+        if (lane < (int)(bytes - bulk)) wbuf(b)[bulk + lane] = R.seq4[g0 + bulk + lane];
     };
     int cur = 0;
     const int wt0 = blockIdx.x * kScanWarps + wib;
     if (S.stage_tile && wt0 < n_wtiles) issue_tile(wt0, 0);
+    uint16_t fl_next = (wt0 < n_wtiles && wt0 * 32 + lane < R.n) ? R.flags[wt0 * 32 + lane] : (uint16_t)0;
     for (int wt = wt0; wt < n_wtiles; wt += warps_total) {
         const int r = wt * 32 + lane;
         const bool active = r < R.n;
+        const uint16_t fl = fl_next;
+        {   // the next tile's flags travel while this tile is matched
+            const int rn = (wt + warps_total) * 32 + lane;
+            if (wt + warps_total < n_wtiles && rn < R.n) fl_next = R.flags[rn];
+        }
         if (S.stage_tile) {
             if (wt + warps_total < n_wtiles) issue_tile(wt + warps_total, cur ^ 1);  // prefetch; that buffer was released below
-            mbar_wait(&tile_bar[wib][cur], phase[cur]);
-            phase[cur] ^= 1u;
+            mbar_wait(&tile_bar[wib][cur], (phase >> cur) & 1u);
+            phase ^= 1u << cur;
             __syncwarp();  // tail bytes visible
         }
         bool need_gapped = false;
         c.compares = 0;
         if (active) {
-            const uint16_t fl = R.flags[r];
             const uint8_t *s;
             read_geom(R, r, s, c.len);
             const bool rc = seq_order_is_rc(fl);
             const uint8_t *sp = ONCHIP ? smem + (size_t)(2 * wib + cur) * S.tile_smem_bytes + (size_t)lane * S.stride
-                                       : (S.stage_tile ? wbuf[cur] + (size_t)lane * S.stride : s);  // shared or global
+                                       : (S.stage_tile ? wbuf(cur) + (size_t)lane * S.stride : s);  // shared or global
             // ---- basesInSequencingOrder (PM:39-45), only the prefix the matchers can look at ----
             if (!rc && ((c.len + 1) >> 1) >= 4 * RW + 4) {
                 const uint32_t *wp;
@@ -432,7 +482,17 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
                         q0 = q1 = q2 = q3 = -1;
                     };
                     int n_surv = 2;  // "unknown": the general loop below decides
-                    if (ONCHIP && fixed_groups) {
+                    bool seeded = false;
+                    if (P.seed_ok) {
+                        int s0, s1, s2, s3;
+                        if (seed_filter<RW>(P, c, seed_tab, s0, s1, s2, s3)) {
+                            seeded = true;
+                            n_surv = 0;
+                            q0 = s0 == INT_MAX ? -1 : s0; q1 = s1 == INT_MAX ? -1 : s1;
+                            q2 = s2 == INT_MAX ? -1 : s2; q3 = s3 == INT_MAX ? -1 : s3;
+                        }
+                    }
+                    if (!seeded && ONCHIP && fixed_groups) {
                         uint32_t first_word = 0;
                         int first_group = 0;
                         n_surv = 0;
@@ -463,7 +523,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
                             if (q0 < 0) q0 = p; else if (q1 < 0) q1 = p; else if (q2 < 0) q2 = p; else q3 = p;
                         }
                     }
-                    c.compares += (unsigned)(P.n_primers * kBsPositions);
+                    if (!seeded) c.compares += (unsigned)(P.n_primers * kBsPositions);
                     flush();
                     if (ix.k > 0) {
                         if (n_acc == 1) {

@@ -106,6 +106,34 @@ def _reads(rng, primers, n):
     return H.pair_records(recs[: 2 * n_pairs]) + recs[2 * n_pairs:]
 
 
+@pytest.mark.parametrize("seed", range(0, 96, 2))
+def test_random_configurations_seed_index(seed, monkeypatch):
+    """The same draws with the seed index forced on (by default only panels of more than 256 primers use it)."""
+    monkeypatch.setenv("IDP_SCAN_SEED", "1")
+    test_random_configurations(seed)
+
+
+@pytest.mark.parametrize("seed", range(0, 96, 3))
+def test_random_configurations_bit_sliced(seed, monkeypatch):
+    monkeypatch.setenv("IDP_SCAN_SEED", "0")
+    test_random_configurations(seed)
+
+
+def test_large_panel_uses_seed_index():
+    """1,200 primers (38 groups): the seed index path by default; near-duplicate primers share seeds."""
+    rng = np.random.default_rng(77)
+    primers = []
+    for i in range(600):
+        for strand in (True, False):
+            seq = _seq(rng, int(rng.integers(18, 34)))
+            if i % 50 == 1 and primers:  # shares both seeds with the previous pair's primer, differs further in
+                seq = primers[-2].sequence[:16] + _seq(rng, 8)
+            primers.append(H.Primer(f"p{i}", f"p{i}{'+' if strand else '-'}", seq, strand))
+    recs = _reads(rng, primers, 6000)
+    run_both(primers, H.recs_to_arrays(recs), max_mismatch_rate=0.05, ungapped_kmer_length=6, gapped_kmer_length=10)
+    run_both(primers, H.recs_to_arrays(recs[:2000]), max_mismatch_rate=0.05, ungapped_kmer_length=None, gapped_kmer_length=8)
+
+
 @pytest.mark.parametrize("seed", range(96))
 def test_random_configurations(seed):
     rng = np.random.default_rng(1000 + seed)
