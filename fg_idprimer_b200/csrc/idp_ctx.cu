@@ -147,6 +147,13 @@ static int upload_panel(idp_ctx *c) {
     {   // (score << 14 | rank << 12 | start) register traceback: |score| * (rows + columns) must stay below 2^16
         const long maxabs = std::max<long>({std::labs(d.match_score), std::labs(d.mismatch_score), std::labs((long)d.gap_open + d.gap_extend), std::labs(d.gap_extend)});
         d.packed_trace_ok = d.smat == nullptr && maxabs * (kMaxPrimerBases + kMaxReadLen + 1) < (1L << 16);
+        // 16-bit halves (sw_score2_fast): Glocal runs in coordinates shifted by extend * (row + column) over at most
+        // max_seq_len + slop columns, Local values are bounded by the query length alone (gaps open from non-negative cells)
+        const long m16 = std::max<long>({maxabs, std::labs((long)d.match_score - 2L * d.gap_extend), std::labs((long)d.mismatch_score - 2L * d.gap_extend)});
+        const long span = 64 + (long)p.max_seq_len + std::max(p.params.slop, 0) + 2;
+        const bool no16 = getenv("IDP_SW_NO_16X2") != nullptr;
+        d.fits16_glocal = !no16 && d.smat == nullptr && 2 * m16 * span < 16000;
+        d.fits16_local = !no16 && d.smat == nullptr && m16 * (64 + 2) < 16000;
     }
     d.slop = p.params.slop; d.three_prime = p.params.three_prime;
     d.max_mismatch_rate = p.params.max_mismatch_rate; d.min_alignment_score_rate = p.params.min_alignment_score_rate;
@@ -258,10 +265,17 @@ static void launch_sw_all_t(const idp_ctx *c, cudaStream_t st, const DevReads &R
                             Fin *fin, Counters *ctr, int as5) {
     const int threads = c->dp.n_primers <= 32 ? 32 : c->dp.n_primers <= 64 ? 64 : 128;
     const int grid = c->sm_count * (threads == 128 ? 8 : threads == 64 ? 16 : 32);
+    const bool packed = !SMAT && (LOCAL ? c->dp.fits16_local : c->dp.fits16_glocal);  // two alignments per register
     switch (c->nq) {
-        case 32: sw_all_kernel<32, LOCAL, SMAT><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5); break;
-        case 64: sw_all_kernel<64, LOCAL, SMAT><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5); break;
-        default: sw_all_kernel<0, LOCAL, SMAT><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5); break;
+        case 32:
+            if (packed) sw_all_kernel<32, LOCAL, SMAT, !SMAT><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5);
+            else sw_all_kernel<32, LOCAL, SMAT, false><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5);
+            break;
+        case 64:
+            if (packed) sw_all_kernel<64, LOCAL, SMAT, !SMAT><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5);
+            else sw_all_kernel<64, LOCAL, SMAT, false><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5);
+            break;
+        default: sw_all_kernel<0, LOCAL, SMAT, false><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5); break;
     }
 }
 static void launch_sw_all(const idp_ctx *c, cudaStream_t st, bool local, const DevReads &R, const unsigned *work_read, const unsigned *n_work,

@@ -71,6 +71,7 @@ struct DevPanel {
     int32_t match_score, mismatch_score, gap_open, gap_extend;
     const int32_t *smat;       // NULL or [16*16] primer nibble x read nibble, INT32_MIN = missing
     int32_t packed_trace_ok;   // scores are small enough for the (score << 14 | rank << 12 | start) register traceback
+    int32_t fits16_glocal, fits16_local;  // every value of a 5' (Glocal) / 3' (Local) score matrix fits 16 bits: two alignments per register
     int32_t slop, three_prime;
     double max_mismatch_rate, min_alignment_score_rate;
 };

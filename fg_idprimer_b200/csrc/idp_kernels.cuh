@@ -569,6 +569,95 @@ __device__ __forceinline__ int sw_score_fast(const DevPanel &P, const uint32_t *
     return best;
 }
 
+// Two alignments of the same target per thread, one in each 16-bit half of every register, on the packed DPX forms
+// (VIADDMNMX.S16x2, VIMNMX3.S16x2, VIADD.16x2): twice the cells per issued instruction.  Queries a and b (bottom-aligned
+// like above) may differ in length; lo / hi bound the ragged rows over both.  Scores only; the caller guarantees the
+// value range (DevPanel::fits16_glocal / fits16_local).  Glocal runs in the shifted coordinates of
+// sw_score_glocal_shifted, Local in plain coordinates with the zero clamp folded into the .RELU form.
+__device__ __forceinline__ uint32_t pack16(int x) { return ((uint32_t)x & 0xFFFFu) * 0x00010001u; }
+
+template <int NQ, bool LOCAL>
+__device__ __forceinline__ void sw_score2_fast(const DevPanel &P, const uint32_t *__restrict__ qbot_a, const uint32_t *__restrict__ qbot_b, int na,
+                                               int nb, int lo, int hi, const Oriented &T, int m_a, int m_b, int &score_a, int &score_b) {
+    static_assert(NQ == 32 || NQ == 64, "row count");
+    const int o = P.gap_open, e = P.gap_extend;
+    const int m = max(m_a, m_b);  // the shorter target is a prefix of the longer one; its half stops taking end cells at its own m
+    if (m == 0) { score_a = LOCAL ? 0 : o + na * e; score_b = LOCAL ? 0 : o + nb * e; return; }
+    uint32_t ma2 = pack16(LOCAL ? P.match_score : P.match_score - 2 * e);
+    uint32_t selx = ma2 ^ pack16(LOCAL ? P.mismatch_score : P.mismatch_score - 2 * e);  // score = ma2 ^ (mismatch mask & selx)
+    uint32_t o2 = pack16(LOCAL ? o + e : o), e2 = pack16(e);
+    asm volatile("" : "+r"(ma2), "+r"(selx), "+r"(o2), "+r"(e2));  // keep the constants in registers across the unrolled rows
+    constexpr uint32_t NEG2 = 0xC000C000u;  // -16384 in both halves
+    const int offa = NQ - na, offb = NQ - nb;
+    uint32_t qa[NQ / 8], qb[NQ / 8];
+#pragma unroll
+    for (int w = 0; w < NQ / 8; ++w) { qa[w] = __ldg(&qbot_a[w]); qb[w] = __ldg(&qbot_b[w]); }
+    uint32_t D[NQ], L[NQ], M[NQ];
+#pragma unroll
+    for (int r = 0; r < NQ; ++r) {
+        if (LOCAL) { D[r] = 0u; L[r] = 0u; M[r] = 0u; }
+        else { D[r] = NEG2; L[r] = NEG2; M[r] = o2; }  // Up'(i,0) = open + i*extend - extend*i
+    }
+    uint32_t best = LOCAL ? 0u : NEG2;
+    uint32_t conv = (((uint32_t)(e * nb) & 0xFFFFu) << 16) | ((uint32_t)(e * na) & 0xFFFFu);  // Glocal: extend * (n + j), per half
+    uint32_t edge = 0u;                                                                   // Glocal: -extend * j in both halves
+    const uint32_t ne2 = pack16(-e);
+    TargetStream ts(T);
+    for (int j = 1; j <= m; ++j) {
+        uint32_t t = ts.nib(j - 1);
+        asm volatile("" : "+r"(t));
+        const uint32_t trep = t * 0x11111111u;
+        uint32_t pk[NQ / 4];  // rows 4w..4w+3: mismatch flags of a at bits 0,4,8,12 and of b at bits 16,20,24,28
+#pragma unroll
+        for (int w = 0; w < NQ / 8; ++w) {
+            const uint32_t fa = nib_nonzero(qa[w] ^ trep), fb = nib_nonzero(qb[w] ^ trep);
+            pk[2 * w] = __byte_perm(fa, fb, 0x5410);
+            pk[2 * w + 1] = __byte_perm(fa, fb, 0x7632);
+        }
+        uint32_t mdiag, d_up, u_up;
+        if (LOCAL) { mdiag = 0u; d_up = 0u; u_up = 0u; }
+        else { mdiag = edge; edge = __vadd2(edge, ne2); d_up = edge; u_up = edge; }  // row 0 is all zero: shifted by -extend*(0+j)
+#define IDP_CELL(r)                                                                                        \
+            const uint32_t mask = ((pk[(r) >> 2] >> (4 * ((r) & 3))) & 0x00010001u) * 0xFFFFu;               \
+            const uint32_t s2 = ma2 ^ (mask & selx);                                                       \
+            const uint32_t dn = LOCAL ? __viaddmax_s16x2_relu(mdiag, s2, 0u) : __vadd2(mdiag, s2);           \
+            const uint32_t un = LOCAL ? __viaddmax_s16x2(d_up, o2, __vadd2(u_up, e2)) : __viaddmax_s16x2(d_up, o2, u_up);       \
+            const uint32_t ln = LOCAL ? __viaddmax_s16x2(D[(r)], o2, __vadd2(L[(r)], e2)) : __viaddmax_s16x2(D[(r)], o2, L[(r)]); \
+            const uint32_t mold = M[(r)];                                                                  \
+            M[(r)] = __vimax3_s16x2(dn, ln, un);                                                           \
+            D[(r)] = dn; L[(r)] = ln;
+#define IDP_ROW(r)                                                                                         \
+    case (r): {                                                                                            \
+        if ((r) >= hi) break;                                                                              \
+        const uint32_t act = ((r) >= offa ? 0x0000FFFFu : 0u) | ((r) >= offb ? 0xFFFF0000u : 0u);            \
+        IDP_CELL(r)                                                                                        \
+        mdiag = (mold & act) | (mdiag & ~act); d_up = (dn & act) | (d_up & ~act); u_up = (un & act) | (u_up & ~act); \
+        if (LOCAL) best = __vmaxs2(best, dn & act);                                                        \
+    }
+        IDP_SWITCH_ROWS(NQ, lo)
+#undef IDP_ROW
+#define IDP_ROW(r)                                                                                         \
+    case (r): {                                                                                            \
+        IDP_CELL(r)                                                                                        \
+        mdiag = mold; d_up = dn; u_up = un;                                                                \
+        if (LOCAL) best = __vmaxs2(best, dn);                                                              \
+    }
+        IDP_SWITCH_ROWS(NQ, hi)
+#undef IDP_ROW
+#undef IDP_CELL
+        if (!LOCAL) {  // last query row, this column, back in true coordinates: M(n,j) = M'(n,j) + extend*(n+j)
+            conv = __vadd2(conv, e2);
+            const uint32_t upd = __viaddmax_s16x2(M[NQ - 1], conv, best);
+            const uint32_t in = (j <= m_a ? 0x0000FFFFu : 0u) | (j <= m_b ? 0xFFFF0000u : 0u);
+            best = (upd & in) | (best & ~in);
+        }
+    }
+    score_a = (int)(int16_t)(best & 0xFFFFu);
+    score_b = (int)(int16_t)(best >> 16);
+    if (!LOCAL && m_a == 0) score_a = o + na * e;
+    if (!LOCAL && m_b == 0) score_b = o + nb * e;
+}
+
 // Same, carrying where each path started and resolving ties the way an explicit traceback would, in ONE integer per
 // matrix value:      value = (score << 14) | (rank << 12) | start
 // `start` (12 bits) is the target offset at which the path left the free first row / a zero cell.  `rank` (2 bits) is the
@@ -746,7 +835,7 @@ struct GBest2 {
 
 // Every primer is a candidate (no -K, or 3' with no 5' match anywhere): one block per read, threads stride the panel
 // in file order, the best two are reduced on chip.  Nothing per-pair ever touches HBM.
-template <int NQ, bool LOCAL, bool SMAT>
+template <int NQ, bool LOCAL, bool SMAT, bool PACKED>
 __global__ void __launch_bounds__(128, 4) sw_all_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
                                                      const unsigned int *__restrict__ n_work_ptr, Fin *__restrict__ fin,
                                                      Counters *__restrict__ ctr_out, int count_as_5p) {
@@ -761,7 +850,31 @@ __global__ void __launch_bounds__(128, 4) sw_all_kernel(DevPanel P, DevReads R, 
         GBest2 g;
         bool any_missing = false;
         constexpr int NQF = NQ == 64 ? 64 : 32;
-        for (int p0 = 0; p0 < P.n_primers; p0 += blockDim.x) {
+        constexpr bool packed = PACKED && NQ > 0 && !SMAT;  // the launcher checked DevPanel::fits16_*
+        for (int p0 = 0; packed && p0 < P.n_primers; p0 += 2 * blockDim.x) {
+            // two primers of (nearly) equal length per thread, one per 16-bit half
+            const int ia = p0 + 2 * (int)threadIdx.x, ib = ia + 1;
+            const bool active = ia < P.n_primers, both = ib < P.n_primers;
+            const int pa = active ? (int)__ldg(&P.by_len[ia]) : 0, pb = both ? (int)__ldg(&P.by_len[ib]) : pa;
+            int na = 0, nb = 0, m_a = 0, m_b = 0;
+            Oriented T{nullptr, 0, false};
+            if (active) {
+                na = __ldg(&P.pinfo[pa]).w; nb = __ldg(&P.pinfo[pb]).w;
+                T = make_target(P, R, r, na, LOCAL, m_a);
+                make_target(P, R, r, nb, LOCAL, m_b);
+            }
+            const int n_warp_max = __reduce_max_sync(0xffffffffu, max(na, nb));
+            const int n_warp_min = __reduce_min_sync(0xffffffffu, active ? min(na, nb) : n_warp_max);
+            if (active) {
+                int sa, sb;
+                sw_score2_fast<NQF, LOCAL>(P, P.qbot + (size_t)pa * (NQF / 8), P.qbot + (size_t)pb * (NQF / 8), na, nb, NQF - n_warp_max,
+                                           NQF - n_warp_min, T, m_a, m_b, sa, sb);
+                g.offer(pa, pa, sa, na);
+                cells += (unsigned long long)na * (unsigned long long)m_a;
+                if (both) { g.offer(pb, pb, sb, nb); cells += (unsigned long long)nb * (unsigned long long)m_b; }
+            }
+        }
+        for (int p0 = 0; !packed && p0 < P.n_primers; p0 += blockDim.x) {
             // primers are visited sorted by length so that a warp's alignments have (nearly) the same number of rows;
             // ties are still broken by the primer's position in the file (the ordinal offered below)
             const bool active = p0 + (int)threadIdx.x < P.n_primers;

@@ -151,6 +151,20 @@ def test_no_kmer_filters_and_unusual_options():
     run_both(prs, arrays, ref_names=panel.ref_names, three_prime=0, gapped_kmer_length=10, ungapped_kmer_length=6)
 
 
+@pytest.mark.parametrize("scores", [(1, -4, -6, -1), (7, -9, -11, -3), (40, -45, -30, -5), (60, -70, -64, -12), (300, -400, -250, -60),
+                                    (5, 0, 0, 0), (0, -3, -2, 0)])
+def test_score_ranges_all_primers_and_three_prime(scores):
+    """Every primer is aligned (no -K) and 3' matching is on: the packed 16-bit aligner where the score range allows it,
+    the 32-bit one above that (the last but two rows), odd primer counts and mixed primer lengths."""
+    match, mismatch, gap_open, gap_extend = scores
+    panel, reads, _ = synth.workload("c3", 700)
+    prs = _synth_primers(panel)[:75]          # odd count: the last thread pairs a primer with itself
+    arrays = reads.oracle_arrays()
+    for slop, three in ((5, -1), (0, 4), (11, 0)):
+        run_both(prs, arrays, ref_names=panel.ref_names, slop=slop, three_prime=three, gapped_kmer_length=None, ungapped_kmer_length=6,
+                 match_score=match, mismatch_score=mismatch, gap_open=gap_open, gap_extend=gap_extend, min_alignment_score_rate=0.05)
+
+
 def test_ties_near_duplicate_primers():
     """Candidate order decides ties (PM:241, PM:309): near-duplicate primers, with and without the k-mer filters."""
     rng = np.random.default_rng(11)
