@@ -468,9 +468,11 @@ __device__ __forceinline__ int sw_score_glocal_shifted(const DevPanel &P, const 
     uint32_t q[NQ / 8];
 #pragma unroll
     for (int w = 0; w < NQ / 8; ++w) q[w] = __ldg(&qbot[w]);
-    int D[NQ], L[NQ], M[NQ];
+    // LN[r] is Left'(r, next column) = max(Diagonal'(r, j) + open, Left'(r, j)), formed as soon as column j's cell is known:
+    // two register arrays instead of three
+    int LN[NQ], M[NQ];
 #pragma unroll
-    for (int r = 0; r < NQ; ++r) { D[r] = kNegInf; L[r] = kNegInf; M[r] = o; }  // Up'(i,0) = open + i*extend - extend*i
+    for (int r = 0; r < NQ; ++r) { LN[r] = kNegInf; M[r] = o; }  // Up'(i,0) = open + i*extend - extend*i
     int best = kNegInf;
     TargetStream ts(T);
     for (int j = 1; j <= m; ++j) {
@@ -484,10 +486,10 @@ __device__ __forceinline__ int sw_score_glocal_shifted(const DevPanel &P, const 
 #define IDP_CELL(r)                                                                    \
             const int dn = mdiag + ((ne[(r) >> 3] & (1u << (4 * ((r) & 7)))) ? mi : ma); \
             const int un = __viaddmax_s32(d_up, o, u_up);                              \
-            const int ln = __viaddmax_s32(D[(r)], o, L[(r)]);                          \
+            const int ln = LN[(r)];                                                    \
             const int mold = M[(r)];                                                   \
             M[(r)] = __vimax3_s32(dn, ln, un);                                         \
-            D[(r)] = dn; L[(r)] = ln;
+            LN[(r)] = __viaddmax_s32(dn, o, ln);
 #define IDP_ROW(r)                                                                     \
     case (r): {                                                                        \
         if ((r) >= hi) break;                                                          \
@@ -521,11 +523,11 @@ __device__ __forceinline__ int sw_score_fast(const DevPanel &P, const uint32_t *
     uint32_t q[NQ / 8];
 #pragma unroll
     for (int w = 0; w < NQ / 8; ++w) q[w] = __ldg(&qbot[w]);
-    int D[NQ], L[NQ], M[NQ];
+    int LN[NQ], M[NQ];  // LN[r] = Left(r, next column) = max(Diagonal(r, j) + open + extend, Left(r, j) + extend)
 #pragma unroll
     for (int r = 0; r < NQ; ++r) {
-        if (LOCAL) { D[r] = 0; L[r] = 0; M[r] = 0; }
-        else { D[r] = kNegInf; L[r] = kNegInf; M[r] = P.gap_open + (r - off + 1) * P.gap_extend; }  // Up(i,0), i = r-off+1
+        if (LOCAL) { LN[r] = max(oe, e); M[r] = 0; }  // column 0 is all zero
+        else { LN[r] = kNegInf; M[r] = P.gap_open + (r - off + 1) * P.gap_extend; }  // Up(i,0), i = r-off+1
     }
     int best = LOCAL ? 0 : kNegInf;
     TargetStream ts(T);
@@ -541,10 +543,10 @@ __device__ __forceinline__ int sw_score_fast(const DevPanel &P, const uint32_t *
             int dn = mdiag + ((ne[(r) >> 3] & (1u << (4 * ((r) & 7)))) ? mi : ma);      \
             if (LOCAL) dn = max(dn, 0);                                                \
             const int un = __viaddmax_s32(d_up, oe, u_up + e);                         \
-            const int ln = __viaddmax_s32(D[(r)], oe, L[(r)] + e);                     \
+            const int ln = LN[(r)];                                                    \
             const int mold = M[(r)];                                                   \
             M[(r)] = __vimax3_s32(dn, ln, un);                                         \
-            D[(r)] = dn; L[(r)] = ln;
+            LN[(r)] = __viaddmax_s32(dn, oe, ln + e);
 #define IDP_ROW(r)                                                                     \
     case (r): {                                                                        \
         if ((r) >= hi) break;                                                          \
@@ -592,11 +594,11 @@ __device__ __forceinline__ void sw_score2_fast(const DevPanel &P, const uint32_t
     uint32_t qa[NQ / 8], qb[NQ / 8];
 #pragma unroll
     for (int w = 0; w < NQ / 8; ++w) { qa[w] = __ldg(&qbot_a[w]); qb[w] = __ldg(&qbot_b[w]); }
-    uint32_t D[NQ], L[NQ], M[NQ];
+    uint32_t LN[NQ], M[NQ];  // LN[r] = Left(r, next column), formed as soon as this column's cell is known
 #pragma unroll
     for (int r = 0; r < NQ; ++r) {
-        if (LOCAL) { D[r] = 0u; L[r] = 0u; M[r] = 0u; }
-        else { D[r] = NEG2; L[r] = NEG2; M[r] = o2; }  // Up'(i,0) = open + i*extend - extend*i
+        if (LOCAL) { LN[r] = __vmaxs2(o2, e2); M[r] = 0u; }  // column 0 is all zero
+        else { LN[r] = NEG2; M[r] = o2; }                  // Up'(i,0) = open + i*extend - extend*i
     }
     uint32_t best = LOCAL ? 0u : NEG2;
     uint32_t conv = (((uint32_t)(e * nb) & 0xFFFFu) << 16) | ((uint32_t)(e * na) & 0xFFFFu);  // Glocal: extend * (n + j), per half
@@ -621,11 +623,11 @@ __device__ __forceinline__ void sw_score2_fast(const DevPanel &P, const uint32_t
             const uint32_t mask = ((pk[(r) >> 2] >> (4 * ((r) & 3))) & 0x00010001u) * 0xFFFFu;               \
             const uint32_t s2 = ma2 ^ (mask & selx);                                                       \
             const uint32_t dn = LOCAL ? __viaddmax_s16x2_relu(mdiag, s2, 0u) : __vadd2(mdiag, s2);           \
-            const uint32_t un = LOCAL ? __viaddmax_s16x2(d_up, o2, __vadd2(u_up, e2)) : __viaddmax_s16x2(d_up, o2, u_up);       \
-            const uint32_t ln = LOCAL ? __viaddmax_s16x2(D[(r)], o2, __vadd2(L[(r)], e2)) : __viaddmax_s16x2(D[(r)], o2, L[(r)]); \
+            const uint32_t un = LOCAL ? __viaddmax_s16x2(d_up, o2, __vadd2(u_up, e2)) : __viaddmax_s16x2(d_up, o2, u_up); \
+            const uint32_t ln = LN[(r)];                                                                   \
             const uint32_t mold = M[(r)];                                                                  \
             M[(r)] = __vimax3_s16x2(dn, ln, un);                                                           \
-            D[(r)] = dn; L[(r)] = ln;
+            LN[(r)] = LOCAL ? __viaddmax_s16x2(dn, o2, __vadd2(ln, e2)) : __viaddmax_s16x2(dn, o2, ln);
 #define IDP_ROW(r)                                                                                         \
     case (r): {                                                                                            \
         if ((r) >= hi) break;                                                                              \
@@ -668,11 +670,80 @@ __device__ __forceinline__ void sw_score2_fast(const DevPanel &P, const uint32_t
 //   a.score > b.score  <=>  a > (b | 0x3FFF)
 struct TracedReg { int score, t_start, t_end; };
 
+// Glocal in the shifted coordinates of sw_score_glocal_shifted: every candidate of a cell carries the same shift, so the
+// comparisons (and the rank / start bits below the score) are untouched, a gap extension costs nothing and the two
+// "+ extend" additions per cell disappear.  End cells of different columns are compared after shifting back.
+template <int NQ>
+__device__ __forceinline__ TracedReg sw_trace_reg_glocal_shifted(const DevPanel &P, const uint32_t *__restrict__ qbot, int n, int lo, int hi,
+                                                                 const Oriented &T, int m) {
+    constexpr int SH = 14, LOW = 0x3FFF, RANK = 0x3000, RD = 0x3000, RL = 0x2000, RU = 0x1000;
+    TracedReg out{0, 1, 0};
+    const int e1 = P.gap_extend;
+    int o = P.gap_open * (1 << SH), ma = (P.match_score - 2 * e1) * (1 << SH), mi = (P.mismatch_score - 2 * e1) * (1 << SH);
+    asm volatile("" : "+r"(o), "+r"(ma), "+r"(mi));
+    constexpr int NEG = -(1 << 30);
+    const int off = NQ - n;
+    uint32_t q[NQ / 8];
+#pragma unroll
+    for (int w = 0; w < NQ / 8; ++w) q[w] = __ldg(&qbot[w]);
+    int LN[NQ], M[NQ];  // LN[r] = Left'(r, next column), stamped
+#pragma unroll
+    for (int r = 0; r < NQ; ++r) { LN[r] = NEG | RL; M[r] = o | RU; }  // Up'(i,0) = open, start 0
+    int best = NEG, bj = 0;
+    const int ne1 = -e1 * (1 << SH);   // one column (or row) further: the shift grows by -extend
+    int edge = 0;                       // (-extend * (j-1)) << SH at the top of column j
+    int back = (e1 * n) * (1 << SH);    // (extend * (n + j)) << SH, added to an end cell of column j
+    TargetStream ts(T);
+    for (int j = 1; j <= m; ++j) {
+        uint32_t t = ts.nib(j - 1);
+        asm volatile("" : "+r"(t));
+        const uint32_t trep = t * 0x11111111u;
+        uint32_t ne[NQ / 8];
+#pragma unroll
+        for (int w = 0; w < NQ / 8; ++w) ne[w] = nib_nonzero(q[w] ^ trep);
+        int mdiag = edge + (j - 1);  // row 0: score 0, path starts at this column
+        edge += ne1;
+        back += e1 * (1 << SH);
+        int d_up = edge | RD | j, u_up = edge | RU | j;
+#define IDP_CELL(r)                                                                                   \
+            const int dn = ((mdiag + ((ne[(r) >> 3] & (1u << (4 * ((r) & 7)))) ? mi : ma)) & ~RANK) | RD; \
+            const int un = (__viaddmax_s32(d_up, o, u_up) & ~RANK) | RU; /* equal scores: opened from Diagonal */ \
+            const int ln = LN[(r)];                                                                    \
+            const int mold = M[(r)];                                                                   \
+            M[(r)] = __vimax3_s32(dn, ln, un); /* equal scores: Diagonal, then Left, then Up */        \
+            LN[(r)] = (__viaddmax_s32(dn, o, ln) & ~RANK) | RL;
+#define IDP_ROW(r)                                                                     \
+    case (r): {                                                                        \
+        if ((r) >= hi) break;                                                          \
+        const bool act = (r) >= off;                                                   \
+        IDP_CELL(r)                                                                    \
+        mdiag = act ? mold : mdiag; d_up = act ? dn : d_up; u_up = act ? un : u_up;    \
+    }
+        IDP_SWITCH_ROWS(NQ, lo)
+#undef IDP_ROW
+#define IDP_ROW(r)                                                                     \
+    case (r): {                                                                        \
+        IDP_CELL(r)                                                                    \
+        mdiag = mold; d_up = dn; u_up = un;                                            \
+    }
+        IDP_SWITCH_ROWS(NQ, hi)
+#undef IDP_ROW
+#undef IDP_CELL
+        // last row, columns ascending, Diagonal / Left / Up, strict '>': Left(n,j) never exceeds an earlier Diagonal(n,j')
+        const int dt = d_up + back, ut = u_up + back;
+        if (dt > (best | LOW)) { best = dt; bj = j; }
+        if (ut > (best | LOW)) { best = ut; bj = j; }
+    }
+    out.score = best >> SH; out.t_start = (best & 0xFFF) + 1; out.t_end = bj;
+    return out;
+}
+
 template <int NQ, bool LOCAL>
 __device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint32_t *__restrict__ qbot, int n, int lo, int hi, const Oriented &T, int m) {
     static_assert(NQ == 32 || NQ == 64, "row count");
     TracedReg out{0, 1, 0};
     if (m == 0) { out.score = LOCAL ? 0 : P.gap_open + n * P.gap_extend; return out; }
+    if constexpr (!LOCAL) return sw_trace_reg_glocal_shifted<NQ>(P, qbot, n, lo, hi, T, m);
     constexpr int SH = 14, LOW = 0x3FFF, RANK = 0x3000, RD = 0x3000, RL = 0x2000, RU = 0x1000;
     int oe = (P.gap_open + P.gap_extend) << SH, e = P.gap_extend * (1 << SH), ma = P.match_score << SH, mi = P.mismatch_score * (1 << SH);
     oe = (P.gap_open + P.gap_extend) * (1 << SH);
@@ -682,11 +753,11 @@ __device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint3
     uint32_t q[NQ / 8];
 #pragma unroll
     for (int w = 0; w < NQ / 8; ++w) q[w] = __ldg(&qbot[w]);
-    int D[NQ], L[NQ], M[NQ];
+    int LN[NQ], M[NQ];  // LN[r] = Left(r, next column), stamped
 #pragma unroll
     for (int r = 0; r < NQ; ++r) {
-        if (LOCAL) { D[r] = RD; L[r] = RL; M[r] = RD; }
-        else { D[r] = NEG | RD; L[r] = NEG | RL; M[r] = ((P.gap_open + (r - off + 1) * P.gap_extend) * (1 << SH)) | RU; }  // Up(i,0), start 0
+        if (LOCAL) { LN[r] = (__viaddmax_s32(RD, oe, RL + e) & ~RANK) | RL; M[r] = RD; }  // column 0: all zero, start 0
+        else { LN[r] = NEG | RL; M[r] = ((P.gap_open + (r - off + 1) * P.gap_extend) * (1 << SH)) | RU; }  // Up(i,0), start 0
     }
     int best = NEG, bi = 0, bj = 0;
     TargetStream ts(T);
@@ -702,10 +773,10 @@ __device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint3
             int dn = ((mdiag + ((ne[(r) >> 3] & (1u << (4 * ((r) & 7)))) ? mi : ma)) & ~RANK) | RD;               \
             if (LOCAL) dn = dn < 0 ? (RD | j) : dn; /* clamp at zero: the path (re)starts after this cell */      \
             const int un = (__viaddmax_s32(d_up, oe, u_up + e) & ~RANK) | RU; /* equal scores: opened from Diagonal */ \
-            const int ln = (__viaddmax_s32(D[(r)], oe, L[(r)] + e) & ~RANK) | RL;                                 \
+            const int ln = LN[(r)];                                                                               \
             const int mold = M[(r)];                                                                              \
             M[(r)] = __vimax3_s32(dn, ln, un); /* equal scores: Diagonal, then Left, then Up */                   \
-            D[(r)] = dn; L[(r)] = ln;
+            LN[(r)] = (__viaddmax_s32(dn, oe, ln + e) & ~RANK) | RL;
         // Local best cell: lowest row, then lowest column; Left/Up values never win (each is bounded by a Diagonal value of a
         // cell scanned earlier, gap scores being <= 0, and ties go to the earlier cell)
 #define IDP_BEST(r, cond)                                                                      \
