@@ -151,6 +151,10 @@ static int upload_panel(idp_ctx *c) {
         // max_seq_len + slop columns, Local values are bounded by the query length alone (gaps open from non-negative cells)
         const long m16 = std::max<long>({maxabs, std::labs((long)d.match_score - 2L * d.gap_extend), std::labs((long)d.mismatch_score - 2L * d.gap_extend)});
         const long span = 64 + (long)p.max_seq_len + std::max(p.params.slop, 0) + 2;
+        const long ma = d.match_score, mi = d.mismatch_score, go = d.gap_open, ge = d.gap_extend;
+        d.tr_open = (int32_t)(go * 16384); d.tr_open_ext = (int32_t)((go + ge) * 16384); d.tr_ext = (int32_t)(ge * 16384);
+        d.tr_match = (int32_t)(ma * 16384); d.tr_mismatch = (int32_t)(mi * 16384);
+        d.tr_match_shifted = (int32_t)((ma - 2 * ge) * 16384); d.tr_mismatch_shifted = (int32_t)((mi - 2 * ge) * 16384);
         const bool no16 = getenv("IDP_SW_NO_16X2") != nullptr;
         d.fits16_glocal = !no16 && d.smat == nullptr && 2 * m16 * span < 16000;
         d.fits16_local = !no16 && d.smat == nullptr && m16 * (64 + 2) < 16000;

@@ -71,6 +71,10 @@ struct DevPanel {
     int32_t match_score, mismatch_score, gap_open, gap_extend;
     const int32_t *smat;       // NULL or [16*16] primer nibble x read nibble, INT32_MIN = missing
     int32_t packed_trace_ok;   // scores are small enough for the (score << 14 | rank << 12 | start) register traceback
+    // scoring constants pre-shifted / pre-packed on the host, so that the kernels read them as plain constant-bank operands
+    // (a product formed in the kernel is folded back into every use as a multiply-add):
+    // tr_*: value << 14 for the register traceback (glocal ones in shifted coordinates: match/mismatch - 2*extend)
+    int32_t tr_open, tr_open_ext, tr_ext, tr_match, tr_mismatch, tr_match_shifted, tr_mismatch_shifted;
     int32_t fits16_glocal, fits16_local;  // every value of a 5' (Glocal) / 3' (Local) score matrix fits 16 bits: two alignments per register
     int32_t slop, three_prime;
     double max_mismatch_rate, min_alignment_score_rate;

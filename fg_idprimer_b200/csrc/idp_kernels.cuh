@@ -588,7 +588,7 @@ __device__ __forceinline__ void sw_score2_fast(const DevPanel &P, const uint32_t
     uint32_t ma2 = pack16(LOCAL ? P.match_score : P.match_score - 2 * e);
     uint32_t selx = ma2 ^ pack16(LOCAL ? P.mismatch_score : P.mismatch_score - 2 * e);  // score = ma2 ^ (mismatch mask & selx)
     uint32_t o2 = pack16(LOCAL ? o + e : o), e2 = pack16(e);
-    asm volatile("" : "+r"(ma2), "+r"(selx), "+r"(o2), "+r"(e2));  // keep the constants in registers across the unrolled rows
+    asm volatile("" : "+r"(ma2), "+r"(selx), "+r"(o2), "+r"(e2));
     constexpr uint32_t NEG2 = 0xC000C000u;  // -16384 in both halves
     const int offa = NQ - na, offb = NQ - nb;
     uint32_t qa[NQ / 8], qb[NQ / 8];
@@ -679,8 +679,12 @@ __device__ __forceinline__ TracedReg sw_trace_reg_glocal_shifted(const DevPanel 
     constexpr int SH = 14, LOW = 0x3FFF, RANK = 0x3000, RD = 0x3000, RL = 0x2000, RU = 0x1000;
     TracedReg out{0, 1, 0};
     const int e1 = P.gap_extend;
-    int o = P.gap_open * (1 << SH), ma = (P.match_score - 2 * e1) * (1 << SH), mi = (P.mismatch_score - 2 * e1) * (1 << SH);
-    asm volatile("" : "+r"(o), "+r"(ma), "+r"(mi));
+    const int o = P.tr_open;  // a constant-bank operand of VIADDMNMX
+    // registers (selected per cell / one LOP3 per re-stamp): a value that went through a shuffle is not re-derived from
+    // the constant bank inside every row
+    const unsigned am = __activemask();
+    const int self = (int)(threadIdx.x & 31u);
+    const int ma = __shfl_sync(am, P.tr_match_shifted, self), mi = __shfl_sync(am, P.tr_mismatch_shifted, self), keep = __shfl_sync(am, ~RANK, self);
     constexpr int NEG = -(1 << 30);
     const int off = NQ - n;
     uint32_t q[NQ / 8];
@@ -690,7 +694,7 @@ __device__ __forceinline__ TracedReg sw_trace_reg_glocal_shifted(const DevPanel 
 #pragma unroll
     for (int r = 0; r < NQ; ++r) { LN[r] = NEG | RL; M[r] = o | RU; }  // Up'(i,0) = open, start 0
     int best = NEG, bj = 0;
-    const int ne1 = -e1 * (1 << SH);   // one column (or row) further: the shift grows by -extend
+    const int ne1 = -P.tr_ext;          // one column (or row) further: the shift grows by -extend
     int edge = 0;                       // (-extend * (j-1)) << SH at the top of column j
     int back = (e1 * n) * (1 << SH);    // (extend * (n + j)) << SH, added to an end cell of column j
     TargetStream ts(T);
@@ -703,15 +707,15 @@ __device__ __forceinline__ TracedReg sw_trace_reg_glocal_shifted(const DevPanel 
         for (int w = 0; w < NQ / 8; ++w) ne[w] = nib_nonzero(q[w] ^ trep);
         int mdiag = edge + (j - 1);  // row 0: score 0, path starts at this column
         edge += ne1;
-        back += e1 * (1 << SH);
+        back += P.tr_ext;
         int d_up = edge | RD | j, u_up = edge | RU | j;
 #define IDP_CELL(r)                                                                                   \
             const int dn = ((mdiag + ((ne[(r) >> 3] & (1u << (4 * ((r) & 7)))) ? mi : ma)) & ~RANK) | RD; \
-            const int un = (__viaddmax_s32(d_up, o, u_up) & ~RANK) | RU; /* equal scores: opened from Diagonal */ \
+            const int un = (__viaddmax_s32(d_up, o, u_up) & keep) | RU; /* equal scores: opened from Diagonal */ \
             const int ln = LN[(r)];                                                                    \
             const int mold = M[(r)];                                                                   \
             M[(r)] = __vimax3_s32(dn, ln, un); /* equal scores: Diagonal, then Left, then Up */        \
-            LN[(r)] = (__viaddmax_s32(dn, o, ln) & ~RANK) | RL;
+            LN[(r)] = (__viaddmax_s32(dn, o, ln) & keep) | RL;
 #define IDP_ROW(r)                                                                     \
     case (r): {                                                                        \
         if ((r) >= hi) break;                                                          \
@@ -745,9 +749,10 @@ __device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint3
     if (m == 0) { out.score = LOCAL ? 0 : P.gap_open + n * P.gap_extend; return out; }
     if constexpr (!LOCAL) return sw_trace_reg_glocal_shifted<NQ>(P, qbot, n, lo, hi, T, m);
     constexpr int SH = 14, LOW = 0x3FFF, RANK = 0x3000, RD = 0x3000, RL = 0x2000, RU = 0x1000;
-    int oe = (P.gap_open + P.gap_extend) << SH, e = P.gap_extend * (1 << SH), ma = P.match_score << SH, mi = P.mismatch_score * (1 << SH);
-    oe = (P.gap_open + P.gap_extend) * (1 << SH);
-    asm volatile("" : "+r"(oe), "+r"(e), "+r"(ma), "+r"(mi));  // keep the constants in registers across the unrolled rows
+    const int oe = P.tr_open_ext, e = P.tr_ext;  // constant-bank operands
+    const unsigned am = __activemask();
+    const int self = (int)(threadIdx.x & 31u);
+    const int ma = __shfl_sync(am, P.tr_match, self), mi = __shfl_sync(am, P.tr_mismatch, self), keep = __shfl_sync(am, ~RANK, self);  // registers
     constexpr int NEG = -(1 << 30);  // score -2^16
     const int off = NQ - n;
     uint32_t q[NQ / 8];
@@ -772,11 +777,11 @@ __device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint3
 #define IDP_CELL(r)                                                                                              \
             int dn = ((mdiag + ((ne[(r) >> 3] & (1u << (4 * ((r) & 7)))) ? mi : ma)) & ~RANK) | RD;               \
             if (LOCAL) dn = dn < 0 ? (RD | j) : dn; /* clamp at zero: the path (re)starts after this cell */      \
-            const int un = (__viaddmax_s32(d_up, oe, u_up + e) & ~RANK) | RU; /* equal scores: opened from Diagonal */ \
+            const int un = (__viaddmax_s32(d_up, oe, u_up + e) & keep) | RU; /* equal scores: opened from Diagonal */ \
             const int ln = LN[(r)];                                                                               \
             const int mold = M[(r)];                                                                              \
             M[(r)] = __vimax3_s32(dn, ln, un); /* equal scores: Diagonal, then Left, then Up */                   \
-            LN[(r)] = (__viaddmax_s32(dn, oe, ln + e) & ~RANK) | RL;
+            LN[(r)] = (__viaddmax_s32(dn, oe, ln + e) & keep) | RL;
         // Local best cell: lowest row, then lowest column; Left/Up values never win (each is bounded by a Diagonal value of a
         // cell scanned earlier, gap scores being <= 0, and ties go to the earlier cell)
 #define IDP_BEST(r, cond)                                                                      \
