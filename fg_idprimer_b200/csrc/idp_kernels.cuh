@@ -845,37 +845,82 @@ __global__ void __launch_bounds__(128, 4) sw_pairs_kernel(DevPanel P, DevReads R
     const unsigned n_pairs = min(ctr->n_pairs, pair_cap);
     const unsigned n_work = work_read ? ctr->n_fall : (unsigned)R.n;
     unsigned long long cells = 0;
-    for (unsigned base = blockIdx.x * blockDim.x; base < n_pairs; base += gridDim.x * blockDim.x) {
-        const unsigned t = base + threadIdx.x;
-        bool active = t < n_pairs;
-        int n = 0, m = 0, p = 0;
-        Oriented T{nullptr, 0, false};
-        if (active) {
-            const unsigned w = pair_work[t];
-            p = (int)pair_primer[t];
-            active = w < n_work && (unsigned)p < (unsigned)P.n_primers;
-            if (active) {
-                const int r = work_read ? (int)work_read[w] : (int)w;
-                n = __ldg(&P.pinfo[p]).w;
-                T = make_target(P, R, r, n, LOCAL, m);
+    // A block takes `tile` x blockDim pairs at a time and deals them to its warps sorted by primer length (a counting sort
+    // in shared memory), so that the 32 alignments of a warp have (nearly) the same number of rows: the unrolled rows are
+    // entered at the longest query of the warp and the rows between the longest and the shortest run the slower ragged form.
+    constexpr int kTileMax = 4, kBins = kMaxPrimerBases + 2;
+    __shared__ unsigned short order_s[128 * kTileMax];
+    __shared__ int hist_s[kBins];
+    const unsigned per_round = gridDim.x * blockDim.x;
+    const int tile = n_pairs >= 4u * per_round ? 4 : n_pairs >= 2u * per_round ? 2 : 1;  // keep every SM busy on small batches
+    const unsigned span = (unsigned)tile * blockDim.x;
+    for (unsigned base = blockIdx.x * span; base < n_pairs; base += gridDim.x * span) {
+        for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist_s[i] = 0;
+        __syncthreads();
+        int bin[kTileMax], rank[kTileMax];
+#pragma unroll
+        for (int k = 0; k < kTileMax; ++k) {
+            bin[k] = kBins - 1;  // not a pair: sorts to the end
+            if (k < tile) {
+                const unsigned t = base + (unsigned)k * blockDim.x + threadIdx.x;
+                if (t < n_pairs) {
+                    const unsigned pp = pair_primer[t];
+                    if (pp < (unsigned)P.n_primers) bin[k] = min(__ldg(&P.pinfo[pp]).w, kBins - 2);
+                }
+                rank[k] = atomicAdd(&hist_s[bin[k]], 1);
             }
         }
-        const int n_warp_max = __reduce_max_sync(0xffffffffu, n);
-        const int n_warp_min = __reduce_min_sync(0xffffffffu, active ? n : n_warp_max);
-        constexpr int NQF = NQ == 64 ? 64 : 32;
-        if (active) {
-            bool missing = false;
-            int sc;
-            if (TRACE) {  // few candidates per read: carry the start column too, so no second alignment is needed
-                const TracedReg tr = sw_trace_reg<NQF, LOCAL>(P, P.qbot + (size_t)p * (NQF / 8), n, NQF - n_warp_max, NQF - n_warp_min, T, m);
-                sc = tr.score;
-                pair_se[t] = ((unsigned)tr.t_start & 0xFFFFu) | ((unsigned)tr.t_end << 16);
-            } else if (NQ > 0 && !SMAT) sc = sw_score_fast<NQF, LOCAL>(P, P.qbot + (size_t)p * (NQF / 8), n, NQF - n_warp_max, NQF - n_warp_min, T, m);
-            else if (NQ > 0) sc = sw_score<(NQ > 0 ? NQ : 8), LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, n_warp_max, T, m, missing);
-            else sc = sw_score_generic<LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, T, m, missing);
-            pair_score[t] = missing ? kScoreMissing : sc;
-            cells += (unsigned long long)n * (unsigned long long)m;
+        __syncthreads();
+        if (threadIdx.x < 32) {  // exclusive prefix sum over the bins, one warp
+            int carry = 0;
+            for (int b0 = 0; b0 < kBins; b0 += 32) {
+                const int b = b0 + (int)threadIdx.x;
+                const int v = b < kBins ? hist_s[b] : 0;
+                int incl = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, d); if ((int)threadIdx.x >= d) incl += u; }
+                if (b < kBins) hist_s[b] = carry + incl - v;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
         }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kTileMax; ++k)
+            if (k < tile) order_s[hist_s[bin[k]] + rank[k]] = (unsigned short)(k * blockDim.x + threadIdx.x);
+        __syncthreads();
+        for (int k = 0; k < tile; ++k) {
+            const unsigned t = base + order_s[k * blockDim.x + threadIdx.x];
+            bool active = t < n_pairs;
+            int n = 0, m = 0, p = 0;
+            Oriented T{nullptr, 0, false};
+            if (active) {
+                const unsigned w = pair_work[t];
+                p = (int)pair_primer[t];
+                active = w < n_work && (unsigned)p < (unsigned)P.n_primers;
+                if (active) {
+                    const int r = work_read ? (int)work_read[w] : (int)w;
+                    n = __ldg(&P.pinfo[p]).w;
+                    T = make_target(P, R, r, n, LOCAL, m);
+                }
+            }
+            const int n_warp_max = __reduce_max_sync(0xffffffffu, n);
+            const int n_warp_min = __reduce_min_sync(0xffffffffu, active ? n : n_warp_max);
+            constexpr int NQF = NQ == 64 ? 64 : 32;
+            if (active) {
+                bool missing = false;
+                int sc;
+                if (TRACE) {  // few candidates per read: carry the start column too, so no second alignment is needed
+                    const TracedReg tr = sw_trace_reg<NQF, LOCAL>(P, P.qbot + (size_t)p * (NQF / 8), n, NQF - n_warp_max, NQF - n_warp_min, T, m);
+                    sc = tr.score;
+                    pair_se[t] = ((unsigned)tr.t_start & 0xFFFFu) | ((unsigned)tr.t_end << 16);
+                } else if (NQ > 0 && !SMAT) sc = sw_score_fast<NQF, LOCAL>(P, P.qbot + (size_t)p * (NQF / 8), n, NQF - n_warp_max, NQF - n_warp_min, T, m);
+                else if (NQ > 0) sc = sw_score<(NQ > 0 ? NQ : 8), LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, n_warp_max, T, m, missing);
+                else sc = sw_score_generic<LOCAL, SMAT>(P, smat_s, P.pmask + (size_t)p * P.ww, n, T, m, missing);
+                pair_score[t] = missing ? kScoreMissing : sc;
+                cells += (unsigned long long)n * (unsigned long long)m;
+            }
+        }
+        __syncthreads();  // order_s / hist_s are rewritten by the next tile
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, d);
