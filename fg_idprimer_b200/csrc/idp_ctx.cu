@@ -221,7 +221,7 @@ static int launch_scan_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, i
     S.off_heads = place((size_t)ix.n_postings * 8, !FAST && ix.k > 0);
     const int n_tiles = (R.n + kScanThreads - 1) / kScanThreads;
     const int grid = std::max(1, std::min(n_tiles, kScanMinBlocks * c->sm_count));
-    const bool onchip = FAST && S.stage_tile && S.off_bsmm != 0xFFFFFFFFu && S.off_bsacc != 0xFFFFFFFFu;
+    const bool onchip = FAST && S.stage_tile;
     auto launch = [&](auto kernel) -> int {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) {
             set_error("cudaFuncSetAttribute(scan_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));

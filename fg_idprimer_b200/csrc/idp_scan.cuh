@@ -290,8 +290,8 @@ __device__ __forceinline__ bool seed_filter(const DevPanel &P, ScanCtx<RW> &c, c
     return fits;
 }
 
-// ONCHIP: the read tiles and the bit-sliced tables are known at compile time to sit in shared memory, so the hot loads are
-// LDS rather than generic loads (the launcher picks it when the shared-memory plan placed all of them)
+// ONCHIP: the read tiles are known at compile time to sit in shared memory, so the window loads are LDS rather than generic
+// loads; the unrolled bit-sliced filter addresses its tables as shared memory as well (the general loop does not)
 template <int RW, bool FAST, bool ONCHIP>
 __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(const __grid_constant__ DevPanel P, const __grid_constant__ DevReads R, const __grid_constant__ ScanLaunch S, idp_result *__restrict__ five,
                                                                unsigned int *__restrict__ fall, Counters *__restrict__ ctr) {
@@ -330,12 +330,12 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
     if (FAST && S.off_bsmm != 0xFFFFFFFFu) {
         uint32_t *d = reinterpret_cast<uint32_t *>(smem + S.off_bsmm);
         for (int i = tid; i < P.bs_groups * kBsStride * 16; i += blockDim.x) d[i] = P.bs_mm[i];
-        if (!ONCHIP) bs_mm = d;
+        bs_mm = d;
     }
     if (FAST && S.off_bsacc != 0xFFFFFFFFu) {
         uint2 *d = reinterpret_cast<uint2 *>(smem + S.off_bsacc);
         for (int i = tid; i < P.bs_groups; i += blockDim.x) d[i] = P.bs_acc[i];
-        if (!ONCHIP) bs_acc = d;
+        bs_acc = d;
     }
     const uint32_t *seed_tab = P.seed_tab;
     if (FAST && P.seed_ok && S.off_seed != 0xFFFFFFFFu) {
@@ -343,12 +343,9 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
         for (int i = tid; i < 2 * P.seed_slots; i += blockDim.x) d[i] = P.seed_tab[i];
         seed_tab = d;
     }
-    if (ONCHIP) {  // provably shared pointers
-        bs_mm = reinterpret_cast<const uint32_t *>(smem + S.off_bsmm);
-        bs_acc = reinterpret_cast<const uint2 *>(smem + S.off_bsacc);
-    }
-    const uint32_t tab_addr = ONCHIP ? smem_u32(smem) + S.off_bsmm : 0u, acc_addr = ONCHIP ? smem_u32(smem) + S.off_bsacc : 0u;
-    const bool fixed_groups = ONCHIP && (tab_addr & 63u) == 0u && P.bs_groups >= 2 && P.bs_groups <= 8 && (P.bs_groups & 1) == 0;
+    const bool bs_onchip = ONCHIP && S.off_bsmm != 0xFFFFFFFFu && S.off_bsacc != 0xFFFFFFFFu;  // large panels keep them in global memory
+    const uint32_t tab_addr = bs_onchip ? smem_u32(smem) + S.off_bsmm : 0u, acc_addr = bs_onchip ? smem_u32(smem) + S.off_bsacc : 0u;
+    const bool fixed_groups = bs_onchip && (tab_addr & 63u) == 0u && P.bs_groups >= 2 && P.bs_groups <= 8 && (P.bs_groups & 1) == 0;
     if (S.stage_tile && lane == 0) {
         mbar_init(&tile_bar[wib][0], 1);
         mbar_init(&tile_bar[wib][1], 1);
@@ -462,6 +459,19 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
             // ---- UngappedAlignmentBasedPrimerMatcher.find (PM:230-248) ----
             if (res.type == IDP_NONE && !(ix.k > 0 && c.len < ix.k)) {  // PM:109: a read shorter than k has no candidates
                 Best2 best;
+                // the out-of-line walks get COPIES: an object whose address reaches a call lives in local memory for the
+                // whole kernel, and the read window / running best are touched by every instruction of the hot path
+                auto scan_exact = [&](const uint32_t *dir, const uint2 *hd) {
+                    ScanCtx<RW> cc = c;
+                    Best2 bb = best;
+                    kmer_scan_exact<RW>(P, cc, bb, dir, hd);
+                    best = bb;
+                    c.compares = cc.compares;
+                };
+                auto member_exact = [&](int p) {
+                    const ScanCtx<RW> cc = c;
+                    return kmer_member_exact<RW>(P, cc, p);
+                };
                 if (FAST) {
                     // survivors of the 16-base bit-sliced filter, ascending primer index (file order)
                     int n_acc = 0, a_p = -1, a_mm = 0, a_plen = 1, a_seq = 0;
@@ -528,10 +538,10 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
                     if (ix.k > 0) {
                         if (n_acc == 1) {
                             const int n_bases = min(ix.window, c.len);
-                            if (diagonal_kmer<RW>(P, c, a_p, a_seq, ix.k, n_bases) || kmer_member_exact<RW>(P, c, a_p))
+                            if (diagonal_kmer<RW>(P, c, a_p, a_seq, ix.k, n_bases) || member_exact(a_p))
                                 best.offer(a_p, a_mm, 0.0);  // the only accepted candidate: its sort key is never compared
                         } else if (n_acc >= 2) {
-                            kmer_scan_exact<RW>(P, c, best, ix.direct, ix.heads);  // ties: the reference's candidate order decides
+                            scan_exact(ix.direct, ix.heads);  // ties: the reference's candidate order decides
                         }
                     }
                 } else if (ix.k <= 0) {  // PM:100: every primer, file order
@@ -540,7 +550,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
                         if (mismatch_align<RW>(P, c, p, mm, plen)) best.offer(p, mm, __ddiv_rn((double)mm, (double)plen));
                     }
                 } else {
-                    kmer_scan_exact<RW>(P, c, best, direct, heads);
+                    scan_exact(direct, heads);
                 }
                 if (best.bp >= 0) {
                     res.primer = best.bp; res.type = IDP_UNGAPPED; res.mm = best.bmm;
