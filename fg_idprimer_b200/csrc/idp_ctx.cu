@@ -200,7 +200,10 @@ static int launch_scan_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, i
     // a warp tile is 32 reads: 32 * stride bytes, always a multiple of 16 as the TMA bulk copy requires
     S.stage_tile = R.fixed_len > 0 && (reinterpret_cast<uintptr_t>(R.seq4) & 15) == 0;
     if (S.stage_tile) {
-        S.tile_smem_bytes = (uint32_t)((32 * (size_t)S.stride + 4 * RW + 16 + 15) & ~size_t(15));
+        // 32 reads, slack for the last read's window words, then the tile's 32 flag words
+        S.flags_off = (uint32_t)((32 * (size_t)S.stride + 4 * RW + 16 + 15) & ~size_t(15));
+        S.tile_smem_bytes = S.flags_off + 64;
+        S.stage_flags = (reinterpret_cast<uintptr_t>(R.flags) & 15) == 0;
         used = (size_t)S.tile_smem_bytes * 2 * kScanWarps;
         if (used > budget - 16 * 1024) { S.stage_tile = 0; S.tile_smem_bytes = 0; used = 0; }
     }

@@ -29,6 +29,8 @@ struct ScanLaunch {
     int32_t stage_tile;        // 1: reads are fixed-length and 16-byte aligned: tiles are staged into shared memory by TMA
     uint32_t stride;           // bytes per read when fixed-length
     uint32_t tile_smem_bytes;  // shared-memory bytes of one warp tile buffer (incl. slack), multiple of 16
+    int32_t stage_flags;       // 1: the tile's flag words ride along (16-byte aligned flags array), at flags_off in the tile buffer
+    uint32_t flags_off;
     // byte offsets into dynamic shared memory, or 0xFFFFFFFF when the structure stays in global memory
     uint32_t off_direct, off_heads, off_pmask, off_pinfo, off_bsmm, off_bsacc, off_seed;
     uint32_t direct_entries;
@@ -362,25 +364,23 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
         const size_t g0 = (size_t)wt * 32 * S.stride;
         const uint32_t bytes = (uint32_t)min(32, R.n - wt * 32) * S.stride;
         const uint32_t bulk = bytes & ~15u;
+        const uint32_t fbytes = S.stage_flags ? (uint32_t)min(32, R.n - wt * 32) * 2u : 0u, fbulk = fbytes & ~15u;
         if (lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&tile_bar[wib][b], bulk);
+            mbar_expect_tx(&tile_bar[wib][b], bulk + fbulk);
             if (bulk) tma_load_1d(wbuf(b), R.seq4 + g0, bulk, &tile_bar[wib][b]);
+            if (fbulk) tma_load_1d(wbuf(b) + S.flags_off, R.flags + (size_t)wt * 32, fbulk, &tile_bar[wib][b]);
         }
         if (lane < (int)(bytes - bulk)) wbuf(b)[bulk + lane] = R.seq4[g0 + bulk + lane];
+        if (2u * lane >= fbulk && 2u * lane < fbytes) reinterpret_cast<uint16_t *>(wbuf(b) + S.flags_off)[lane] = R.flags[(size_t)wt * 32 + lane];
     };
     int cur = 0;
     const int wt0 = blockIdx.x * kScanWarps + wib;
     if (S.stage_tile && wt0 < n_wtiles) issue_tile(wt0, 0);
-    uint16_t fl_next = (wt0 < n_wtiles && wt0 * 32 + lane < R.n) ? R.flags[wt0 * 32 + lane] : (uint16_t)0;
+    const bool flags_staged = S.stage_tile && S.stage_flags;
     for (int wt = wt0; wt < n_wtiles; wt += warps_total) {
         const int r = wt * 32 + lane;
         const bool active = r < R.n;
-        const uint16_t fl = fl_next;
-        {   // the next tile's flags travel while this tile is matched
-            const int rn = (wt + warps_total) * 32 + lane;
-            if (wt + warps_total < n_wtiles && rn < R.n) fl_next = R.flags[rn];
-        }
         if (S.stage_tile) {
             if (wt + warps_total < n_wtiles) issue_tile(wt + warps_total, cur ^ 1);  // prefetch; that buffer was released below
             mbar_wait(&tile_bar[wib][cur], (phase >> cur) & 1u);
@@ -390,6 +390,8 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
         bool need_gapped = false;
         c.compares = 0;
         if (active) {
+            const uint16_t fl = flags_staged ? reinterpret_cast<const uint16_t *>(smem + (size_t)(2 * wib + cur) * S.tile_smem_bytes + S.flags_off)[lane]
+                                             : R.flags[r];
             const uint8_t *s;
             read_geom(R, r, s, c.len);
             const bool rc = seq_order_is_rc(fl);
