@@ -348,12 +348,22 @@ def main():
                 cells = tms[-1]["sw_cells"]; ms = statistics.mean(t["ms_sw_score"] for t in tms)
                 out["gapped_stress"] = {"workload": "c3b: 200000 read pairs vs 1000-pair panel, 5% indel reads, -k 6, no -K", "gcups": cells / (ms / 1e3) / 1e9,
                                         "cells": int(cells), "alignments": int(tms[-1]["n_alignments_5p"]), "sw_kernel_ms": ms}
-                try:  # integer roofline: measured INT32 issue rate (tools/int_peak.cu) / 9 instructions per cell
+                try:
+                    # integer issue roofline of the packed aligner (two alignments per register): per PAIR of cells
+                    # 3 full-rate instructions (SHF, LOP3, LOP3) and 5 half-rate ones (IMAD, VIADD.16x2, 2 x VIADDMNMX.S16x2,
+                    # VIMNMX3.S16x2), at the issue rates measured by tools/int_peak.cu and tools/int_peak16.cu
                     with open(os.path.join(ROOT, "profiles", "int_peak_b200.json")) as fh:
                         ip = json.load(fh)
-                    peak = ip["lop_iadd_mix_ops_per_s"] / 9 / 1e9
+                    with open(os.path.join(ROOT, "profiles", "int_peak16_b200.json")) as fh:
+                        ip16 = json.load(fh)
+                    full = ip["lop_iadd_per_clk_per_sm"]
+                    half = min(ip16["per_clk_per_sm"]["viaddmax_s16x2"], ip16["per_clk_per_sm"]["vimax3_s16x2"], ip16["per_clk_per_sm"]["imad"])
+                    clk_per_pair = 3.0 / full + 5.0 / half
+                    peak = 2.0 / clk_per_pair * ip["sms"] * ip["sm_clock_mhz_max"] * 1e6 / 1e9
                     out["gapped_stress"].update({"roofline_gcups": peak, "frac": out["gapped_stress"]["gcups"] / peak,
-                                                 "peak_source": "measured INT32 (lop3+iadd) issue rate / 9 instr per cell, profiles/int_peak_b200.json"})
+                                                 "peak_source": "integer issue roofline: 3 full-rate + 5 half-rate instructions per two cells at the measured "
+                                                                "rates (profiles/int_peak_b200.json, profiles/int_peak16_b200.json)",
+                                                 "roofline_gcups_32bit_9_instr_per_cell": ip["lop_iadd_mix_ops_per_s"] / 9 / 1e9})
                 except Exception:
                     pass
         except Exception as e:  # pragma: no cover
