@@ -764,7 +764,8 @@ __device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint3
         if (LOCAL) { LN[r] = (__viaddmax_s32(RD, oe, RL + e) & ~RANK) | RL; M[r] = RD; }  // column 0: all zero, start 0
         else { LN[r] = NEG | RL; M[r] = ((P.gap_open + (r - off + 1) * P.gap_extend) * (1 << SH)) | RU; }  // Up(i,0), start 0
     }
-    int best = NEG, bi = 0, bj = 0;
+    int best = NEG, bestkey = INT_MIN, bj = 0;
+    const int keeplow = __shfl_sync(am, ~LOW, self);
     TargetStream ts(T);
     for (int j = 1; j <= m; ++j) {
         uint32_t t = ts.nib(j - 1);
@@ -784,11 +785,13 @@ __device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint3
             LN[(r)] = (__viaddmax_s32(dn, oe, ln + e) & keep) | RL;
         // Local best cell: lowest row, then lowest column; Left/Up values never win (each is bounded by a Diagonal value of a
         // cell scanned earlier, gap scores being <= 0, and ties go to the earlier cell)
+        // as ONE integer comparison: key = score bits | (NQ-1 - row); a larger key is a higher score or the same score in a lower
+        // row, an equal key is the same row in a later column and does not replace
 #define IDP_BEST(r, cond)                                                                      \
             if (LOCAL) {                                                                       \
-                const int ds = dn >> SH, bs = best >> SH;                                      \
-                const bool better = (cond) && (ds > bs || (ds == bs && (r) + 1 < bi));         \
-                best = better ? dn : best; bi = better ? (r) + 1 : bi; bj = better ? j : bj;   \
+                const int key = (cond) ? ((dn & keeplow) | (NQ - 1 - (r))) : INT_MIN;          \
+                const bool better = key > bestkey;                                             \
+                bestkey = max(bestkey, key); best = better ? dn : best; bj = better ? j : bj;  \
             }
 #define IDP_ROW(r)                                                                     \
     case (r): {                                                                        \
