@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(256) cand5_thread_kernel(DevPanel P, DevReads 
     const unsigned n_work = ctr->n_fall;
     const int lane = threadIdx.x & 31;
     const uint64_t kmask = ix.k >= 16 ? ~0ull : ((1ull << (4 * ix.k)) - 1ull);
+    const uint32_t kmask2 = ix.k >= 16 ? ~0u : ((1u << (2 * ix.k)) - 1u);
     for (unsigned base = blockIdx.x * blockDim.x; base < n_work; base += gridDim.x * blockDim.x) {
         const unsigned w = base + threadIdx.x;
         const bool active = w < n_work;
@@ -175,10 +176,21 @@ __global__ void __launch_bounds__(256) cand5_thread_kernel(DevPanel P, DevReads 
             TargetStream ts(Oriented{s, len, seq_order_is_rc(R.flags[r])});
             const int n_bases = len >= ix.k ? min(ix.window, len) : 0;  // k-mers start at 0 .. n_bases - k (PM:110)
             uint64_t key = 0;
+            uint32_t key2 = 0;
+            int bad = 0;  // > 0 while the current k-mer holds a code that is not exactly one of A/C/G/T
             for (int i = 0; i < n_bases && !spilled; ++i) {
-                key = ((key << 4) | ts.nib(i)) & kmask;
+                const uint32_t nib = ts.nib(i);
+                key = ((key << 4) | nib) & kmask;
+                key2 = ((key2 << 2) | ((0x30210u >> (2 * nib)) & 3u)) & kmask2;  // A,C,G,T (1,2,4,8) -> 0..3
+                bad = max(bad - 1, 0);
+                if (__popc(nib) != 1) bad = ix.k;
                 OffCnt oc;
-                if (i < ix.k - 1 || !kmer_lookup(ix, key, oc)) continue;
+                if (i < ix.k - 1) continue;
+                if (ix.direct != nullptr && bad == 0) {  // one load, no probing: the lanes of a warp stay together
+                    const uint32_t e = __ldg(&ix.direct[key2]);
+                    if (!e) continue;
+                    oc.off = e & 0xFFFFFu; oc.cnt = e >> 20;
+                } else if (!kmer_lookup(ix, key, oc)) continue;
                 for (uint32_t j = 0; j < oc.cnt; ++j) {
                     const int p = (int)__ldg(&ix.postings[oc.off + j]);
                     bool seen = false;

@@ -169,6 +169,7 @@ static bool build_kmer_index(const idp_panel &p, int k, KmerIndexHost &out) {
         }
     }
     size_t slots = 16;
+    while (slots < 8 * kmers.size() + 2 && slots < (size_t(1) << 22)) slots *= 2;  // sparse: a warp probes until its slowest lane is done
     while (slots < 2 * kmers.size() + 2) slots *= 2;
     out.keys.assign(slots, 0);
     out.off.assign(slots, 0);
@@ -198,7 +199,7 @@ static bool build_kmer_index(const idp_panel &p, int k, KmerIndexHost &out) {
         out.heads[2 * j + 1] = p.pmask[(size_t)id * p.ww];
     }
     // direct-address table over the 4^k all-ACGT k-mers (2 bits per base): entry = posting offset (20 bits) | count (12 bits)
-    if (k <= 7 && out.postings.size() < (1u << 20) && p.n < (1 << 20)) {
+    if (k <= 11 && out.postings.size() < (1u << 20) && p.n < (1 << 20)) {  // up to 16 MB; the scan kernel stages it in shared memory when k <= 6
         bool fits = true;
         std::vector<uint32_t> direct((size_t)1 << (2 * k), 0);
         for (auto &kv : out.by_string) {
