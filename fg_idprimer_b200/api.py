@@ -397,6 +397,29 @@ class IdentifyPrimers:
             tags["f5"] = self.info(three, flags)
         return tags
 
+    def annotate_bam(self, bam: bytes, five, three=None) -> bytes:
+        """The records of `bam` (the bytes ReadBatch.from_bam was given) with the f5/r5(/f3/r3) tags set as addTagsToPair /
+        addTagsToFragment do (IP:522-569); `five` / `three` are the result rows of process_batch on that batch."""
+        lib = L.lib()
+        buf = np.frombuffer(bam, dtype=np.uint8)
+        five = np.ascontiguousarray(five, dtype=L.RESULT_DTYPE)
+        three_ptr = None
+        if three is not None:
+            three = np.ascontiguousarray(three, dtype=L.RESULT_DTYPE)
+            three_ptr = three.ctypes.data
+        need = C.c_size_t(0)
+        L.check(lib.idp_bam_annotate(self._panel, buf.ctypes.data, len(buf), five.ctypes.data, three_ptr, len(five), None, 0, C.byref(need)))
+        out = np.zeros(need.value, dtype=np.uint8)
+        L.check(lib.idp_bam_annotate(self._panel, buf.ctypes.data, len(buf), five.ctypes.data, three_ptr, len(five), out.ctypes.data, len(out), C.byref(need)))
+        return out.tobytes()
+
+    @staticmethod
+    def header_comments() -> List[str]:
+        """The @CO lines the tool adds to the output header (IP:243-250)."""
+        buf = C.create_string_buffer(2048)
+        L.lib().idp_header_comments(buf, 2048)
+        return buf.value.decode().split("\n")
+
     # ---- downstream classification (scripts/post_process_bam.py:56-78) ----
     CLASS_NAMES = ["Canonical", "SelfDimer", "CrossDimer", "NonCanonical", "Single", "NoMatch"]
 

@@ -1,4 +1,5 @@
-// Host ingest: uncompressed BAM alignment records -> the SoA batch of include/idprimer.h.
+// Host ingest / egress: uncompressed BAM alignment records -> the SoA batch of include/idprimer.h, and the same records
+// with the primer-match tags added.
 //
 // The reference reaches its matchers through fgbio's Bams.templateIterator (IdentifyPrimers.scala:288-289), which yields the
 // primary R1 / R2 of each queryname group; the matchers then look at rec.bases, rec.unmapped, rec.positiveStrand, rec.refIndex,
@@ -144,6 +145,135 @@ int idp_bam_to_batch(const uint8_t *bam, size_t n_bytes, uint8_t *seq4, uint64_t
         group.push_back({r, ord});
     }
     return flush();
+}
+
+// The three @CO header lines the tool adds (IdentifyPrimers.scala:243-250), '\n'-separated; returns the length.
+int idp_header_comments(char *buf, int32_t cap) {
+    static const char *text =
+        "The f5/r5/f3/r3 tags store the primer match metadata for the forward and reverse strand respectively.\n"
+        "The f5/r5/f3/r3 tags are formatted as follow: <pair_id>,<primer_id>,<ref_name>:<start>-<end>,<strand>,<read-num>,<match-offset>,"
+        "<match-length>,<match-type>,<match-type-info>.\n"
+        "The match-type is 'location', 'gapped', or 'ungapped' based on if the match was found using the location, mismatch-based (ungapped) "
+        "alignment, or gapped-alignment.";
+    if (buf && cap > 0) snprintf(buf, (size_t)cap, "%s", text);
+    return (int)strlen(text);
+}
+
+// Host egress: the input records with the primer-match tags set the way addTagsToPair / addTagsToFragment do
+// (IdentifyPrimers.scala:522-569): Z-type aux fields f5 / r5 (and f3 / r3 when --three-prime >= 0) on the primary R1 / R2 of
+// every template, including the fragment quirk (with --three-prime the 3' match overwrites f5 and no f3 / r3 is written).
+// five / three are the results of idp_match_batch for the batch idp_bam_to_batch made from the same bytes (n_reads rows, R1
+// then R2 per template).  Records come out template by template in Template.allReads order: R1, R2, then supplementary and
+// secondary records (R1's before R2's), untouched.  A record that already carries one of the tags has it replaced.
+// out == NULL sizes the output (*out_bytes); IDP_ERR_ARG when out_cap is too small or the batch does not match the bytes.
+int idp_bam_annotate(const idp_panel *panel, const uint8_t *bam, size_t n_bytes, const idp_result *five, const idp_result *three,
+                     int32_t n_reads, uint8_t *out, size_t out_cap, size_t *out_bytes) {
+    if (!panel || !bam || !five || !out_bytes) { idp::set_error("idp_bam_annotate: NULL argument"); return IDP_ERR_ARG; }
+    const bool want3 = panel->params.three_prime >= 0;
+    if (want3 && !three) { idp::set_error("idp_bam_annotate: the panel has --three-prime set but no 3' results were passed"); return IDP_ERR_ARG; }
+    size_t off = 0, w = 0;
+    int32_t read = 0;
+    bool fits = true;
+    auto put = [&](const void *src, size_t n) {
+        if (out) { if (w + n <= out_cap) memcpy(out + w, src, n); else fits = false; }
+        w += n;
+    };
+    auto info = [&](const idp_result *r, uint16_t fl) {
+        char buf[1024];
+        idp_format_info(panel, r, fl, buf, (int32_t)sizeof buf);
+        return std::string(buf);
+    };
+    auto is_ours = [](const uint8_t *t) { return (t[0] == 'f' || t[0] == 'r') && (t[1] == '5' || t[1] == '3'); };
+    // copies a record, dropping f5/r5/f3/r3 aux fields, and appends the given tags
+    auto write_rec = [&](const BamRec &r, const std::vector<std::pair<const char *, std::string>> &tags) -> int {
+        const uint8_t *aux = r.seq + (size_t)((r.l_seq + 1) / 2) + (size_t)r.l_seq, *end = r.p + r.block_size;
+        std::vector<std::pair<const uint8_t *, size_t>> keep;  // aux byte ranges that stay
+        const uint8_t *a = aux;
+        while (a < end) {
+            if (end - a < 3) { idp::set_error("idp_bam_annotate: truncated aux field"); return IDP_ERR_ARG; }
+            const uint8_t *f = a;
+            const char ty = (char)a[2];
+            a += 3;
+            auto fixed = [](char t) { return t == 'A' || t == 'c' || t == 'C' ? 1 : t == 's' || t == 'S' ? 2 : t == 'i' || t == 'I' || t == 'f' ? 4 : 0; };
+            if (fixed(ty)) a += fixed(ty);
+            else if (ty == 'Z' || ty == 'H') { while (a < end && *a) ++a; ++a; }
+            else if (ty == 'B') {
+                if (end - a < 5) { idp::set_error("idp_bam_annotate: truncated B aux field"); return IDP_ERR_ARG; }
+                const int es = fixed((char)a[0]);
+                const uint32_t cnt = (uint32_t)rd32(a + 1);
+                if (!es) { idp::set_error("idp_bam_annotate: unknown B subtype"); return IDP_ERR_ARG; }
+                a += 5 + (size_t)es * cnt;
+            } else { idp::set_error("idp_bam_annotate: unknown aux type '%c'", ty); return IDP_ERR_ARG; }
+            if (a > end) { idp::set_error("idp_bam_annotate: aux field runs past the record"); return IDP_ERR_ARG; }
+            if (!(tags.size() && is_ours(f))) keep.push_back({f, (size_t)(a - f)});
+        }
+        size_t body = (size_t)(aux - r.p);
+        for (auto &k : keep) body += k.second;
+        for (auto &t : tags) body += 3 + t.second.size() + 1;
+        const int32_t bs = (int32_t)body;
+        put(&bs, 4);
+        put(r.p, (size_t)(aux - r.p));
+        for (auto &k : keep) put(k.first, k.second);
+        for (auto &t : tags) { put(t.first, 2); put("Z", 1); put(t.second.c_str(), t.second.size() + 1); }
+        return IDP_OK;
+    };
+    std::vector<BamRec> group;
+    std::string group_name;
+    auto flush = [&]() -> int {
+        if (group.empty()) return IDP_OK;
+        const BamRec *r1 = nullptr, *r2 = nullptr;
+        for (auto &g : group) {
+            if (g.flag & 0x900) continue;
+            const bool paired = g.flag & 0x1;
+            if (!paired || (g.flag & 0x40)) r1 = r1 ? r1 : &g; else r2 = r2 ? r2 : &g;
+        }
+        if (!r1) { idp::set_error("Template did not have an R1: %s", group_name.c_str()); return IDP_ERR_ARG; }
+        const int32_t i1 = read, i2 = r2 ? read + 1 : -1;
+        read += r2 ? 2 : 1;
+        if (read > n_reads) { idp::set_error("idp_bam_annotate: more reads in the BAM bytes than results"); return IDP_ERR_ARG; }
+        std::vector<std::pair<const char *, std::string>> tags;
+        const uint16_t fl1 = (uint16_t)r1->flag, fl2 = r2 ? (uint16_t)r2->flag : 0;
+        if (r2) {  // addTagsToPair: which read is "forward" follows R1's 5' primer, then R2's, else R1 (IP:530-540)
+            bool fwd_is_r1 = true;
+            if (five[i1].type != IDP_NONE && five[i1].primer >= 0 && five[i1].primer < panel->n) fwd_is_r1 = panel->positive[five[i1].primer] != 0;
+            else if (five[i2].type != IDP_NONE && five[i2].primer >= 0 && five[i2].primer < panel->n) fwd_is_r1 = panel->positive[five[i2].primer] == 0;
+            const int32_t fi = fwd_is_r1 ? i1 : i2, ri = fwd_is_r1 ? i2 : i1;
+            const uint16_t ffl = fwd_is_r1 ? fl1 : fl2, rfl = fwd_is_r1 ? fl2 : fl1;
+            tags.push_back({"f5", info(&five[fi], ffl)});
+            tags.push_back({"r5", info(&five[ri], rfl)});
+            if (want3) { tags.push_back({"f3", info(&three[fi], ffl)}); tags.push_back({"r3", info(&three[ri], rfl)}); }
+        } else {   // addTagsToFragment (IP:557-569)
+            tags.push_back({"f5", want3 ? info(&three[i1], fl1) : info(&five[i1], fl1)});
+            tags.push_back({"r5", "none"});
+        }
+        int rc = write_rec(*r1, tags);
+        if (!rc && r2) rc = write_rec(*r2, tags);
+        // Template.allReads: r1, r2, r1 supplementals, r2 supplementals, r1 secondaries, r2 secondaries
+        for (int pass = 0; pass < 4 && !rc; ++pass)
+            for (auto &g : group) {
+                if (rc || !(g.flag & 0x900)) continue;
+                const bool supp = (g.flag & 0x800) != 0, second_end = (g.flag & 0x1) && !(g.flag & 0x40);
+                if ((pass == 0 && supp && !second_end) || (pass == 1 && supp && second_end) || (pass == 2 && !supp && !second_end) ||
+                    (pass == 3 && !supp && second_end))
+                    rc = write_rec(g, {});
+            }
+        group.clear();
+        return rc;
+    };
+    BamRec r;
+    while (off < n_bytes) {
+        if (!parse(bam, n_bytes, off, r)) { idp::set_error("idp_bam_annotate: malformed BAM record at byte %zu", off); return IDP_ERR_ARG; }
+        const std::string name(r.name, r.l_read_name > 0 ? strnlen(r.name, (size_t)r.l_read_name) : 0);
+        if (!group.empty() && name != group_name) { int rc = flush(); if (rc) return rc; }
+        group_name = name;
+        group.push_back(r);
+    }
+    int rc = flush();
+    if (rc) return rc;
+    if (read != n_reads) { idp::set_error("idp_bam_annotate: %d results for %d reads in the BAM bytes", n_reads, read); return IDP_ERR_ARG; }
+    *out_bytes = w;
+    if (out && !fits) { idp::set_error("idp_bam_annotate: output needs %zu bytes, %zu given", w, out_cap); return IDP_ERR_ARG; }
+    return IDP_OK;
 }
 
 }  // extern "C"

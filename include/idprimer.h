@@ -212,6 +212,14 @@ int    idp_classify_templates(const idp_panel *panel, const uint16_t *flags, con
 int    idp_bam_scan(const uint8_t *bam, size_t n_bytes, int32_t *n_reads, uint64_t *seq_bytes);
 int    idp_bam_to_batch(const uint8_t *bam, size_t n_bytes, uint8_t *seq4, uint64_t *seq_off, int32_t *len, int32_t *ref_idx,
                         int32_t *unclipped_start, int32_t *unclipped_end, uint16_t *flags, int32_t *rec_index);
+/* Host egress: the records of the same bytes with the primer-match tags set as addTagsToPair / addTagsToFragment do
+ * (IP:522-569): Z-type aux fields f5 / r5 (+ f3 / r3 when --three-prime >= 0) on the primary R1 / R2 of every template, the tag
+ * strings being PrimerMatch.info / "none" (idp_format_info).  five / three are the idp_match_batch results of the batch
+ * idp_bam_to_batch made from these bytes.  Records come out in Template.allReads order; out == NULL only sizes (*out_bytes).
+ * idp_header_comments returns the three @CO lines of IP:243-250 ('\n'-separated). */
+int    idp_bam_annotate(const idp_panel *panel, const uint8_t *bam, size_t n_bytes, const idp_result *five, const idp_result *three,
+                        int32_t n_reads, uint8_t *out, size_t out_cap, size_t *out_bytes);
+int    idp_header_comments(char *buf, int32_t cap);
 /* pack ASCII bases to BAM nibbles / back (htsjdk SAMUtils.bytesToCompressedBases semantics) */
 void   idp_pack_bases(const char *ascii, int32_t n, uint8_t *seq4);
 void   idp_unpack_bases(const uint8_t *seq4, int32_t n, char *ascii);

@@ -176,6 +176,21 @@ class IdentifyPrimers {
         if (threePrime_ >= 0 && three) tags["f5"] = info(*three, f);
         return tags;
     }
+    // the records ReadBatch::fromBam was made from, with the tags written back (idp_bam_annotate)
+    std::vector<uint8_t> annotateBam(const uint8_t *bam, size_t n_bytes, const std::vector<idp_result> &five,
+                                     const std::vector<idp_result> *three = nullptr) const {
+        size_t need = 0;
+        const idp_result *t = three ? three->data() : nullptr;
+        check(idp_bam_annotate(panel_, bam, n_bytes, five.data(), t, (int32_t)five.size(), nullptr, 0, &need));
+        std::vector<uint8_t> out(need);
+        check(idp_bam_annotate(panel_, bam, n_bytes, five.data(), t, (int32_t)five.size(), out.data(), out.size(), &need));
+        return out;
+    }
+    static std::string headerComments() {  // the @CO lines of IdentifyPrimers.scala:243-250
+        char buf[2048];
+        idp_header_comments(buf, sizeof buf);
+        return buf;
+    }
     std::array<int64_t, 17> summary() const {  // IdentifyPrimersMetric, field order of the case class
         std::array<int64_t, 17> out{};
         idp_summary_metrics(metricCounter.data(), out.data());

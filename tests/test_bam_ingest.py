@@ -113,3 +113,103 @@ def test_bam_packer_rejects_malformed_input():
     with pytest.raises(idp.IdpError) as e:
         idp.ReadBatch.from_bam(only_r2)
     assert "did not have an R1" in str(e.value)            # IdentifyPrimers.scala:411
+
+
+# ---- host egress: the tags written back into the records (IdentifyPrimers.scala:522-569) ----
+
+def _aux_fields(rec_body, l_seq, n_cigar, l_name):
+    """(tag, type, value) of a record's aux area."""
+    a = 32 + l_name + 4 * n_cigar + (l_seq + 1) // 2 + l_seq
+    out = []
+    while a < len(rec_body):
+        tag, ty = rec_body[a:a + 2].decode(), chr(rec_body[a + 2])
+        a += 3
+        if ty == "Z":
+            e = rec_body.index(b"\0", a)
+            out.append((tag, ty, rec_body[a:e].decode()))
+            a = e + 1
+        else:
+            n = {"A": 1, "c": 1, "C": 1, "s": 2, "S": 2, "i": 4, "I": 4, "f": 4}[ty]
+            out.append((tag, ty, rec_body[a:a + n]))
+            a += n
+    return out
+
+
+def _records(bam):
+    off, out = 0, []
+    while off < len(bam):
+        (bs,) = struct.unpack_from("<i", bam, off)
+        body = bam[off + 4: off + 4 + bs]
+        l_name, n_cigar, flag, l_seq = body[8], struct.unpack_from("<H", body, 12)[0], struct.unpack_from("<H", body, 14)[0], struct.unpack_from("<i", body, 16)[0]
+        out.append(dict(name=body[32:32 + l_name - 1].decode(), flag=flag, body=body, aux=_aux_fields(body, l_seq, n_cigar, l_name)))
+        off += 4 + bs
+    assert off == len(bam)
+    return out
+
+
+def _rec_with_aux(name, flag, bases, aux=b"XYZhello\0NMC\x05"):
+    r = bam_record(name, flag, -1, 0, [], bases)
+    body = r[4:-4] + aux                                   # bam_record's own trailing bytes are not a well-formed field
+    return struct.pack("<i", len(body)) + body
+
+
+def _row(**kw):
+    r = np.zeros(1, dtype=L.RESULT_DTYPE)
+    r["primer"] = -1
+    for k, v in kw.items():
+        r[k] = v
+    return r[0]
+
+
+@pytest.mark.parametrize("three_prime", [-1, 3])
+def test_bam_annotate_sets_the_tags_like_addTagsToPair_and_addTagsToFragment(three_prime):
+    primers = H.primers_from(K["ipt_panel"], mapped=True)
+    tool = idp.IdentifyPrimers(primers, ref_names=H.DEFAULT_DICT, device=None, three_prime=three_prime)
+    bam = b"".join([
+        _rec_with_aux("a", 0x1 | 0x80 | 0x4, "ACGTAC"),                                # R2 arrives first
+        _rec_with_aux("a", 0x1 | 0x40 | 0x4 | 0x800, "AC"),                            # supplementary: passes through untouched
+        _rec_with_aux("a", 0x1 | 0x40 | 0x4, "ACGTACGT", aux=b"f5Zstale\0XYZhello\0"),  # R1, already carrying an f5 tag
+        _rec_with_aux("b", 0x4, "ACGTAC"),                                             # fragment
+        _rec_with_aux("c", 0x1 | 0x40 | 0x4, "ACGT"), _rec_with_aux("c", 0x1 | 0x80 | 0x4, "ACGT"),   # nothing matched
+    ])
+    batch, rec_index = idp.ReadBatch.from_bam(bam)
+    assert rec_index.tolist() == [2, 0, 3, 4, 5]
+    neg = next(i for i, p in enumerate(primers) if not p.positive_strand)
+    pos = next(i for i, p in enumerate(primers) if p.positive_strand)
+    five = np.array([_row(primer=neg, type=L.UNGAPPED, mm=1, next_mm=3),           # R1 matched a NEGATIVE primer: R2 is "forward"
+                     _row(primer=pos, type=L.LOCATION, mm=0),
+                     _row(primer=pos, type=L.GAPPED, raw_score=7, raw_next=4, q_len=10, q_len_next=10, t_start=1, t_end=10, multi=1),
+                     _row(), _row()], dtype=L.RESULT_DTYPE)
+    three = np.array([_row(), _row(primer=neg, type=L.GAPPED, raw_score=5, raw_next=0, q_len=10, q_len_next=0, t_start=2, t_end=9),
+                      _row(primer=neg, type=L.GAPPED, raw_score=6, raw_next=0, q_len=10, q_len_next=0, t_start=3, t_end=8), _row(), _row()],
+                     dtype=L.RESULT_DTYPE)
+    out = tool.annotate_bam(bam, five, three if three_prime >= 0 else None)
+    recs = _records(out)
+    assert [(r["name"], r["flag"] & 0x8C0) for r in recs] == [("a", 0x40), ("a", 0x80), ("a", 0x840), ("b", 0), ("c", 0x40), ("c", 0x80)]  # allReads order
+    want_pair = tool.pair_tags(int(batch.flags[0]), int(batch.flags[1]), five[0], five[1], three[0], three[1])
+    names = ["f5", "r5"] + (["f3", "r3"] if three_prime >= 0 else [])
+    for r in recs[:2]:
+        ours = [(t, v) for t, ty, v in r["aux"] if t in ("f5", "r5", "f3", "r3")]
+        assert ours == [(t, want_pair[t]) for t in names]
+        assert ("XY", "Z", "hello") in r["aux"] and not any(v == "stale" for _, _, v in r["aux"])
+    assert want_pair["f5"].split(",")[1] == primers[pos].primer_id and want_pair["f5"].split(",")[4] == "2"   # the forward slot is R2's match
+    assert recs[2]["aux"] == [("XY", "Z", "hello"), ("NM", "C", b"\x05")]
+    want_frag = tool.fragment_tags(int(batch.flags[2]), five[2], three[2])
+    assert [(t, v) for t, ty, v in recs[3]["aux"] if t[0] in "fr"] == [("f5", want_frag["f5"]), ("r5", "none")]
+    assert ("Gapped" in want_frag["f5"]) and (",3,8" in want_frag["f5"]) == (three_prime >= 0)    # the 3' match overwrites f5 (IP:565-568)
+    for r in recs[4:]:
+        assert [(t, v) for t, ty, v in r["aux"] if t[0] in "fr"] == [(t, "none") for t in names]
+    tool.close()
+
+
+def test_bam_annotate_rejects_mismatched_inputs_and_header_comments():
+    primers = H.primers_from(K["ipt_panel"], mapped=True)
+    tool = idp.IdentifyPrimers(primers, ref_names=H.DEFAULT_DICT, device=None)
+    bam = _rec_with_aux("b", 0x4, "ACGTAC")
+    with pytest.raises(idp.IdpError):
+        tool.annotate_bam(bam, np.zeros(2, dtype=L.RESULT_DTYPE))       # one read, two result rows
+    with pytest.raises(idp.IdpError):
+        tool.annotate_bam(bam[:-2], np.zeros(1, dtype=L.RESULT_DTYPE))
+    co = tool.header_comments()
+    assert len(co) == 3 and co[0].startswith("The f5/r5/f3/r3 tags store") and "<pair_id>,<primer_id>,<ref_name>:<start>-<end>,<strand>,<read-num>" in co[1]
+    tool.close()

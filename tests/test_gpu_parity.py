@@ -104,6 +104,39 @@ def test_ipt_two_pairs_per_read_on_gpu():  # IdentifyPrimersTest.scala:238-297
                 assert got == want, (et, rec.bases, info)
 
 
+@pytest.mark.parametrize("three_prime", [-1, 5])
+def test_bam_in_bam_out(three_prime):
+    """BAM record bytes -> idp_bam_to_batch -> GPU -> idp_bam_annotate: the records written back carry the strings
+    addTagsToPair / addTagsToFragment produce (IdentifyPrimers.scala:522-569), and the matches behind them are the oracle's."""
+    from test_bam_ingest import recs_to_bam, _records
+    primers = H.primers_from(K["ipt_panel"], mapped=True)
+    recs = H.ipt_metrics_reads(primers)
+    bam = recs_to_bam(recs)
+    opts = dict(_ipt_opts(), three_prime=three_prime)
+    gp = [idp.Primer(p.pair_id, p.primer_id, p.sequence, p.positive_strand, p.ref_name, p.start, p.end) for p in primers]
+    with idp.IdentifyPrimers(gp, ref_names=H.DEFAULT_DICT, **opts) as tool:
+        batch, _ = idp.ReadBatch.from_bam(bam)
+        five, three = tool.process_batch(batch)
+        out = _records(tool.annotate_bam(bam, five, three if three_prime >= 0 else None))
+        names = ["f5", "r5"] + (["f3", "r3"] if three_prime >= 0 else [])
+        i = k = 0
+        while i < len(batch):
+            if batch.flags[i] & H.F_MATE_NEXT:
+                tags = tool.pair_tags(int(batch.flags[i]), int(batch.flags[i + 1]), five[i], five[i + 1],
+                                      three[i] if three_prime >= 0 else None, three[i + 1] if three_prime >= 0 else None)
+                want, n = [(t, tags[t]) for t in names], 2
+            else:
+                tags = tool.fragment_tags(int(batch.flags[i]), five[i], three[i] if three_prime >= 0 else None)
+                want, n = [("f5", tags["f5"]), ("r5", "none")], 1
+            for rec in out[k:k + n]:
+                assert [(t, v) for t, ty, v in rec["aux"] if t in ("f5", "r5", "f3", "r3")] == want
+            i += n
+            k += n
+        assert k == len(out) == len(recs)
+        assert sum(1 for r in out for t, ty, v in r["aux"] if t == "f5" and v != "none") > 40
+    run_both(primers, H.recs_to_arrays(recs), **opts)
+
+
 def test_pmt_panel_location_and_ungapped_on_gpu():  # PrimerMatcherTest.scala:236-374
     primers = H.primers_from(K["pmt_panel"])
     recs = []
