@@ -15,7 +15,7 @@ K = H.kats()
 _CIGAR_OPS = "MIDNSHP=X"
 
 
-def bam_record(name, flag, ref_id, pos1, cigar, bases, next_ref=-1, next_pos1=0, tlen=0, mapq=60):
+def bam_record(name, flag, ref_id, pos1, cigar, bases, next_ref=-1, next_pos1=0, tlen=0, mapq=60, aux=b"XYZq\0"):
     """One BAM alignment record (block_size-prefixed).  cigar: [(op_char, len)], pos1 / next_pos1 are 1-based."""
     seq = bytearray((len(bases) + 1) // 2)
     lib = L.lib()
@@ -24,7 +24,7 @@ def bam_record(name, flag, ref_id, pos1, cigar, bases, next_ref=-1, next_pos1=0,
     qname = name.encode() + b"\0"
     cig = b"".join(struct.pack("<I", (n << 4) | _CIGAR_OPS.index(op)) for op, n in cigar)
     body = struct.pack("<iiBBHHHiiii", ref_id, pos1 - 1, len(qname), mapq, 0, len(cigar), flag, len(bases), next_ref, next_pos1 - 1, tlen)
-    body += qname + cig + arr.tobytes() + bytes([30] * len(bases)) + b"XYZ\x05"   # one tag, to be skipped
+    body += qname + cig + arr.tobytes() + bytes([30] * len(bases)) + aux   # one tag by default, skipped by the ingest
     return struct.pack("<i", len(body)) + body
 
 
@@ -148,9 +148,7 @@ def _records(bam):
 
 
 def _rec_with_aux(name, flag, bases, aux=b"XYZhello\0NMC\x05"):
-    r = bam_record(name, flag, -1, 0, [], bases)
-    body = r[4:-4] + aux                                   # bam_record's own trailing bytes are not a well-formed field
-    return struct.pack("<i", len(body)) + body
+    return bam_record(name, flag, -1, 0, [], bases, aux=aux)
 
 
 def _row(**kw):
