@@ -178,8 +178,22 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the IdentifyPrimers GPU path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("IDP_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # keep stdout to the one JSON line: the NCCL banner ("NCCL version ...") is written to fd 1 by the library when the
+        # communicator comes up, so fd 1 points at stderr until the first collective has run
+        if "IDP_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["IDP_NCCL_DEBUG"]
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device=torch.device("cuda", local))
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     dev = torch.device("cuda", local)
 
     # ---- synthetic batch, generated in chunks straight into pinned host memory ----
