@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libidprimer_b200.so")
 SOURCES = ["idp_panel.cpp", "idp_bam.cpp", "idp_ctx.cu"]
-HEADERS = ["idp_internal.h", "idp_kernels.cuh", os.path.join("..", "..", "include", "idprimer.h")]
+HEADERS = ["idp_internal.h", "idp_kernels.cuh", "idp_scan.cuh", os.path.join("..", "..", "include", "idprimer.h")]
 
 
 def stale() -> bool:

@@ -75,7 +75,7 @@ struct idp_ctx {
     int device = 0, sm_count = 148;
     DevPanel dp{};
     DevBuf b_qbot, b_bylen, b_pmask, b_pinfo, b_positive, b_loc_key[2], b_loc_primer[2], b_mate_off, b_mate_idx, b_smat;
-    DevBuf b_keys[2], b_offcnt[2], b_postings[2], b_heads[2], b_direct[2], b_bsmm, b_bsacc, b_seedtab, b_seedlist;
+    DevBuf b_keys[2], b_offcnt[2], b_postings[2], b_heads[2], b_direct[2], b_bsmm, b_bsacc, b_seedtab, b_seedlist, b_diag;
     Slot slots[kSlots];
     cudaStream_t user_stream = nullptr;
     idp_timings last{};
@@ -129,6 +129,27 @@ static int upload_panel(idp_ctx *c) {
     if ((rc = upload(p.bs_mm, c->b_bsmm)) || (rc = upload(p.bs_acc, c->b_bsacc))) return rc;
     d.bs_mm = c->b_bsmm.as<uint32_t>(); d.bs_acc = c->b_bsacc.as<uint2>(); d.bs_groups = (int)(p.bs_acc.size() / 2);
     d.bs_ok = p.acc_max <= 1 && p.window_bases <= 64;
+    d.diag = nullptr;
+    if (d.bs_ok && p.kidx[0].k > 0 && p.ww <= 4) {
+        // a position holding one of A/C/G/T that the read matches carries the same letter in the read (PM:143 on one-bit
+        // masks), so the literally equal positions are the non-degenerate ones minus the mismatch position
+        const int k = p.kidx[0].k;
+        std::vector<uint2> diag(p.n);
+        for (int i = 0; i < p.n; ++i) {
+            const int L = std::min(p.max_primer_length, p.seq_len[i]);  // the k-mer window (PM:110) inside the primer
+            uint32_t plain = 0;
+            for (int b = 0; b < L && b < 32; ++b) {
+                const uint32_t code = (p.pmask[(size_t)i * p.ww + b / 8] >> (4 * (b % 8))) & 15u;
+                if (__builtin_popcount(code) == 1) plain |= 1u << b;
+            }
+            auto has_run = [&](uint32_t e) { uint32_t r = e; for (int t = 1; t < k; ++t) r &= e >> t; return k <= 32 && r != 0u; };
+            uint32_t ok = 0;
+            for (int b = 0; b < 32; ++b) if (has_run(plain & ~(1u << b))) ok |= 1u << (4 * (b % 8) + b / 8);
+            diag[i] = make_uint2(ok, has_run(plain) ? 1u : 0u);
+        }
+        if ((rc = upload(diag, c->b_diag))) return rc;
+        d.diag = c->b_diag.as<uint2>();
+    }
     d.seed_ok = 0; d.seed_tab = nullptr; d.seed_list = nullptr; d.seed_S = 0; d.seed_shift = 0; d.seed_slots = 0;
     // panels of up to 8 x 32 primers are scanned faster by the unrolled bit-sliced filter (measured on c2: 0.36 vs 0.43 ms per 8 M reads)
     const bool want_seed = getenv("IDP_SCAN_SEED") ? atoi(getenv("IDP_SCAN_SEED")) != 0 : d.bs_groups > 8;
@@ -219,6 +240,7 @@ static int launch_scan_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, i
     S.off_bsmm = place((size_t)c->dp.bs_groups * kBsStride * 16 * 4, FAST, 64);  // 64-byte aligned: table offsets are OR-ed in
     S.off_seed = place((size_t)c->dp.seed_slots * 2 * 4, FAST && c->dp.seed_ok && c->dp.seed_slots <= 2048);
     S.off_direct = place((size_t)S.direct_entries * 4, !FAST && ix.direct != nullptr);
+    S.off_diag = place((size_t)c->dp.n_primers * sizeof(uint2), FAST && c->dp.diag != nullptr);
     S.off_pinfo = place((size_t)c->dp.n_primers * sizeof(int4), true);
     S.off_pmask = place((size_t)c->dp.n_primers * c->dp.ww * 4, true);
     S.off_heads = place((size_t)ix.n_postings * 8, !FAST && ix.k > 0);

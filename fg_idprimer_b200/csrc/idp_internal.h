@@ -58,6 +58,11 @@ struct DevPanel {
     const uint2 *bs_acc;
     int32_t bs_groups;
     int32_t bs_ok;             // every primer accepts at most one mismatch, so two bit planes decide the filter
+    // k-mer rule shortcut for a primer accepted with at most one mismatch by a read that covers the whole window: a run
+    // of k literally equal letters exists iff a run of k non-degenerate primer letters avoids the mismatch position, which
+    // depends on the primer alone.  diag[p] = {bit 4*(pos%8)+pos/8: such a run exists when the mismatch sits at pos,
+    // non-zero: such a run exists with no mismatch}; NULL when primers are longer than 32 bases or -k is off
+    const uint2 *diag;
     // seed index over the first 2*S read bases (pigeonhole: at most one mismatch => one of the two S-base seeds matches a
     // primer exactly).  seed_tab[t * seed_slots + hash(seed t)] = count | (primer or offset into seed_list) << 8; the table
     // holds every read spelling (non-empty submasks of the IUPAC codes) a primer's seed matches without a mismatch

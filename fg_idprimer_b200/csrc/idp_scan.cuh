@@ -32,7 +32,7 @@ struct ScanLaunch {
     int32_t stage_flags;       // 1: the tile's flag words ride along (16-byte aligned flags array), at flags_off in the tile buffer
     uint32_t flags_off;
     // byte offsets into dynamic shared memory, or 0xFFFFFFFF when the structure stays in global memory
-    uint32_t off_direct, off_heads, off_pmask, off_pinfo, off_bsmm, off_bsacc, off_seed;
+    uint32_t off_direct, off_heads, off_pmask, off_pinfo, off_bsmm, off_bsacc, off_seed, off_diag;
     uint32_t direct_entries;
 };
 
@@ -77,14 +77,21 @@ struct ScanCtx {
 };
 
 // numMismatches + mismatchAlign (PM:128-147).  Returns true and mm when the rate test passes.
+// where: the mismatch flags of the first four words folded into one word, bit 4*(pos%8) + pos/8 (see DevPanel::diag)
 template <int RW>
-__device__ __forceinline__ bool mismatch_align(const DevPanel &P, ScanCtx<RW> &c, int p, int &mm_out, int &plen_out) {
+__device__ __forceinline__ bool mismatch_align(const DevPanel &P, ScanCtx<RW> &c, int p, int &mm_out, int &plen_out, uint32_t *where = nullptr) {
     const int4 info = c.pinfo[p];  // {Primer.length, cap, accept, sequence.length}
     const uint32_t *pm = c.pmask + (size_t)p * P.ww;
     int total = 0;
+    uint32_t folded = 0;
 #pragma unroll
     for (int w = 0; w < RW; ++w)
-        if (w < P.ww) total += __popc(nib_nonzero(c.win[w] & ~pm[w]));  // read mask not a subset of primer mask (PM:143)
+        if (w < P.ww) {
+            const uint32_t z = nib_nonzero(c.win[w] & ~pm[w]);  // read mask not a subset of primer mask (PM:143)
+            total += __popc(z);
+            if (w < 4) folded |= z << w;
+        }
+    if (where != nullptr) *where = folded;
     c.compares += (unsigned)min(c.len, info.w);
     plen_out = info.x;
     if (c.len >= info.x) {
@@ -339,6 +346,12 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
         for (int i = tid; i < P.bs_groups; i += blockDim.x) d[i] = P.bs_acc[i];
         bs_acc = d;
     }
+    const uint2 *diag = P.diag;
+    if (FAST && P.diag != nullptr && S.off_diag != 0xFFFFFFFFu) {
+        uint2 *d = reinterpret_cast<uint2 *>(smem + S.off_diag);
+        for (int i = tid; i < P.n_primers; i += blockDim.x) d[i] = P.diag[i];
+        diag = d;
+    }
     const uint32_t *seed_tab = P.seed_tab;
     if (FAST && P.seed_ok && S.off_seed != 0xFFFFFFFFu) {
         uint32_t *d = reinterpret_cast<uint32_t *>(smem + S.off_seed);
@@ -371,8 +384,9 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
             if (bulk) tma_load_1d(wbuf(b), R.seq4 + g0, bulk, &tile_bar[wib][b]);
             if (fbulk) tma_load_1d(wbuf(b) + S.flags_off, R.flags + (size_t)wt * 32, fbulk, &tile_bar[wib][b]);
         }
-        if (lane < (int)(bytes - bulk)) wbuf(b)[bulk + lane] = R.seq4[g0 + bulk + lane];
-        if (2u * lane >= fbulk && 2u * lane < fbytes) reinterpret_cast<uint16_t *>(wbuf(b) + S.flags_off)[lane] = R.flags[(size_t)wt * 32 + lane];
+        if (bytes != bulk && lane < (int)(bytes - bulk)) wbuf(b)[bulk + lane] = R.seq4[g0 + bulk + lane];  // only the last tile has tails
+        if (fbytes != fbulk && 2u * lane >= fbulk && 2u * lane < fbytes)
+            reinterpret_cast<uint16_t *>(wbuf(b) + S.flags_off)[lane] = R.flags[(size_t)wt * 32 + lane];
     };
     int cur = 0;
     const int wt0 = blockIdx.x * kScanWarps + wib;
@@ -477,12 +491,14 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
                 if (FAST) {
                     // survivors of the 16-base bit-sliced filter, ascending primer index (file order)
                     int n_acc = 0, a_p = -1, a_mm = 0, a_plen = 1, a_seq = 0;
+                    uint32_t a_where = 0;
                     int q0 = -1, q1 = -1, q2 = -1, q3 = -1;
                     auto evaluate = [&](int p) {
                         int mm, plen;
-                        if (mismatch_align<RW>(P, c, p, mm, plen)) {
+                        uint32_t where;
+                        if (mismatch_align<RW>(P, c, p, mm, plen, &where)) {
                             if (ix.k <= 0) best.offer(p, mm, __ddiv_rn((double)mm, (double)plen));  // PM:100: file order
-                            else if (n_acc == 0) { a_p = p; a_mm = mm; a_plen = plen; a_seq = c.pinfo[p].w; }
+                            else if (n_acc == 0) { a_p = p; a_mm = mm; a_plen = plen; a_seq = c.pinfo[p].w; a_where = where; }
                             ++n_acc;
                         }
                     };
@@ -540,7 +556,19 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
                     if (ix.k > 0) {
                         if (n_acc == 1) {
                             const int n_bases = min(ix.window, c.len);
-                            if (diagonal_kmer<RW>(P, c, a_p, a_seq, ix.k, n_bases) || member_exact(a_p))
+                            bool proved;
+                            // a window without a zero code lies inside the read and spells every matched A/C/G/T
+                            // primer letter literally; the table then knows whether a k-run avoids the one mismatch
+                            bool full = diag != nullptr && (a_where & (a_where - 1u)) == 0u;
+#pragma unroll
+                            for (int w = 0; w < RW; ++w) full = full && (((c.win[w] - 0x11111111u) & ~c.win[w] & 0x88888888u) == 0u);
+                            if (full) {
+                                const uint2 d = diag[a_p];
+                                proved = a_where ? ((d.x >> (__ffs((int)a_where) - 1)) & 1u) != 0u : d.y != 0u;
+                            } else {
+                                proved = diagonal_kmer<RW>(P, c, a_p, a_seq, ix.k, n_bases);
+                            }
+                            if (proved || member_exact(a_p))
                                 best.offer(a_p, a_mm, 0.0);  // the only accepted candidate: its sort key is never compared
                         } else if (n_acc >= 2) {
                             scan_exact(ix.direct, ix.heads);  // ties: the reference's candidate order decides
