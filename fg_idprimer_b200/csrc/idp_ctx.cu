@@ -54,7 +54,7 @@ struct Slot {
     // staging for the host-pointer path
     DevBuf seq4, seq_off, len, ref_idx, ustart, uend, flags, five, three;
     // scratch of the chain
-    DevBuf fall, spill, all_list, seg_off, seg_cnt, pair_work, pair_primer, pair_score, pair_se, fin;
+    DevBuf fall, rtype, spill, all_list, seg_off, seg_cnt, pair_work, pair_primer, pair_score, pair_se, fin;
     Counters *d_ctr = nullptr, *h_ctr = nullptr;
     size_t pair_cap = 0;
     bool busy = false;
@@ -210,7 +210,7 @@ static int upload_panel(idp_ctx *c) {
 }
 
 template <int RW, bool FAST>
-static int launch_scan_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp_result *five, unsigned *fall, Counters *ctr) {
+static int launch_scan_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp_result *five, uint8_t *rtype, unsigned *fall, Counters *ctr) {
     // shared-memory plan: the per-warp read tiles first (two buffers each), then as much of the panel side as fits in half
     // an SM (two CTAs per SM)
     ScanLaunch S{};
@@ -237,7 +237,7 @@ static int launch_scan_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, i
     };
     S.direct_entries = ix.direct ? (1u << (2 * ix.k)) : 0;
     S.off_bsacc = place((size_t)c->dp.bs_groups * sizeof(uint2), FAST);
-    S.off_bsmm = place((size_t)c->dp.bs_groups * kBsStride * 16 * 4, FAST, 64);  // 64-byte aligned: table offsets are OR-ed in
+    S.off_bsmm = place((size_t)c->dp.bs_groups * kBsStride * 16 * 4, FAST, 128);  // 128-byte aligned: table offsets are OR-ed in
     S.off_seed = place((size_t)c->dp.seed_slots * 2 * 4, FAST && c->dp.seed_ok && c->dp.seed_slots <= 2048);
     S.off_direct = place((size_t)S.direct_entries * 4, !FAST && ix.direct != nullptr);
     S.off_diag = place((size_t)c->dp.n_primers * sizeof(uint2), FAST && c->dp.diag != nullptr);
@@ -252,16 +252,16 @@ static int launch_scan_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, i
             set_error("cudaFuncSetAttribute(scan_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
             return IDP_ERR_CUDA;
         }
-        kernel<<<grid, kScanThreads, used, st>>>(c->dp, R, S, five, fall, ctr);
+        kernel<<<grid, kScanThreads, used, st>>>(c->dp, R, S, five, rtype, fall, ctr);
         return IDP_OK;
     };
     if (FAST && onchip) return launch(scan_kernel<RW, FAST, FAST>);
     return launch(scan_kernel<RW, FAST, false>);
 }
 template <int RW>
-static int launch_scan(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp_result *five, unsigned *fall, Counters *ctr) {
-    if (RW <= 8 && c->dp.bs_ok && !getenv("IDP_SCAN_EXACT_WALK")) return launch_scan_t<(RW <= 8 ? RW : 8), true>(c, st, R, five, fall, ctr);
-    return launch_scan_t<RW, false>(c, st, R, five, fall, ctr);
+static int launch_scan(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp_result *five, uint8_t *rtype, unsigned *fall, Counters *ctr) {
+    if (RW <= 8 && c->dp.bs_ok && !getenv("IDP_SCAN_EXACT_WALK")) return launch_scan_t<(RW <= 8 ? RW : 8), true>(c, st, R, five, rtype, fall, ctr);
+    return launch_scan_t<RW, false>(c, st, R, five, rtype, fall, ctr);
 }
 
 // the pair kernel also produces the traceback-equivalent (start, end) when the packed register variant applies
@@ -316,18 +316,18 @@ static void launch_sw_all(const idp_ctx *c, cudaStream_t st, bool local, const D
 
 static void launch_finalize_pairs(const idp_ctx *c, cudaStream_t st, const DevReads &R, const unsigned *work_read, const unsigned *n_work_ptr,
                                   unsigned n_work_fixed, const unsigned *seg_off, const int *seg_cnt, const unsigned *pp, const int *ps,
-                                  const unsigned *pse, idp_result *out, Counters *ctr, int three) {
+                                  const unsigned *pse, idp_result *out, uint8_t *rtype, Counters *ctr, int three) {
     const int grid = c->sm_count * 8;
     if (!pairs_trace(c)) pse = nullptr;
-    if (c->dp.max_seq_len <= 64) finalize_pairs_kernel<64, 0><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, n_work_fixed, seg_off, seg_cnt, pp, ps, pse, out, ctr, three);
-    else finalize_pairs_kernel<kMaxPrimerBases, 0><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, n_work_fixed, seg_off, seg_cnt, pp, ps, pse, out, ctr, three);
+    if (c->dp.max_seq_len <= 64) finalize_pairs_kernel<64, 0><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, n_work_fixed, seg_off, seg_cnt, pp, ps, pse, out, rtype, ctr, three);
+    else finalize_pairs_kernel<kMaxPrimerBases, 0><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, n_work_fixed, seg_off, seg_cnt, pp, ps, pse, out, rtype, ctr, three);
 }
 static void launch_finalize_all(const idp_ctx *c, cudaStream_t st, const DevReads &R, const unsigned *work_read, const unsigned *n_work_ptr,
-                                const Fin *fin, idp_result *out, int three) {
+                                const Fin *fin, idp_result *out, uint8_t *rtype, int three) {
     const int grid = c->sm_count * 8;
-    if (c->nq == 32) finalize_all_kernel<64, 32><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, three);
-    else if (c->nq == 64) finalize_all_kernel<64, 64><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, three);
-    else finalize_all_kernel<kMaxPrimerBases, 0><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, three);
+    if (c->nq == 32) finalize_all_kernel<64, 32><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, rtype, three);
+    else if (c->nq == 64) finalize_all_kernel<64, 64><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, rtype, three);
+    else finalize_all_kernel<kMaxPrimerBases, 0><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, rtype, three);
 }
 
 // Enqueue the whole matcher chain for reads already on the device.  Nothing here waits on the host.
@@ -345,18 +345,20 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
     }
     if (!k_gapped || do3) { if ((rc = s.fin.ensure(n * sizeof(Fin)))) return rc; }
     if (do3) { if ((rc = s.all_list.ensure(n * 4))) return rc; }
+    if ((rc = s.rtype.ensure(n))) return rc;
     Counters *ctr = s.d_ctr;
     unsigned *fall = s.fall.as<unsigned>();
+    uint8_t *rtype = s.rtype.as<uint8_t>();
     s.launches = 0;
     CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(Counters), st));
     CUDA_TRY(cudaEventRecord(s.ev[EV_START], st));
     if (n > 0) {
         switch (c->rw) {
-            case 4: rc = launch_scan<4>(c, st, R, five, fall, ctr); break;
-            case 5: rc = launch_scan<5>(c, st, R, five, fall, ctr); break;
-            case 8: rc = launch_scan<8>(c, st, R, five, fall, ctr); break;
-            case 16: rc = launch_scan<16>(c, st, R, five, fall, ctr); break;
-            default: rc = launch_scan<32>(c, st, R, five, fall, ctr); break;
+            case 4: rc = launch_scan<4>(c, st, R, five, rtype, fall, ctr); break;
+            case 5: rc = launch_scan<5>(c, st, R, five, rtype, fall, ctr); break;
+            case 8: rc = launch_scan<8>(c, st, R, five, rtype, fall, ctr); break;
+            case 16: rc = launch_scan<16>(c, st, R, five, rtype, fall, ctr); break;
+            default: rc = launch_scan<32>(c, st, R, five, rtype, fall, ctr); break;
         }
         if (rc) return rc;
         ++s.launches;
@@ -376,13 +378,13 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
             launch_sw_pairs(c, st, false, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), (unsigned)s.pair_cap);
             CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st));
             launch_finalize_pairs(c, st, R, fall, &ctr->n_fall, 0u, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(),
-                                  s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), five, ctr, 0);
+                                  s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), five, rtype, ctr, 0);
             s.launches += 3;
         } else {
             CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st));
             launch_sw_all(c, st, false, R, fall, &ctr->n_fall, s.fin.as<Fin>(), ctr, 1);
             CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st));
-            launch_finalize_all(c, st, R, fall, &ctr->n_fall, s.fin.as<Fin>(), five, 0);
+            launch_finalize_all(c, st, R, fall, &ctr->n_fall, s.fin.as<Fin>(), five, rtype, 0);
             s.launches += 2;
         }
     } else { CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st)); CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st)); }
@@ -397,12 +399,12 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
         launch_sw_all(c, st, true, R, s.all_list.as<unsigned>(), &ctr->n_all, s.fin.as<Fin>(), ctr, 0);
         CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_B], st));
         launch_finalize_pairs(c, st, R, nullptr, nullptr, (unsigned)R.n, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(),
-                              s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), three, ctr, 1);
-        launch_finalize_all(c, st, R, s.all_list.as<unsigned>(), &ctr->n_all, s.fin.as<Fin>(), three, 1);
+                              s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), three, nullptr, ctr, 1);
+        launch_finalize_all(c, st, R, s.all_list.as<unsigned>(), &ctr->n_all, s.fin.as<Fin>(), three, nullptr, 1);
         s.launches += 5;
     } else { CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_A], st)); CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_B], st)); }
     CUDA_TRY(cudaEventRecord(s.ev[EV_THREE], st));
-    if (n > 0) { metrics_kernel<<<std::min<int>((R.n + 255) / 256, c->sm_count * 8), 256, 0, st>>>(R, five, ctr); ++s.launches; }
+    if (n > 0) { metrics_kernel<<<std::min<int>((R.n + 255) / 256, c->sm_count * 8), 256, 0, st>>>(R, rtype, ctr); ++s.launches; }
     CUDA_TRY(cudaMemcpyAsync(s.h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(s.ev[EV_END], st));
     CUDA_TRY(cudaGetLastError());
@@ -473,7 +475,7 @@ void idp_ctx_destroy(idp_ctx *c) {
     cudaDeviceSynchronize();
     for (Slot &s : c->slots) {
         for (DevBuf *b : {&s.seq4, &s.seq_off, &s.len, &s.ref_idx, &s.ustart, &s.uend, &s.flags, &s.five, &s.three, &s.fall, &s.spill, &s.all_list,
-                          &s.seg_off, &s.seg_cnt, &s.pair_work, &s.pair_primer, &s.pair_score, &s.pair_se, &s.fin}) b->release();
+                          &s.seg_off, &s.seg_cnt, &s.pair_work, &s.pair_primer, &s.pair_score, &s.pair_se, &s.fin, &s.rtype}) b->release();
         if (s.d_ctr) cudaFree(s.d_ctr);
         if (s.h_ctr) cudaFreeHost(s.h_ctr);
         for (auto &e : s.ev) if (e) cudaEventDestroy(e);
@@ -481,7 +483,7 @@ void idp_ctx_destroy(idp_ctx *c) {
     }
     for (DevBuf *b : {&c->b_qbot, &c->b_bylen, &c->b_pmask, &c->b_pinfo, &c->b_positive, &c->b_loc_key[0], &c->b_loc_key[1], &c->b_loc_primer[0], &c->b_loc_primer[1],
                       &c->b_mate_off, &c->b_mate_idx, &c->b_smat, &c->b_keys[0], &c->b_keys[1], &c->b_offcnt[0], &c->b_offcnt[1],
-                      &c->b_postings[0], &c->b_postings[1], &c->b_heads[0], &c->b_heads[1], &c->b_direct[0], &c->b_direct[1], &c->b_bsmm, &c->b_bsacc, &c->b_seedtab, &c->b_seedlist}) b->release();
+                      &c->b_postings[0], &c->b_postings[1], &c->b_heads[0], &c->b_heads[1], &c->b_direct[0], &c->b_direct[1], &c->b_bsmm, &c->b_bsacc, &c->b_seedtab, &c->b_seedlist, &c->b_diag}) b->release();
     delete c;
 }
 

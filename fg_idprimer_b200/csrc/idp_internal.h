@@ -52,8 +52,9 @@ struct DevPanel {
     const int32_t *loc_primer[2];
     int32_t n_loc[2];
     DevKmerIndex kidx[2];      // 0: ungapped matcher (-k), 1: gapped matcher (-K)
-    // bit-sliced ungapped filter: primers in groups of 32 (file order); bs_mm[(g*16 + i)*16 + nib] has bit b set when read
-    // code `nib` at position i mismatches primer 32g+b (PM:143); bs_acc[g] = {primers accepting >= 0 mismatches, >= 1 mismatch}
+    // bit-sliced ungapped filter: primers in groups of 32 (file order); bs_mm[(((g/2)*16 + i)*16 + nib)*2 + (g&1)] has bit b
+    // set when read code `nib` at position i mismatches primer 32g+b (PM:143) -- two groups side by side, so one 64-bit
+    // load serves both; bs_acc[g] = {primers accepting >= 0 mismatches, >= 1 mismatch}
     const uint32_t *bs_mm;
     const uint2 *bs_acc;
     int32_t bs_groups;

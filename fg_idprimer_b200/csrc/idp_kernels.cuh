@@ -1118,7 +1118,7 @@ __device__ Traced sw_trace(const DevPanel &P, const uint32_t *__restrict__ qword
 // NQ > 0 selects the register-resident re-alignment, otherwise the generic one with TN rows in local memory.
 template <int TN, int NQ>
 __device__ void finish_gapped(const DevPanel &P, const DevReads &R, int r, const Fin &f, bool three_prime, const TracedReg *pre,
-                              idp_result *__restrict__ out) {
+                              idp_result *__restrict__ out, uint8_t *__restrict__ rtype) {
     idp_result res = none_result();
     if (f.count > 0) {
         if (f.raw == kScoreMissing) res.status = IDP_STATUS_SCORE_MISSING;
@@ -1152,6 +1152,7 @@ __device__ void finish_gapped(const DevPanel &P, const DevReads &R, int r, const
         }
     }
     write_result(&out[r], res);
+    if (rtype != nullptr && res.type != IDP_NONE) rtype[r] = res.type;  // the scan kernel left IDP_NONE there
 }
 
 // pair mode: one thread per work item picks the best two of its segment, then finishes
@@ -1161,7 +1162,7 @@ __global__ void __launch_bounds__(128) finalize_pairs_kernel(DevPanel P, DevRead
                                                              const unsigned int *__restrict__ seg_off, const int *__restrict__ seg_cnt,
                                                              const unsigned int *__restrict__ pair_primer, const int *__restrict__ pair_score,
                                                              const unsigned int *__restrict__ pair_se, idp_result *__restrict__ out,
-                                                             Counters *__restrict__ ctr_out, int three_prime) {
+                                                             uint8_t *__restrict__ rtype, Counters *__restrict__ ctr_out, int three_prime) {
     const unsigned n_work = n_work_ptr ? *n_work_ptr : n_work_fixed;
     unsigned long long aligned = 0;
     for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
@@ -1185,7 +1186,7 @@ __global__ void __launch_bounds__(128) finalize_pairs_kernel(DevPanel P, DevRead
             aligned += (unsigned)cnt;
             if (pair_se) { const unsigned se = pair_se[o + g.b_ord]; pre.score = g.b_score; pre.t_start = (int)(se & 0xFFFFu); pre.t_end = (int)(se >> 16); }
         }
-        finish_gapped<TN, NQ>(P, R, r, f, three_prime != 0, pair_se ? &pre : nullptr, out);
+        finish_gapped<TN, NQ>(P, R, r, f, three_prime != 0, pair_se ? &pre : nullptr, out, rtype);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) aligned += __shfl_xor_sync(0xffffffffu, aligned, d);
@@ -1196,33 +1197,39 @@ __global__ void __launch_bounds__(128) finalize_pairs_kernel(DevPanel P, DevRead
 template <int TN, int NQ>
 __global__ void __launch_bounds__(128) finalize_all_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
                                                            const unsigned int *__restrict__ n_work_ptr, const Fin *__restrict__ fin,
-                                                           idp_result *__restrict__ out, int three_prime) {
+                                                           idp_result *__restrict__ out, uint8_t *__restrict__ rtype, int three_prime) {
     const unsigned n_work = *n_work_ptr;
     for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x)
-        finish_gapped<TN, NQ>(P, R, (int)work_read[w], fin[w], three_prime != 0, nullptr, out);
+        finish_gapped<TN, NQ>(P, R, (int)work_read[w], fin[w], three_prime != 0, nullptr, out, rtype);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// TemplateTypeMetric counter (IP:413; TemplateType.scala:52-63): one thread per read, R1 of each template counts
+// TemplateTypeMetric counter (IP:413; TemplateType.scala:52-63): one thread per read, R1 of each template counts.
+// Reads the one-byte match type per read that the scan and finalize kernels keep next to the 32-byte results.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) metrics_kernel(DevReads R, const idp_result *__restrict__ five, Counters *__restrict__ ctr) {
+__global__ void __launch_bounds__(256) metrics_kernel(DevReads R, const uint8_t *__restrict__ rtype, Counters *__restrict__ ctr) {
     __shared__ unsigned int hist[160];
     for (int i = threadIdx.x; i < 160; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R.n; r += gridDim.x * blockDim.x) {
-        const uint16_t fl = R.flags[r];
-        if (r > 0 && (R.flags[r - 1] & IDP_F_MATE_NEXT)) continue;  // this read is an R2
-        const bool has_r2 = (fl & IDP_F_MATE_NEXT) && r + 1 < R.n;
-        const bool m1 = !(fl & IDP_F_UNMAPPED);
-        int tt, t2 = IDP_NONE;
-        if (!has_r2) tt = m1 ? 3 : 4;
-        else {
-            const bool m2 = !(R.flags[r + 1] & IDP_F_UNMAPPED);
-            tt = (m1 && m2) ? 0 : (m1 != m2 ? 1 : 2);
-            t2 = five[r + 1].type;
+    for (int base = blockIdx.x * blockDim.x; base < R.n; base += gridDim.x * blockDim.x) {
+        const int r = base + (int)threadIdx.x;
+        int bin = -1;
+        if (r < R.n && !(r > 0 && (R.flags[r - 1] & IDP_F_MATE_NEXT))) {  // not an R2
+            const uint16_t fl = R.flags[r];
+            const bool has_r2 = (fl & IDP_F_MATE_NEXT) && r + 1 < R.n;
+            const bool m1 = !(fl & IDP_F_UNMAPPED);
+            int tt, t2 = IDP_NONE;
+            if (!has_r2) tt = m1 ? 3 : 4;
+            else {
+                const bool m2 = !(R.flags[r + 1] & IDP_F_UNMAPPED);
+                tt = (m1 && m2) ? 0 : (m1 != m2 ? 1 : 2);
+                t2 = rtype[r + 1];
+            }
+            bin = ((tt * 2 + ((fl & IDP_F_FR_PAIR) ? 1 : 0)) * 4 + rtype[r]) * 4 + t2;
         }
-        const int bin = ((tt * 2 + ((fl & IDP_F_FR_PAIR) ? 1 : 0)) * 4 + five[r].type) * 4 + t2;
-        atomicAdd(&hist[bin], 1u);
+        // most templates of a batch land in a handful of bins: one shared-memory atomic per distinct bin of the warp
+        const unsigned same = __match_any_sync(0xffffffffu, bin);
+        if (bin >= 0 && (int)(threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&hist[bin], (unsigned)__popc(same));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 160; i += blockDim.x) if (hist[i]) atomicAdd(&ctr->metrics[i], (unsigned long long)hist[i]);

@@ -319,7 +319,7 @@ int idp_panel_create(const idp_primer *primers, int32_t n, const idp_params *par
             for (int pos = 0; pos < 16; ++pos) {
                 const uint32_t mask = pos < p->seq_len[i] ? (uint32_t)base_to_nibble((unsigned char)p->sequence[i][pos]) : 0xFu;
                 for (uint32_t nib = 0; nib < 16; ++nib)
-                    if (nib & ~mask) p->bs_mm[((size_t)g * 16 + pos) * 16 + nib] |= 1u << b;
+                    if (nib & ~mask) p->bs_mm[((((size_t)(g / 2) * 16 + pos) * 16 + nib) << 1) + (g & 1)] |= 1u << b;  // group pairs interleaved
             }
         }
     }

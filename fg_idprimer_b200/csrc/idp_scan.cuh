@@ -227,10 +227,11 @@ __device__ __forceinline__ void static_for_impl(std::integer_sequence<int, I...>
 template <int N, class F>
 __device__ __forceinline__ void static_for(F &&f) { static_for_impl(std::make_integer_sequence<int, N>{}, f); }
 
-// The bit-sliced filter for a compile-time number of 32-primer groups, tables in shared memory at a 64-byte aligned address
-// `tab`.  The per-position table offsets (nibble * 4, OR-ed into the aligned base) are formed once per read; every lookup is
-// then one LDS with an immediate offset and the two bit planes cost two LOP3.  Reports the number of survivors and the first
-// one (lowest primer index); the caller re-runs the general loop only when a read has more than one survivor.
+// The bit-sliced filter for a compile-time number of 32-primer groups, tables in shared memory at a 128-byte aligned address
+// `tab`.  The per-position table offsets (nibble * 8, OR-ed into the aligned base) are formed once per read; every lookup is
+// then one 64-bit LDS with an immediate offset that serves two groups, and the two bit planes of a group cost two LOP3.
+// Reports the number of survivors and the first one (lowest primer index); the caller re-runs the general loop only when a
+// read has more than one survivor.
 template <int G, int RW>
 __device__ __forceinline__ void bs_filter_fixed(uint32_t tab, uint32_t acc, const uint32_t *win, int &n_surv, uint32_t &first_word, int &first_group) {
     uint32_t o[kBsPositions];
@@ -238,25 +239,32 @@ __device__ __forceinline__ void bs_filter_fixed(uint32_t tab, uint32_t acc, cons
     for (int i = 0; i < kBsPositions; ++i) {
         const uint32_t w = win[(i >> 3) < RW ? (i >> 3) : 0];
         const int s = 4 * (i & 7);
-        o[i] = ((s == 0 ? (w << 2) : (w >> (s - 2))) & 0x3Cu) | tab;
+        o[i] = ((s < 3 ? (w << (3 - s)) : (w >> (s - 3))) & 0x78u) | tab;
     }
-    static_for<G>([&](auto gc) {
-        constexpr int g = decltype(gc)::value;
-        uint32_t ones = 0, twos = 0;
+    static_for<G / 2>([&](auto gc) {
+        constexpr int gp = decltype(gc)::value;
+        uint32_t ones0 = 0, twos0 = 0, ones1 = 0, twos1 = 0;
         static_for<kBsPositions>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
-            uint32_t v;
-            asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(o[i]), "n"((g * kBsStride + i) * 64));
-            twos |= ones & v;
-            ones |= v;
+            uint32_t v0, v1;
+            asm("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v0), "=r"(v1) : "r"(o[i]), "n"((gp * kBsStride + i) * 128));
+            twos0 |= ones0 & v0;
+            ones0 |= v0;
+            twos1 |= ones1 & v1;
+            ones1 |= v1;
         });
-        uint32_t ax, ay;
-        asm("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(ax), "=r"(ay) : "r"(acc), "n"(g * 8));
-        const uint32_t surv = ax & ~twos & (~ones | ay);  // at most acc (0 or 1) mismatches in the positions looked at
-        const bool first = surv != 0u && n_surv == 0;
-        first_word = first ? surv : first_word;
-        first_group = first ? g : first_group;
-        n_surv += __popc(surv);
+        uint32_t ax0, ay0, ax1, ay1;
+        asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(ax0), "=r"(ay0), "=r"(ax1), "=r"(ay1) : "r"(acc), "n"(gp * 16));
+        // at most acc (0 or 1) mismatches in the positions looked at
+        const uint32_t surv0 = ax0 & ~twos0 & (~ones0 | ay0), surv1 = ax1 & ~twos1 & (~ones1 | ay1);
+        const bool first0 = surv0 != 0u && n_surv == 0;
+        first_word = first0 ? surv0 : first_word;
+        first_group = first0 ? 2 * gp : first_group;
+        n_surv += __popc(surv0);
+        const bool first1 = surv1 != 0u && n_surv == 0;
+        first_word = first1 ? surv1 : first_word;
+        first_group = first1 ? 2 * gp + 1 : first_group;
+        n_surv += __popc(surv1);
     });
 }
 
@@ -303,8 +311,8 @@ __device__ __forceinline__ bool seed_filter(const DevPanel &P, ScanCtx<RW> &c, c
 // loads; the unrolled bit-sliced filter addresses its tables as shared memory as well (the general loop does not)
 template <int RW, bool FAST, bool ONCHIP>
 __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(const __grid_constant__ DevPanel P, const __grid_constant__ DevReads R, const __grid_constant__ ScanLaunch S, idp_result *__restrict__ five,
-                                                               unsigned int *__restrict__ fall, Counters *__restrict__ ctr) {
-    extern __shared__ __align__(16) unsigned char smem[];
+                                                               uint8_t *__restrict__ rtype, unsigned int *__restrict__ fall, Counters *__restrict__ ctr) {
+    extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t tile_bar[kScanWarps][2];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const DevKmerIndex &ix = P.kidx[0];
@@ -360,7 +368,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
     }
     const bool bs_onchip = ONCHIP && S.off_bsmm != 0xFFFFFFFFu && S.off_bsacc != 0xFFFFFFFFu;  // large panels keep them in global memory
     const uint32_t tab_addr = bs_onchip ? smem_u32(smem) + S.off_bsmm : 0u, acc_addr = bs_onchip ? smem_u32(smem) + S.off_bsacc : 0u;
-    const bool fixed_groups = bs_onchip && (tab_addr & 63u) == 0u && P.bs_groups >= 2 && P.bs_groups <= 8 && (P.bs_groups & 1) == 0;
+    const bool fixed_groups = bs_onchip && (tab_addr & 127u) == 0u && (acc_addr & 15u) == 0u && P.bs_groups >= 2 && P.bs_groups <= 8 && (P.bs_groups & 1) == 0;
     if (S.stage_tile && lane == 0) {
         mbar_init(&tile_bar[wib][0], 1);
         mbar_init(&tile_bar[wib][1], 1);
@@ -533,12 +541,12 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
                         if (n_surv == 1) q0 = first_group * 32 + __ffs(first_word) - 1;
                     }
                     for (int g = 0; n_surv >= 2 && g < P.bs_groups; ++g) {
-                        const uint32_t *row = bs_mm + (size_t)g * (kBsStride * 16);
+                        const uint32_t *row = bs_mm + (size_t)(g >> 1) * (kBsStride * 32) + (g & 1);  // group pairs are interleaved
                         uint32_t ones = 0, twos = 0;
 #pragma unroll
                         for (int i = 0; i < kBsPositions; ++i) {
                             const uint32_t nib = (c.win[(i >> 3) < RW ? (i >> 3) : 0] >> (4 * (i & 7))) & 15u;
-                            const uint32_t v = row[i * 16 + nib];
+                            const uint32_t v = row[(i * 16 + nib) * 2];
                             twos |= ones & v;
                             ones |= v;
                         }
@@ -590,6 +598,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
             }
             need_gapped = res.type == IDP_NONE;
             write_result(&five[r], res);
+            rtype[r] = res.type;  // what metrics_kernel reads: one byte instead of the 32-byte record
         }
         // fall-through list (IP:444-450), warp-aggregated append
         const unsigned ballot = __ballot_sync(0xffffffffu, need_gapped);
