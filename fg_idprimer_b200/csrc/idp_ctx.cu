@@ -404,7 +404,7 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
         s.launches += 5;
     } else { CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_A], st)); CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_B], st)); }
     CUDA_TRY(cudaEventRecord(s.ev[EV_THREE], st));
-    if (n > 0) { metrics_kernel<<<std::min<int>((R.n + 255) / 256, c->sm_count * 8), 256, 0, st>>>(R, rtype, ctr); ++s.launches; }
+    if (n > 0) { metrics_kernel<<<std::min<int>((R.n + 2047) / 2048, c->sm_count * 8), 256, 0, st>>>(R, rtype, ctr); ++s.launches; }
     CUDA_TRY(cudaMemcpyAsync(s.h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(s.ev[EV_END], st));
     CUDA_TRY(cudaGetLastError());

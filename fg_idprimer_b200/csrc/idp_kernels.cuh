@@ -47,6 +47,7 @@ struct Counters {
     unsigned int overflow;        // pair buffer too small: number of work items not emitted
     unsigned int n_spill;         // fall-through reads with more -K candidates than the per-thread list holds
     unsigned int pad0;
+    unsigned int pair_cursor[2];  // next unclaimed pair of sw_pairs_kernel (0: 5' Glocal pass, 1: 3' Local pass)
     unsigned long long n_align5;  // alignments performed by the 5' aligner (IP:424)
     unsigned long long n_align3;
     unsigned long long sw_cells;
@@ -173,35 +174,62 @@ __global__ void __launch_bounds__(256) cand5_thread_kernel(DevPanel P, DevReads 
             const int r = (int)fall[w];
             const uint8_t *s; int len;
             read_geom(R, r, s, len);
-            TargetStream ts(Oriented{s, len, seq_order_is_rc(R.flags[r])});
+            const bool rc = seq_order_is_rc(R.flags[r]);
+            TargetStream ts(Oriented{s, len, rc});
             const int n_bases = len >= ix.k ? min(ix.window, len) : 0;  // k-mers start at 0 .. n_bases - k (PM:110)
             uint64_t key = 0;
             uint32_t key2 = 0;
             int bad = 0;  // > 0 while the current k-mer holds a code that is not exactly one of A/C/G/T
-            for (int i = 0; i < n_bases && !spilled; ++i) {
-                const uint32_t nib = ts.nib(i);
+            auto visit = [&](uint32_t nib, int i) {  // one more base of the window; false = the candidate list overflowed
                 key = ((key << 4) | nib) & kmask;
                 key2 = ((key2 << 2) | ((0x30210u >> (2 * nib)) & 3u)) & kmask2;  // A,C,G,T (1,2,4,8) -> 0..3
                 bad = max(bad - 1, 0);
                 if (__popc(nib) != 1) bad = ix.k;
                 OffCnt oc;
-                if (i < ix.k - 1) continue;
+                if (i < ix.k - 1) return true;
                 if (ix.direct != nullptr && bad == 0) {  // one load, no probing: the lanes of a warp stay together
                     const uint32_t e = __ldg(&ix.direct[key2]);
-                    if (!e) continue;
+                    if (!e) return true;
                     oc.off = e & 0xFFFFFu; oc.cnt = e >> 20;
-                } else if (!kmer_lookup(ix, key, oc)) continue;
+                } else if (!kmer_lookup(ix, key, oc)) return true;
                 for (uint32_t j = 0; j < oc.cnt; ++j) {
                     const int p = (int)__ldg(&ix.postings[oc.off + j]);
                     bool seen = false;
 #pragma unroll
                     for (int t = 0; t < kCandLocal; ++t) seen |= (t < nc && cand[t] == p);
                     if (seen) continue;
-                    if (nc == kCandLocal) { spilled = true; break; }
+                    if (nc == kCandLocal) return false;
 #pragma unroll
                     for (int t = 0; t < kCandLocal; ++t) if (t == nc) cand[t] = p;
                     ++nc;
                 }
+                return true;
+            };
+            if (!rc && n_bases <= 32 && ((len + 1) >> 1) >= 20) {
+                // forward read, window of at most 32 bases: five aligned words give the window as a 4-word shift register
+                // (base i in nibble i), so a base costs a handful of register operations instead of a byte fetch
+                const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+                const int sh = (int)(a & 3) * 8;
+                uint32_t sr[4];
+                uint32_t prev = __ldg(wp);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t next = __ldg(wp + w + 1);
+                    sr[w] = nibswap(__funnelshift_r(prev, next, sh));
+                    prev = next;
+                }
+                for (int i = 0; i < n_bases; ++i) {
+                    const uint32_t nib = sr[0] & 15u;
+                    sr[0] = __funnelshift_r(sr[0], sr[1], 4);
+                    sr[1] = __funnelshift_r(sr[1], sr[2], 4);
+                    sr[2] = __funnelshift_r(sr[2], sr[3], 4);
+                    sr[3] >>= 4;
+                    if (!visit(nib, i)) { spilled = true; break; }
+                }
+            } else {
+                for (int i = 0; i < n_bases; ++i)
+                    if (!visit(ts.nib(i), i)) { spilled = true; break; }
             }
         }
         const int count = (active && !spilled) ? nc : 0;
@@ -869,9 +897,13 @@ __global__ void __launch_bounds__(128, 4) sw_pairs_kernel(DevPanel P, DevReads R
     const unsigned per_round = gridDim.x * blockDim.x;
     const int tile = n_pairs >= 4u * per_round ? 4 : n_pairs >= 2u * per_round ? 2 : 1;  // keep every SM busy on small batches
     const unsigned span = (unsigned)tile * blockDim.x;
-    for (unsigned base = blockIdx.x * span; base < n_pairs; base += gridDim.x * span) {
+    __shared__ unsigned base_s;
+    for (;;) {  // blocks claim spans from a device-wide cursor: a block whose alignments were short takes more
+        if (threadIdx.x == 0) base_s = atomicAdd(&ctr->pair_cursor[LOCAL ? 1 : 0], span);
         for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist_s[i] = 0;
         __syncthreads();
+        const unsigned base = base_s;
+        if (base >= n_pairs) break;
         int bin[kTileMax], rank[kTileMax];
 #pragma unroll
         for (int k = 0; k < kTileMax; ++k) {
@@ -1211,25 +1243,58 @@ __global__ void __launch_bounds__(256) metrics_kernel(DevReads R, const uint8_t 
     __shared__ unsigned int hist[160];
     for (int i = threadIdx.x; i < 160; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int base = blockIdx.x * blockDim.x; base < R.n; base += gridDim.x * blockDim.x) {
-        const int r = base + (int)threadIdx.x;
-        int bin = -1;
-        if (r < R.n && !(r > 0 && (R.flags[r - 1] & IDP_F_MATE_NEXT))) {  // not an R2
-            const uint16_t fl = R.flags[r];
-            const bool has_r2 = (fl & IDP_F_MATE_NEXT) && r + 1 < R.n;
-            const bool m1 = !(fl & IDP_F_UNMAPPED);
-            int tt, t2 = IDP_NONE;
-            if (!has_r2) tt = m1 ? 3 : 4;
-            else {
-                const bool m2 = !(R.flags[r + 1] & IDP_F_UNMAPPED);
-                tt = (m1 && m2) ? 0 : (m1 != m2 ? 1 : 2);
-                t2 = rtype[r + 1];
+    // a thread takes 8 consecutive reads: one 16-byte load of flags, one 8-byte load of match types, plus the neighbours on
+    // either side (the read before decides whether the first one is an R2, the one after is the last one's mate)
+    const bool vec = (reinterpret_cast<uintptr_t>(R.flags) & 15) == 0 && (reinterpret_cast<uintptr_t>(rtype) & 7) == 0;
+    const long long n8 = ((long long)R.n + 7) / 8;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < n8; base += (long long)gridDim.x * blockDim.x) {
+        const long long g = base + threadIdx.x;
+        int cur = -1;
+        unsigned cnt = 0;
+        if (g < n8) {
+            const int r0 = (int)(g * 8);
+            uint16_t f[10];  // f[0] = flags[r0 - 1], f[1..8] = flags[r0 .. r0 + 7], f[9] = flags[r0 + 8]; zero outside the batch
+            uint8_t t[9];    // t[0..7] = rtype[r0 .. r0 + 7], t[8] = rtype[r0 + 8]
+            if (vec && r0 + 8 <= R.n) {
+                const uint4 fv = *reinterpret_cast<const uint4 *>(R.flags + r0);
+                const uint2 tv = *reinterpret_cast<const uint2 *>(rtype + r0);
+                const uint32_t fw[4] = {fv.x, fv.y, fv.z, fv.w};
+                const uint32_t tw[2] = {tv.x, tv.y};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { f[u + 1] = (uint16_t)(fw[u >> 1] >> (16 * (u & 1))); t[u] = (uint8_t)(tw[u >> 2] >> (8 * (u & 3))); }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const bool in = r0 + u < R.n; f[u + 1] = in ? R.flags[r0 + u] : (uint16_t)0; t[u] = in ? rtype[r0 + u] : (uint8_t)IDP_NONE; }
             }
-            bin = ((tt * 2 + ((fl & IDP_F_FR_PAIR) ? 1 : 0)) * 4 + rtype[r]) * 4 + t2;
+            f[0] = r0 > 0 ? R.flags[r0 - 1] : (uint16_t)0;
+            const bool after = r0 + 8 < R.n;
+            f[9] = after ? R.flags[r0 + 8] : (uint16_t)0;
+            t[8] = after ? rtype[r0 + 8] : (uint8_t)IDP_NONE;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + u;
+                if (r >= R.n || (f[u] & IDP_F_MATE_NEXT)) continue;  // outside the batch, or an R2
+                const uint16_t fl = f[u + 1];
+                const bool has_r2 = (fl & IDP_F_MATE_NEXT) && r + 1 < R.n;
+                const bool m1 = !(fl & IDP_F_UNMAPPED), m2 = !(f[u + 2] & IDP_F_UNMAPPED);
+                const int tt = !has_r2 ? (m1 ? 3 : 4) : ((m1 && m2) ? 0 : (m1 != m2 ? 1 : 2));
+                const int bin = ((tt * 2 + ((fl & IDP_F_FR_PAIR) ? 1 : 0)) * 4 + t[u]) * 4 + (has_r2 ? (int)t[u + 1] : (int)IDP_NONE);
+                if (bin != cur) {  // runs of one bin are counted in a register
+                    if (cnt) atomicAdd(&hist[cur], cnt);
+                    cur = bin; cnt = 0;
+                }
+                ++cnt;
+            }
         }
-        // most templates of a batch land in a handful of bins: one shared-memory atomic per distinct bin of the warp
-        const unsigned same = __match_any_sync(0xffffffffu, bin);
-        if (bin >= 0 && (int)(threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&hist[bin], (unsigned)__popc(same));
+        // most templates of a batch land in one bin: the warp adds that bin once, the other lanes add their own
+        const unsigned have = __ballot_sync(0xffffffffu, cnt != 0u);
+        if (have) {
+            const int lead = __ffs(have) - 1;
+            const int b0 = __shfl_sync(0xffffffffu, cur, lead);
+            const unsigned sum = __reduce_add_sync(0xffffffffu, (cnt != 0u && cur == b0) ? cnt : 0u);
+            if ((int)(threadIdx.x & 31) == lead) atomicAdd(&hist[b0], sum);
+            else if (cnt != 0u && cur != b0) atomicAdd(&hist[cur], cnt);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 160; i += blockDim.x) if (hist[i]) atomicAdd(&ctr->metrics[i], (unsigned long long)hist[i]);
