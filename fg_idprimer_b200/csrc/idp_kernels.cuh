@@ -895,7 +895,7 @@ __global__ void __launch_bounds__(128, 4) sw_pairs_kernel(DevPanel P, DevReads R
     __shared__ unsigned short order_s[128 * kTileMax];
     __shared__ int hist_s[kBins];
     const unsigned per_round = gridDim.x * blockDim.x;
-    const int tile = n_pairs >= 4u * per_round ? 4 : n_pairs >= 2u * per_round ? 2 : 1;  // keep every SM busy on small batches
+    const int tile = 2u * n_pairs >= per_round ? 4 : 4u * n_pairs >= per_round ? 2 : 1;  // keep every SM busy on small batches
     const unsigned span = (unsigned)tile * blockDim.x;
     __shared__ unsigned base_s;
     for (;;) {  // blocks claim spans from a device-wide cursor: a block whose alignments were short takes more
@@ -936,7 +936,10 @@ __global__ void __launch_bounds__(128, 4) sw_pairs_kernel(DevPanel P, DevReads R
             if (k < tile) order_s[hist_s[bin[k]] + rank[k]] = (unsigned short)(k * blockDim.x + threadIdx.x);
         __syncthreads();
         for (int k = 0; k < tile; ++k) {
-            const unsigned t = base + order_s[k * blockDim.x + threadIdx.x];
+            // the sorted span is dealt to the warps in snake order (0 1 2 3 / 3 2 1 0 / ...), so every warp gets the same mix
+            // of short and long primers and the warps reach the barrier below together
+            const unsigned slot = (k & 1) ? (blockDim.x - 32u - (threadIdx.x & ~31u)) + (threadIdx.x & 31u) : threadIdx.x;
+            const unsigned t = base + order_s[k * blockDim.x + slot];
             bool active = t < n_pairs;
             int n = 0, m = 0, p = 0;
             Oriented T{nullptr, 0, false};

@@ -243,15 +243,25 @@ __device__ __forceinline__ void bs_filter_fixed(uint32_t tab, uint32_t acc, cons
     }
     static_for<G / 2>([&](auto gc) {
         constexpr int gp = decltype(gc)::value;
+        // four positions per step: "seen twice" gains the majority of (two new vectors, seen once) for each half of the
+        // step, which is five 3-input logic operations per four positions instead of eight
+        static_assert(kBsPositions % 4 == 0, "positions are taken four at a time");
         uint32_t ones0 = 0, twos0 = 0, ones1 = 0, twos1 = 0;
-        static_for<kBsPositions>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            uint32_t v0, v1;
-            asm("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v0), "=r"(v1) : "r"(o[i]), "n"((gp * kBsStride + i) * 128));
-            twos0 |= ones0 & v0;
-            ones0 |= v0;
-            twos1 |= ones1 & v1;
-            ones1 |= v1;
+        static_for<kBsPositions / 4>([&](auto ic) {
+            constexpr int i = 4 * decltype(ic)::value;
+            uint32_t a0, a1, b0, b1, c0, c1, d0, d1;
+            asm("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(a0), "=r"(a1) : "r"(o[i]), "n"((gp * kBsStride + i) * 128));
+            asm("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(b0), "=r"(b1) : "r"(o[i + 1]), "n"((gp * kBsStride + i + 1) * 128));
+            asm("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(c0), "=r"(c1) : "r"(o[i + 2]), "n"((gp * kBsStride + i + 2) * 128));
+            asm("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(d0), "=r"(d1) : "r"(o[i + 3]), "n"((gp * kBsStride + i + 3) * 128));
+            const uint32_t m0 = (a0 & b0) | (ones0 & (a0 | b0)), h0 = ones0 | a0 | b0;
+            const uint32_t n0 = (c0 & d0) | (h0 & (c0 | d0));
+            ones0 = h0 | c0 | d0;
+            twos0 = twos0 | m0 | n0;
+            const uint32_t m1 = (a1 & b1) | (ones1 & (a1 | b1)), h1 = ones1 | a1 | b1;
+            const uint32_t n1 = (c1 & d1) | (h1 & (c1 | d1));
+            ones1 = h1 | c1 | d1;
+            twos1 = twos1 | m1 | n1;
         });
         uint32_t ax0, ay0, ax1, ay1;
         asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(ax0), "=r"(ay0), "=r"(ax1), "=r"(ay1) : "r"(acc), "n"(gp * 16));
