@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libidprimer_b200.so")
+LIB_PATH = os.environ.get("IDP_LIB_PATH") or os.path.join(HERE, "libidprimer_b200.so")  # override: A/B builds of the same ABI
 
 OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, 1, 2, 3, 4
 F_PAIRED, F_UNMAPPED, F_REVERSE, F_FIRST, F_SECOND, F_FR_PAIR, F_MATE_NEXT = 0x1, 0x4, 0x10, 0x40, 0x80, 0x1000, 0x2000

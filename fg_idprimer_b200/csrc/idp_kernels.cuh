@@ -25,6 +25,7 @@
 
 #include "idp_internal.h"
 
+
 namespace idp {
 
 struct DevReads {
@@ -713,15 +714,18 @@ struct TracedReg { int score, t_start, t_end; };
 // Glocal in the shifted coordinates of sw_score_glocal_shifted: every candidate of a cell carries the same shift, so the
 // comparisons (and the rank / start bits below the score) are untouched, a gap extension costs nothing and the two
 // "+ extend" additions per cell disappear.  End cells of different columns are compared after shifting back.
+// TWO target columns per sweep: stream A walks column j, stream B walks column j+1 one row behind it
+// (B at row r-1 reads what A left in M / LN at row r-1 a step earlier), so every step holds two independent cell updates
+// and the max-plus chain of one hides the latency of the other.  Rows lo..hi run in the ragged (select) form, which is
+// also what keeps B's first step -- a row above the query -- without effect; the rows after hi run the plain form and B
+// finishes with row NQ-1 after the sweep.  An odd last column pairs with a dummy column whose end cell is not taken.
 template <int NQ>
 __device__ __forceinline__ TracedReg sw_trace_reg_glocal_shifted(const DevPanel &P, const uint32_t *__restrict__ qbot, int n, int lo, int hi,
-                                                                 const Oriented &T, int m) {
+                                                                  const Oriented &T, int m) {
     constexpr int SH = 14, LOW = 0x3FFF, RANK = 0x3000, RD = 0x3000, RL = 0x2000, RU = 0x1000;
     TracedReg out{0, 1, 0};
     const int e1 = P.gap_extend;
-    const int o = P.tr_open;  // a constant-bank operand of VIADDMNMX
-    // registers (selected per cell / one LOP3 per re-stamp): a value that went through a shuffle is not re-derived from
-    // the constant bank inside every row
+    const int o = P.tr_open;
     const unsigned am = __activemask();
     const int self = (int)(threadIdx.x & 31u);
     const int ma = __shfl_sync(am, P.tr_match_shifted, self), mi = __shfl_sync(am, P.tr_mismatch_shifted, self), keep = __shfl_sync(am, ~RANK, self);
@@ -730,53 +734,72 @@ __device__ __forceinline__ TracedReg sw_trace_reg_glocal_shifted(const DevPanel 
     uint32_t q[NQ / 8];
 #pragma unroll
     for (int w = 0; w < NQ / 8; ++w) q[w] = __ldg(&qbot[w]);
-    int LN[NQ], M[NQ];  // LN[r] = Left'(r, next column), stamped
+    int LN[NQ], M[NQ];
 #pragma unroll
-    for (int r = 0; r < NQ; ++r) { LN[r] = NEG | RL; M[r] = o | RU; }  // Up'(i,0) = open, start 0
+    for (int r = 0; r < NQ; ++r) { LN[r] = NEG | RL; M[r] = o | RU; }
     int best = NEG, bj = 0;
-    const int ne1 = -P.tr_ext;          // one column (or row) further: the shift grows by -extend
-    int edge = 0;                       // (-extend * (j-1)) << SH at the top of column j
-    int back = (e1 * n) * (1 << SH);    // (extend * (n + j)) << SH, added to an end cell of column j
+    const int ne1 = -P.tr_ext;
+    int edge = 0;
+    int back = (e1 * n) * (1 << SH);
     TargetStream ts(T);
-    for (int j = 1; j <= m; ++j) {
-        uint32_t t = ts.nib(j - 1);
-        asm volatile("" : "+r"(t));
-        const uint32_t trep = t * 0x11111111u;
-        uint32_t ne[NQ / 8];
+    for (int j = 1; j <= m; j += 2) {
+        uint32_t tA = ts.nib(j - 1), tB = j < m ? ts.nib(j) : 0u;
+        asm volatile("" : "+r"(tA), "+r"(tB));
+        const uint32_t trepA = tA * 0x11111111u, trepB = tB * 0x11111111u;
+        uint32_t neA[NQ / 8], neB[NQ / 8];
 #pragma unroll
-        for (int w = 0; w < NQ / 8; ++w) ne[w] = nib_nonzero(q[w] ^ trep);
-        int mdiag = edge + (j - 1);  // row 0: score 0, path starts at this column
+        for (int w = 0; w < NQ / 8; ++w) { neA[w] = nib_nonzero(q[w] ^ trepA); neB[w] = nib_nonzero(q[w] ^ trepB); }
+        int mdiagA = edge + (j - 1);  // row 0: score 0, path starts at this column
         edge += ne1;
-        back += P.tr_ext;
-        int d_up = edge | RD | j, u_up = edge | RU | j;
-#define IDP_CELL(r)                                                                                   \
-            const int dn = ((mdiag + ((ne[(r) >> 3] & (1u << (4 * ((r) & 7)))) ? mi : ma)) & ~RANK) | RD; \
-            const int un = (__viaddmax_s32(d_up, o, u_up) & keep) | RU; /* equal scores: opened from Diagonal */ \
-            const int ln = LN[(r)];                                                                    \
-            const int mold = M[(r)];                                                                   \
-            M[(r)] = __vimax3_s32(dn, ln, un); /* equal scores: Diagonal, then Left, then Up */        \
-            LN[(r)] = (__viaddmax_s32(dn, o, ln) & keep) | RL;
-#define IDP_ROW(r)                                                                     \
-    case (r): {                                                                        \
-        if ((r) >= hi) break;                                                          \
-        const bool act = (r) >= off;                                                   \
-        IDP_CELL(r)                                                                    \
-        mdiag = act ? mold : mdiag; d_up = act ? dn : d_up; u_up = act ? un : u_up;    \
+        int d_upA = edge | RD | j, u_upA = edge | RU | j;
+        int mdiagB = edge + j;
+        edge += ne1;
+        int d_upB = edge | RD | (j + 1), u_upB = edge | RU | (j + 1);
+#define IDP_CELL2(r, S)                                                                                        \
+            const int dn##S = ((mdiag##S + ((ne##S[(r) >> 3] & (1u << (4 * ((r) & 7)))) ? mi : ma)) & ~RANK) | RD; \
+            const int un##S = (__viaddmax_s32(d_up##S, o, u_up##S) & keep) | RU;                                 \
+            const int ln##S = LN[(r)];                                                                         \
+            const int mold##S = M[(r)];                                                                        \
+            M[(r)] = __vimax3_s32(dn##S, ln##S, un##S);                                                         \
+            LN[(r)] = (__viaddmax_s32(dn##S, o, ln##S) & keep) | RL;
+#define IDP_PREV(r) ((r) > 0 ? (r) - 1 : 0)
+#define IDP_ROW(r)                                                                                 \
+    case (r): {                                                                                    \
+        if ((r) > hi) break;                                                                       \
+        {                                                                                          \
+            const bool act = (r) >= off;                                                           \
+            IDP_CELL2(r, A)                                                                        \
+            mdiagA = act ? moldA : mdiagA; d_upA = act ? dnA : d_upA; u_upA = act ? unA : u_upA;   \
+        }                                                                                          \
+        if ((r) > 0) {                                                                             \
+            const bool act = (r) - 1 >= off;                                                       \
+            IDP_CELL2(IDP_PREV(r), B)                                                              \
+            mdiagB = act ? moldB : mdiagB; d_upB = act ? dnB : d_upB; u_upB = act ? unB : u_upB;   \
+        }                                                                                          \
     }
         IDP_SWITCH_ROWS(NQ, lo)
 #undef IDP_ROW
-#define IDP_ROW(r)                                                                     \
-    case (r): {                                                                        \
-        IDP_CELL(r)                                                                    \
-        mdiag = mold; d_up = dn; u_up = un;                                            \
+#define IDP_ROW(r)                                                                                 \
+    case (r): {                                                                                    \
+        { IDP_CELL2(r, A) mdiagA = moldA; d_upA = dnA; u_upA = unA; }                              \
+        { IDP_CELL2(IDP_PREV(r), B) mdiagB = moldB; d_upB = dnB; u_upB = unB; }                    \
     }
-        IDP_SWITCH_ROWS(NQ, hi)
+        IDP_SWITCH_ROWS(NQ, hi + 1)
 #undef IDP_ROW
-#undef IDP_CELL
-        // last row, columns ascending, Diagonal / Left / Up, strict '>': Left(n,j) never exceeds an earlier Diagonal(n,j')
-        const int dt = d_up + back, ut = u_up + back;
-        if (dt > (best | LOW)) { best = dt; bj = j; }
-        if (ut > (best | LOW)) { best = ut; bj = j; }
+        { IDP_CELL2(NQ - 1, B) d_upB = dnB; u_upB = unB; (void)moldB; }
+#undef IDP_PREV
+#undef IDP_CELL2
+        // last row, columns ascending, Diagonal / Left / Up, strict '>'
+        back += P.tr_ext;
+        const int dtA = d_upA + back, utA = u_upA + back;
+        if (dtA > (best | LOW)) { best = dtA; bj = j; }
+        if (utA > (best | LOW)) { best = utA; bj = j; }
+        back += P.tr_ext;
+        if (j < m) {
+            const int dtB = d_upB + back, utB = u_upB + back;
+            if (dtB > (best | LOW)) { best = dtB; bj = j + 1; }
+            if (utB > (best | LOW)) { best = utB; bj = j + 1; }
+        }
     }
     out.score = best >> SH; out.t_start = (best & 0xFFF) + 1; out.t_end = bj;
     return out;
