@@ -339,7 +339,7 @@ def main():
                      "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PAIR * n_pairs},
         "clocks": clocks,
         "stages_ms": {k: statistics.mean(t[k] for t in tm_res) for k in ("ms_total", "ms_scan", "ms_gapped", "ms_three_prime", "ms_sw_score")},
-        "work": {k: int(tm_res[-1][k]) for k in ("n_fallthrough", "n_alignments_5p", "n_alignments_3p", "sw_cells", "scan_base_compares")},
+        "work": {k: int(tm_res[-1][k]) for k in ("n_fallthrough", "n_alignments_5p", "n_alignments_3p", "sw_cells")},
         "parity_spot_check_vs_oracle": parity,
     }
     sw_ms = out["stages_ms"]["ms_sw_score"]

@@ -80,6 +80,7 @@ struct idp_ctx {
     cudaStream_t user_stream = nullptr;
     idp_timings last{};
     int rw = 4, nq = 32;
+    bool scan_stats = false;  // count base comparisons in the scan kernel (IDP_SCAN_STATS=1 when the context is created)
 };
 
 namespace idp {
@@ -255,8 +256,12 @@ static int launch_scan_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, i
         kernel<<<grid, kScanThreads, used, st>>>(c->dp, R, S, five, rtype, fall, ctr);
         return IDP_OK;
     };
-    if (FAST && onchip) return launch(scan_kernel<RW, FAST, FAST>);
-    return launch(scan_kernel<RW, FAST, false>);
+    if (c->scan_stats) {  // idp_timings.scan_base_compares wanted (IDP_SCAN_STATS=1): the counting variant of the kernel
+        if (FAST && onchip) return launch(scan_kernel<RW, FAST, FAST, true>);
+        return launch(scan_kernel<RW, FAST, false, true>);
+    }
+    if (FAST && onchip) return launch(scan_kernel<RW, FAST, FAST, false>);
+    return launch(scan_kernel<RW, FAST, false, false>);
 }
 template <int RW>
 static int launch_scan(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp_result *five, uint8_t *rtype, unsigned *fall, Counters *ctr) {
@@ -456,6 +461,7 @@ int idp_ctx_create(const idp_panel *panel, int device, idp_ctx **out) {
     if (prop.major < 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return IDP_ERR_CUDA; }
     auto *c = new idp_ctx();
     c->panel = panel; c->device = device; c->sm_count = prop.multiProcessorCount;
+    c->scan_stats = getenv("IDP_SCAN_STATS") && atoi(getenv("IDP_SCAN_STATS")) != 0;
     int rc = upload_panel(c);
     if (rc) { idp_ctx_destroy(c); return rc; }
     for (Slot &s : c->slots) {

@@ -67,19 +67,22 @@ struct Best2 {  // getBestUngappedAlignment (PM:237-248) as a running stable top
     }
 };
 
-template <int RW>
+// ST: count base comparisons (idp_timings.scan_base_compares).  Off in the product build of the kernel: the counter and
+// its 64-bit per-warp total cost registers the hot loop does not have (3 % of the kernel, measured)
+template <int RW, bool ST>
 struct ScanCtx {
     uint32_t win[RW];  // read prefix in sequencing order, base i in nibble i, zero beyond the read
     int len;
     unsigned compares;
+    __device__ __forceinline__ void count(unsigned n) { if constexpr (ST) compares += n; }
     const uint32_t *pmask;  // shared or global
     const int4 *pinfo;
 };
 
 // numMismatches + mismatchAlign (PM:128-147).  Returns true and mm when the rate test passes.
 // where: the mismatch flags of the first four words folded into one word, bit 4*(pos%8) + pos/8 (see DevPanel::diag)
-template <int RW>
-__device__ __forceinline__ bool mismatch_align(const DevPanel &P, ScanCtx<RW> &c, int p, int &mm_out, int &plen_out, uint32_t *where = nullptr) {
+template <int RW, bool ST>
+__device__ __forceinline__ bool mismatch_align(const DevPanel &P, ScanCtx<RW, ST> &c, int p, int &mm_out, int &plen_out, uint32_t *where = nullptr) {
     const int4 info = c.pinfo[p];  // {Primer.length, cap, accept, sequence.length}
     const uint32_t *pm = c.pmask + (size_t)p * P.ww;
     int total = 0;
@@ -92,7 +95,7 @@ __device__ __forceinline__ bool mismatch_align(const DevPanel &P, ScanCtx<RW> &c
             if (w < 4) folded |= z << w;
         }
     if (where != nullptr) *where = folded;
-    c.compares += (unsigned)min(c.len, info.w);
+    c.count((unsigned)min(c.len, info.w));
     plen_out = info.x;
     if (c.len >= info.x) {
         const int mm = min(total, info.y);  // the while loop stops counting once count > maxMismatches (PM:142)
@@ -108,8 +111,8 @@ __device__ __forceinline__ bool mismatch_align(const DevPanel &P, ScanCtx<RW> &c
     return __ddiv_rn((double)mm, (double)length) <= P.max_mismatch_rate;
 }
 
-template <int RW>
-__device__ __noinline__ void offer_candidate(const DevPanel &P, ScanCtx<RW> &c, Best2 &best, int p) {
+template <int RW, bool ST>
+__device__ __noinline__ void offer_candidate(const DevPanel &P, ScanCtx<RW, ST> &c, Best2 &best, int p) {
     // .distinct (PM:114): a primer already holding a top-2 slot is skipped; one that lost before loses again (strict
     // comparisons), so no visited set is needed
     if (p == best.bp || p == best.sp) return;
@@ -119,17 +122,17 @@ __device__ __noinline__ void offer_candidate(const DevPanel &P, ScanCtx<RW> &c, 
 
 // Candidates that survive the 8-base head filter wait here and are evaluated after the k-mer loop, all lanes together
 // (in first-hit order, which is the order the reference visits them in).
-template <int RW>
+template <int RW, bool ST>
 struct Pending {
     int q0 = -1, q1 = -1, q2 = -1, q3 = -1;
-    __device__ __forceinline__ void flush(const DevPanel &P, ScanCtx<RW> &c, Best2 &best) {
+    __device__ __forceinline__ void flush(const DevPanel &P, ScanCtx<RW, ST> &c, Best2 &best) {
         if (q0 >= 0) offer_candidate<RW>(P, c, best, q0);
         if (q1 >= 0) offer_candidate<RW>(P, c, best, q1);
         if (q2 >= 0) offer_candidate<RW>(P, c, best, q2);
         if (q3 >= 0) offer_candidate<RW>(P, c, best, q3);
         q0 = q1 = q2 = q3 = -1;
     }
-    __device__ __forceinline__ void push(const DevPanel &P, ScanCtx<RW> &c, Best2 &best, int p) {
+    __device__ __forceinline__ void push(const DevPanel &P, ScanCtx<RW, ST> &c, Best2 &best, int p) {
         if (p == q0 || p == q1 || p == q2 || p == q3) return;
         if (q3 >= 0) flush(P, c, best);
         if (q0 < 0) q0 = p; else if (q1 < 0) q1 = p; else if (q2 < 0) q2 = p; else q3 = p;
@@ -138,8 +141,8 @@ struct Pending {
 
 // posting list walk: the 8-byte head rejects a candidate whose first 8 bases already exceed the accept threshold
 // (exact: the full count can only be larger, and a short read's threshold can only be smaller)
-template <int RW>
-__device__ __forceinline__ void walk_postings(const DevPanel &P, ScanCtx<RW> &c, Best2 &best, Pending<RW> &pend, const uint2 *heads,
+template <int RW, bool ST>
+__device__ __forceinline__ void walk_postings(const DevPanel &P, ScanCtx<RW, ST> &c, Best2 &best, Pending<RW, ST> &pend, const uint2 *heads,
                                               uint32_t off, uint32_t cnt) {
     for (uint32_t j = 0; j < cnt; ++j) {
         const uint2 h = heads[off + j];
@@ -147,16 +150,16 @@ __device__ __forceinline__ void walk_postings(const DevPanel &P, ScanCtx<RW> &c,
         const uint32_t partial = __popc(nib_nonzero(c.win[0] & ~h.y));
         if (partial < acc1 || acc1 == 255u) pend.push(P, c, best, (int)(h.x & 0xFFFFFu));
     }
-    c.compares += 8u * cnt;
+    c.count(8u * cnt);
 }
 
 // The reference's candidate walk (PM:108-116) with the accept test applied on the fly: read k-mers left to right, each
 // k-mer's primers in Set iteration order, first occurrence wins ties.
-template <int RW>
-__device__ __noinline__ void kmer_scan_exact(const DevPanel &P, ScanCtx<RW> &c, Best2 &best, const uint32_t *direct, const uint2 *heads) {
+template <int RW, bool ST>
+__device__ __noinline__ void kmer_scan_exact(const DevPanel &P, ScanCtx<RW, ST> &c, Best2 &best, const uint32_t *direct, const uint2 *heads) {
     const DevKmerIndex &ix = P.kidx[0];
     const int n_bases = min(ix.window, c.len);  // k-mers start at 0 .. n_bases - k
-    Pending<RW> pend;
+    Pending<RW, ST> pend;
     uint32_t sr[RW];  // shift register over the window: the next base is always the low nibble of sr[0]
 #pragma unroll
     for (int w = 0; w < RW; ++w) sr[w] = c.win[w];
@@ -187,8 +190,8 @@ __device__ __noinline__ void kmer_scan_exact(const DevPanel &P, ScanCtx<RW> &c, 
 }
 
 // Is primer p among getPrimersForAlignmentTasksWithCommonKmer(read) (PM:108-116)?  Exact, by walking the read's k-mers.
-template <int RW>
-__device__ __noinline__ bool kmer_member_exact(const DevPanel &P, const ScanCtx<RW> &c, int p) {
+template <int RW, bool ST>
+__device__ __noinline__ bool kmer_member_exact(const DevPanel &P, const ScanCtx<RW, ST> &c, int p) {
     const DevKmerIndex &ix = P.kidx[0];
     const int n_bases = min(ix.window, c.len);
     const uint64_t kmask4 = ix.k >= 16 ? ~0ull : ((1ull << (4 * ix.k)) - 1ull);
@@ -207,8 +210,8 @@ __device__ __noinline__ bool kmer_member_exact(const DevPanel &P, const ScanCtx<
 
 // A run of k literally equal letters at the same offset in read and primer (inside both the search window and the primer)
 // proves that the primer shares a k-mer with the read.  Nibble codes are letters: equal code <=> equal letter.
-template <int RW>
-__device__ __forceinline__ bool diagonal_kmer(const DevPanel &P, const ScanCtx<RW> &c, int p, int seq_len, int k, int n_bases) {
+template <int RW, bool ST>
+__device__ __forceinline__ bool diagonal_kmer(const DevPanel &P, const ScanCtx<RW, ST> &c, int p, int seq_len, int k, int n_bases) {
     const uint32_t *pm = c.pmask + (size_t)p * P.ww;
     uint64_t eq = 0;
 #pragma unroll
@@ -284,8 +287,8 @@ __device__ __forceinline__ void bs_filter_fixed(uint32_t tab, uint32_t acc, cons
 // primer has at most one mismatch, so it matches one seed without a mismatch and is listed under the read's spelling of
 // it.  Returns false when the read has to take the general loop instead (a zero code in the head: a read shorter than
 // 2*S or the '=' code; or more than four survivors).
-template <int RW>
-__device__ __forceinline__ bool seed_filter(const DevPanel &P, ScanCtx<RW> &c, const uint32_t *tab, int &s0, int &s1, int &s2, int &s3) {
+template <int RW, bool ST>
+__device__ __forceinline__ bool seed_filter(const DevPanel &P, ScanCtx<RW, ST> &c, const uint32_t *tab, int &s0, int &s1, int &s2, int &s3) {
     const bool six = P.seed_S == 6;
     const uint32_t w0 = c.win[0];
     const uint32_t h1 = RW > 1 ? (six ? (c.win[RW > 1 ? 1 : 0] & 0xFFFFu) : c.win[RW > 1 ? 1 : 0]) : 0u;  // head = w0 + h1
@@ -313,13 +316,13 @@ __device__ __forceinline__ bool seed_filter(const DevPanel &P, ScanCtx<RW> &c, c
             fits = fits && x == INT_MAX;
         }
     }
-    c.compares += verified * 2u * (unsigned)P.seed_S;
+    c.count(verified * 2u * (unsigned)P.seed_S);
     return fits;
 }
 
 // ONCHIP: the read tiles are known at compile time to sit in shared memory, so the window loads are LDS rather than generic
 // loads; the unrolled bit-sliced filter addresses its tables as shared memory as well (the general loop does not)
-template <int RW, bool FAST, bool ONCHIP>
+template <int RW, bool FAST, bool ONCHIP, bool ST>
 __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(const __grid_constant__ DevPanel P, const __grid_constant__ DevReads R, const __grid_constant__ ScanLaunch S, idp_result *__restrict__ five,
                                                                uint8_t *__restrict__ rtype, unsigned int *__restrict__ fall, Counters *__restrict__ ctr) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
     const uint2 *heads = ix.heads;
     const uint32_t *bs_mm = P.bs_mm;
     const uint2 *bs_acc = P.bs_acc;
-    ScanCtx<RW> c;
+    ScanCtx<RW, ST> c;
     c.pmask = P.pmask;
     c.pinfo = P.pinfo;
     if (!FAST && S.off_direct != 0xFFFFFFFFu) {
@@ -496,14 +499,14 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
                 // the out-of-line walks get COPIES: an object whose address reaches a call lives in local memory for the
                 // whole kernel, and the read window / running best are touched by every instruction of the hot path
                 auto scan_exact = [&](const uint32_t *dir, const uint2 *hd) {
-                    ScanCtx<RW> cc = c;
+                    ScanCtx<RW, ST> cc = c;
                     Best2 bb = best;
                     kmer_scan_exact<RW>(P, cc, bb, dir, hd);
                     best = bb;
-                    c.compares = cc.compares;
+                    if constexpr (ST) c.compares = cc.compares;
                 };
                 auto member_exact = [&](int p) {
-                    const ScanCtx<RW> cc = c;
+                    const ScanCtx<RW, ST> cc = c;
                     return kmer_member_exact<RW>(P, cc, p);
                 };
                 if (FAST) {
@@ -569,7 +572,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
                             if (q0 < 0) q0 = p; else if (q1 < 0) q1 = p; else if (q2 < 0) q2 = p; else q3 = p;
                         }
                     }
-                    if (!seeded) c.compares += (unsigned)(P.n_primers * kBsPositions);
+                    if (!seeded) c.count((unsigned)(P.n_primers * kBsPositions));
                     flush();
                     if (ix.k > 0) {
                         if (n_acc == 1) {
@@ -618,14 +621,16 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
             base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
             if (need_gapped) fall[base + __popc(ballot & ((1u << lane) - 1u))] = (unsigned)r;
         }
-        compares_total += c.compares;
+        if constexpr (ST) compares_total += c.compares;
         __syncwarp();  // all lanes are done with this tile buffer: the next iteration may overwrite it
         cur ^= 1;
     }
     // statistics: base comparisons performed, one atomic per warp
+    if constexpr (ST) {
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) compares_total += __shfl_xor_sync(0xffffffffu, compares_total, d);
-    if (lane == 0 && compares_total) atomicAdd(&ctr->base_compares, compares_total);
+        for (int d = 16; d > 0; d >>= 1) compares_total += __shfl_xor_sync(0xffffffffu, compares_total, d);
+        if (lane == 0 && compares_total) atomicAdd(&ctr->base_compares, compares_total);
+    }
 }
 
 }  // namespace idp

@@ -131,7 +131,9 @@ typedef struct {
     int64_t  n_alignments_5p;     /* gapped alignments, 5' (== the reference's numAlignments, IP:424)          */
     int64_t  n_alignments_3p;
     int64_t  sw_cells;            /* sum over alignments of |query| * |target|                                 */
-    int64_t  scan_base_compares;  /* sum over (read, candidate) of min(readLen, primer bytes)                  */
+    int64_t  scan_base_compares;  /* sum over (read, candidate) of min(readLen, primer bytes); counted only when
+                                   * IDP_SCAN_STATS=1 is in the environment at idp_ctx_create (the counting variant
+                                   * of the scan kernel is 3 % slower), else 0                                    */
     int64_t  kernel_launches;     /* kernels of this library launched by the call                              */
     int64_t  h2d_bytes, d2h_bytes;
 } idp_timings;
