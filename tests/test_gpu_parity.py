@@ -399,6 +399,46 @@ def test_fast_filter_ties_and_iupac_dense_primers():
             assert (got5["type"] == L.UNGAPPED).any()
 
 
+def test_kmer_rule_depends_on_mismatch_position():
+    """PM:108-116 with degenerate primers: the primer is a candidate only through a run of k literally equal letters, so
+    whether an accepted primer (at most one mismatch) is reported depends on where the mismatch sits.  Primers with a single
+    plain run, with runs of exactly k, with no plain run at all; reads with the mismatch at every position, reads that
+    spell the primer's ambiguity letter literally, reads carrying N."""
+    rng = np.random.default_rng(77)
+    deg = {"A": "R", "C": "Y", "G": "R", "T": "Y"}
+    inst = {"R": "AG", "Y": "CT"}
+    primers = []
+
+    def add(name, seq):
+        primers.append(H.Primer(name, name + "+", seq, True))
+        primers.append(H.Primer(name, name + "-", "".join("ACGT"[x] for x in rng.integers(0, 4, 20)), False))
+
+    for i in range(6):   # one plain run of exactly k = 6 at a different place each time, everything else degenerate
+        s = ["ACGT"[x] for x in rng.integers(0, 4, 20 + i)]
+        lo = 2 * i + 1
+        add(f"one{i}", "".join(ch if lo <= j < lo + 6 else deg[ch] for j, ch in enumerate(s)))
+    for d in (5, 6, 7, 8):   # a degenerate letter every d bases: plain runs of d-1
+        s = ["ACGT"[x] for x in rng.integers(0, 4, 26)]
+        add(f"every{d}", "".join(deg[ch] if j % d == d - 1 else ch for j, ch in enumerate(s)))
+    add("plain", "".join("ACGT"[x] for x in rng.integers(0, 4, 24)))
+    recs = []
+    for p in primers[::2]:
+        n = len(p.sequence)
+        for pos in range(-1, n):   # -1: no mismatch
+            for literal in (False, True):
+                s = [(ch if literal else inst[ch][int(rng.integers(0, 2))]) if ch in inst else ch for ch in p.sequence]
+                if pos >= 0:
+                    allowed = inst.get(p.sequence[pos], p.sequence[pos])
+                    s[pos] = rng.choice([b for b in "ACGTN" if b not in allowed])
+                s += ["ACGT"[x] for x in rng.integers(0, 4, 40)]
+                recs.append(H.Rec("".join(s), True, False))
+    arrays = H.recs_to_arrays(recs)
+    for k in (5, 6, 7):
+        got5, _, _, _ = run_both(primers, arrays, max_mismatch_rate=0.05, ungapped_kmer_length=k, gapped_kmer_length=8)
+        types = got5["type"]
+        assert (types == L.UNGAPPED).any() and (types != L.UNGAPPED).any()
+
+
 @pytest.mark.parametrize("name,n_pairs", [("c2", 300_000), ("c3", 100_000), ("c5", 100_000)])
 def test_fast_filter_equals_exact_walk(name, n_pairs):
     import os
