@@ -48,7 +48,6 @@ struct Counters {
     unsigned int overflow;        // pair buffer too small: number of work items not emitted
     unsigned int n_spill;         // fall-through reads with more -K candidates than the per-thread list holds
     unsigned int pad0;
-    unsigned int pair_cursor[2];  // next unclaimed pair of sw_pairs_kernel (0: 5' Glocal pass, 1: 3' Local pass)
     unsigned long long n_align5;  // alignments performed by the 5' aligner (IP:424)
     unsigned long long n_align3;
     unsigned long long sw_cells;
@@ -918,15 +917,13 @@ __global__ void __launch_bounds__(128, 4) sw_pairs_kernel(DevPanel P, DevReads R
     __shared__ unsigned short order_s[128 * kTileMax];
     __shared__ int hist_s[kBins];
     const unsigned per_round = gridDim.x * blockDim.x;
-    const int tile = 2u * n_pairs >= per_round ? 4 : 4u * n_pairs >= per_round ? 2 : 1;  // keep every SM busy on small batches
+    // a span is tile x 128 pairs; half of the grid is resident (4 blocks per SM), so spans stay single (every pair gets its own
+    // thread at once) until the batch exceeds one round of the whole grid
+    const int tile = n_pairs > 2u * per_round ? 4 : n_pairs > per_round ? 2 : 1;
     const unsigned span = (unsigned)tile * blockDim.x;
-    __shared__ unsigned base_s;
-    for (;;) {  // blocks claim spans from a device-wide cursor: a block whose alignments were short takes more
-        if (threadIdx.x == 0) base_s = atomicAdd(&ctr->pair_cursor[LOCAL ? 1 : 0], span);
+    for (unsigned base = blockIdx.x * span; base < n_pairs; base += gridDim.x * span) {
         for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist_s[i] = 0;
         __syncthreads();
-        const unsigned base = base_s;
-        if (base >= n_pairs) break;
         int bin[kTileMax], rank[kTileMax];
 #pragma unroll
         for (int k = 0; k < kTileMax; ++k) {
