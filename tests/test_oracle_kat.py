@@ -186,3 +186,28 @@ def test_java_format_2f():  # PrimerMatch.scala:115 / PrimerMatchTest
     assert O.java_format_2f(0.995) == "1.00"
     assert O.java_format_2f(99.995) == "100.00"
     assert O.java_format_2f(0.001) == "0.00"
+
+
+def test_kmer_rule_follows_the_mismatch_position():
+    """PM:108-116 from first principles (no GPU): the ungapped matcher only sees primers that share a k-mer STRING with the
+    read window, so a degenerate primer (IUPAC letters match A/C/G/T reads by PM:143 but are different letters) is reported
+    only when a run of k plain letters survives the read's mismatch.  One plain run of exactly k at positions 7..12."""
+    k = 6
+    seq = "RYRYRYR" + "ACGTCA" + "YRYRYRY"            # 20 letters: degenerate, plain run of 6, degenerate
+    primers = [H.Primer("p", "p+", seq, True), H.Primer("p", "p-", "TTGACCATGACCATGACCAT", False)]
+    panel = O.Panel(primers, O.make_params(max_mismatch_rate=0.05, k_ungapped=k, min_alignment_score_rate=1e9))
+    inst = {"R": "A", "Y": "C"}
+    recs, expect = [], []
+    for pos in range(-1, len(seq)):
+        s = [inst.get(ch, ch) for ch in seq]
+        if pos >= 0:
+            s[pos] = "T" if s[pos] != "T" and (seq[pos] not in "Y") else "G"   # a base the primer letter does not allow
+            assert O.num_mismatches("".join(s).encode(), seq.encode(), 0, 5.0) == 1
+        recs.append(H.Rec("".join(s) + "ACGT" * 10, True, False))
+        expect.append(not (7 <= pos <= 12))               # the only literal 6-mer is gone when the mismatch sits inside it
+    # a read that spells the ambiguity letters themselves is literally equal everywhere
+    recs.append(H.Rec(seq + "ACGT" * 10, True, False))
+    expect.append(True)
+    five, _, _, _ = panel.process_batch(H.recs_to_arrays(recs), n_threads=1)
+    got = [int(t) == 2 and int(p) == 0 for t, p in zip(five["type"], five["primer"])]   # 2 = ungapped match to p+
+    assert got == expect
