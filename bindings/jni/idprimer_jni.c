@@ -25,6 +25,9 @@ JNIEXPORT jlong JNICALL Java_com_fulcrumgenomics_identifyprimers_GpuPrimerMatche
 JNIEXPORT void JNICALL Java_com_fulcrumgenomics_identifyprimers_GpuPrimerMatcher_00024Native_panelDestroy(JNIEnv *env, jclass cls, jlong h) {
     idp_panel_destroy((idp_panel *)(intptr_t)h);
 }
+JNIEXPORT jint JNICALL Java_com_fulcrumgenomics_identifyprimers_GpuPrimerMatcher_00024Native_panelWindow(JNIEnv *env, jclass cls, jlong h) {
+    return idp_panel_window((const idp_panel *)(intptr_t)h);
+}
 JNIEXPORT jlong JNICALL Java_com_fulcrumgenomics_identifyprimers_GpuPrimerMatcher_00024Native_ctxCreate(JNIEnv *env, jclass cls, jlong panel, jint device) {
     idp_ctx *c = NULL;
     if (idp_ctx_create((const idp_panel *)(intptr_t)panel, device, &c) != IDP_OK) { throw_idp(env); return 0; }

@@ -15,6 +15,7 @@ private[identifyprimers] object GpuPrimerMatcher {
     System.loadLibrary("idprimer_jni")
     @native def panelCreate(primers: ByteBuffer, n: Int, params: ByteBuffer): Long
     @native def panelDestroy(h: Long): Unit
+    @native def panelWindow(panel: Long): Int  // idp_panel_window: bases the 5' chain can reach, -1 with --three-prime
     @native def ctxCreate(panel: Long, device: Int): Long
     @native def ctxDestroy(h: Long): Unit
     @native def matchBatch(ctx: Long, seq4: ByteBuffer, seqOff: ByteBuffer, len: ByteBuffer, refIdx: ByteBuffer, uStart: ByteBuffer,
@@ -36,9 +37,15 @@ private[identifyprimers] class GpuPrimerMatcher(panel: Long, device: Int, primer
     val n = recs.length
     // SoA packing: BAM's own 4-bit `seq` bytes go in unchanged (htsjdk SAMRecord#getVariableBinaryRepresentation / bytesToCompressedBases)
     val seqOff = direct(8 * n); val len = direct(4 * n); val refIdx = direct(4 * n); val uS = direct(4 * n); val uE = direct(4 * n); val flags = direct(2 * n)
+    // without --three-prime only the leading bases (sequencing order) can matter: ship the first `window` stored bases, or the
+    // last ones of a mapped reverse-strand read (PrimerMatcher.scala:39-45); same results, a quarter of the bytes over PCIe
+    val window = { val w = Native.panelWindow(panel); if (w > 0) w else Int.MaxValue }
+    def shipped(r: SamRecord): Array[Byte] =
+      if (r.length <= window) r.bases else if (r.mapped && r.negativeStrand) r.bases.takeRight(window) else r.bases.take(window)
     var off = 0L
     recs.zipWithIndex.foreach { case (r, i) =>
-      seqOff.putLong(8 * i, off); len.putInt(4 * i, r.length); off += (r.length + 1) / 2
+      val kept = math.min(r.length, window)
+      seqOff.putLong(8 * i, off); len.putInt(4 * i, kept); off += (kept + 1) / 2
       refIdx.putInt(4 * i, if (r.mapped) r.refIndex else -1)
       uS.putInt(4 * i, if (r.mapped) r.unclippedStart else 0); uE.putInt(4 * i, if (r.mapped) r.unclippedEnd else 0)
       var f = r.flags & (0x1 | 0x4 | 0x10 | 0x40 | 0x80)
@@ -49,7 +56,7 @@ private[identifyprimers] class GpuPrimerMatcher(panel: Long, device: Int, primer
     var i = 0
     templates.foreach { t => if (t.r1.isDefined && t.r2.isDefined) flags.putShort(2 * i, (flags.getShort(2 * i) | 0x2000).toShort); i += t.r1.size + t.r2.size }
     val seq4 = direct(off.toInt)
-    recs.zipWithIndex.foreach { case (r, j) => seq4.position(seqOff.getLong(8 * j).toInt); seq4.put(htsjdk.samtools.SAMUtils.bytesToCompressedBases(r.bases)) }
+    recs.zipWithIndex.foreach { case (r, j) => seq4.position(seqOff.getLong(8 * j).toInt); seq4.put(htsjdk.samtools.SAMUtils.bytesToCompressedBases(shipped(r))) }
     val five = direct(ResultBytes * n); val three = if (threePrime >= 0) direct(ResultBytes * n) else null
     val metrics = direct(8 * 160); val nAligned = direct(8)
     Native.matchBatch(ctx, seq4, seqOff, len, refIdx, uS, uE, flags, 0, n, five, three, metrics, nAligned)

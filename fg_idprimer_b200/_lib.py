@@ -21,7 +21,7 @@ EXPORTS = ["idp_abi_version", "idp_last_error", "idp_device_count", "idp_panel_c
            "idp_panel_primer_length", "idp_panel_primer_hash", "idp_panel_kmer_postings", "idp_ctx_create", "idp_ctx_destroy",
            "idp_ctx_set_stream", "idp_ctx_timings", "idp_host_alloc", "idp_host_free", "idp_match_batch", "idp_match_batch_device",
            "idp_align_batch", "idp_result_score", "idp_result_second", "idp_metric_bin", "idp_summary_metrics", "idp_format_info",
-           "idp_pack_bases", "idp_unpack_bases", "idp_classify_primer_pair", "idp_classify_templates", "idp_bam_scan", "idp_bam_to_batch",
+           "idp_pack_bases", "idp_unpack_bases", "idp_classify_primer_pair", "idp_classify_templates", "idp_bam_scan", "idp_bam_to_batch", "idp_bam_to_batch_window", "idp_panel_window",
            "idp_bam_annotate", "idp_header_comments"]
 
 
@@ -102,6 +102,9 @@ def lib() -> C.CDLL:
     L.idp_classify_templates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     L.idp_bam_scan.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.idp_bam_to_batch.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 8
+    L.idp_bam_to_batch_window.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t] + [C.c_void_p] * 8
+    L.idp_panel_window.argtypes = [C.c_void_p]
+    L.idp_panel_window.restype = C.c_int32
     L.idp_bam_annotate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
     L.idp_header_comments.argtypes = [C.c_char_p, C.c_int32]
     L.idp_pack_bases.argtypes = [C.c_char_p, C.c_int32, C.c_void_p]

@@ -205,8 +205,10 @@ class ReadBatch:
         return cls(seq4, flags, boff, lens, ref_idx, unclipped_start, unclipped_end)
 
     @classmethod
-    def from_bam(cls, bam: bytes):
-        """Uncompressed, queryname-grouped BAM alignment records -> (batch, rec_index); see idp_bam_to_batch."""
+    def from_bam(cls, bam: bytes, window_for: "IdentifyPrimers" = None):
+        """Uncompressed, queryname-grouped BAM alignment records -> (batch, rec_index); see idp_bam_to_batch.
+        window_for: a tool without --three-prime; every read is then cut to the bases its 5' chain can reach
+        (idp_bam_to_batch_window), which gives the same results from a much smaller batch."""
         lib = L.lib()
         buf = np.frombuffer(bam, dtype=np.uint8)
         n = C.c_int32(0)
@@ -217,8 +219,14 @@ class ReadBatch:
         seq_off = np.zeros(n, dtype=np.uint64)
         length, ref_idx, us, ue, rec = (np.zeros(n, dtype=np.int32) for _ in range(5))
         flags = np.zeros(n, dtype=np.uint16)
-        L.check(lib.idp_bam_to_batch(buf.ctypes.data, len(buf), seq4.ctypes.data, seq_off.ctypes.data, length.ctypes.data, ref_idx.ctypes.data,
-                                     us.ctypes.data, ue.ctypes.data, flags.ctypes.data, rec.ctypes.data))
+        if window_for is not None:
+            L.check(lib.idp_bam_to_batch_window(window_for._panel, buf.ctypes.data, len(buf), seq4.ctypes.data, seq_off.ctypes.data, length.ctypes.data,
+                                                ref_idx.ctypes.data, us.ctypes.data, ue.ctypes.data, flags.ctypes.data, rec.ctypes.data))
+            used = int(seq_off[-1] + (length[-1] + 1) // 2) if n else 0
+            seq4 = seq4[:used]
+        else:
+            L.check(lib.idp_bam_to_batch(buf.ctypes.data, len(buf), seq4.ctypes.data, seq_off.ctypes.data, length.ctypes.data, ref_idx.ctypes.data,
+                                         us.ctypes.data, ue.ctypes.data, flags.ctypes.data, rec.ctypes.data))
         return cls(seq4, flags, seq_off, length, ref_idx, us, ue), rec
 
     def as_struct(self, keep: list) -> L.IdpReads:
@@ -296,6 +304,10 @@ class IdentifyPrimers:
     # ---- host-side panel queries (no GPU needed) ----
     def primer_length(self, i: int) -> int:
         return L.lib().idp_panel_primer_length(self._panel, i)
+
+    def window(self) -> int:
+        """Leading bases (sequencing order) the 5' chain can reach; -1 with --three-prime (idp_panel_window)."""
+        return L.lib().idp_panel_window(self._panel)
 
     def primer_hash(self, i: int) -> int:
         return L.lib().idp_panel_primer_hash(self._panel, i)

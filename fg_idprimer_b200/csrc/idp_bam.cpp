@@ -88,8 +88,12 @@ int idp_bam_scan(const uint8_t *bam, size_t n_bytes, int32_t *n_reads, uint64_t 
 // Fills the SoA arrays (sized by idp_bam_scan) from queryname-grouped records.  Reads come out template by template, R1 before
 // R2 (Template.r1 / r2 are chosen by the first/second-of-pair flags, not by file order); rec_index[i] is the ordinal of the BAM
 // record read i came from, so that the host can write the tags back.  An unmapped record reports ref_idx -1.
-int idp_bam_to_batch(const uint8_t *bam, size_t n_bytes, uint8_t *seq4, uint64_t *seq_off, int32_t *len, int32_t *ref_idx,
-                     int32_t *unclipped_start, int32_t *unclipped_end, uint16_t *flags, int32_t *rec_index) {
+// window > 0 keeps only the `window` bases of every read that the 5' matchers can look at (idp_panel_window): the first ones
+// of a read whose sequencing order is its stored order, the LAST ones of a mapped reverse-strand read (PM:39-45: its
+// sequencing order is the reverse complement, so its 5' end is the end of the stored bases).  The stored orientation and the
+// flags are kept, unclipped ends still come from the whole CIGAR.
+static int bam_to_batch(const uint8_t *bam, size_t n_bytes, uint8_t *seq4, uint64_t *seq_off, int32_t *len, int32_t *ref_idx,
+                        int32_t *unclipped_start, int32_t *unclipped_end, uint16_t *flags, int32_t *rec_index, int32_t window) {
     if (!bam || !seq4 || !seq_off || !len || !ref_idx || !unclipped_start || !unclipped_end || !flags) { idp::set_error("idp_bam_to_batch: NULL argument"); return IDP_ERR_ARG; }
     size_t off = 0;
     int32_t ordinal = 0, out = 0;
@@ -111,9 +115,29 @@ int idp_bam_to_batch(const uint8_t *bam, size_t n_bytes, uint8_t *seq4, uint64_t
             }
         }
         if (mate_next) f |= IDP_F_MATE_NEXT;
-        const size_t nb = (size_t)((r.l_seq + 1) / 2);
-        memcpy(seq4 + byte_off, r.seq, nb);
-        seq_off[out] = byte_off; len[out] = r.l_seq;
+        int32_t keep = r.l_seq;
+        size_t nb = (size_t)((r.l_seq + 1) / 2);
+        if (window > 0 && r.l_seq > window) {
+            keep = window;
+            nb = (size_t)((window + 1) / 2);
+            const bool from_end = !unmapped && (r.flag & 0x10);
+            const int32_t first = from_end ? r.l_seq - window : 0;  // first stored base kept
+            uint8_t *dst = seq4 + byte_off;
+            if ((first & 1) == 0) memcpy(dst, r.seq + first / 2, nb);
+            else {  // odd start: every output byte straddles two stored bytes
+                const uint8_t *src = r.seq + first / 2;
+                const size_t src_bytes = (size_t)((r.l_seq + 1) / 2) - (size_t)(first / 2);
+                for (size_t i = 0; i < nb; ++i) {
+                    const uint8_t hi = (uint8_t)(src[i] << 4);
+                    const uint8_t lo = i + 1 < src_bytes ? (uint8_t)(src[i + 1] >> 4) : (uint8_t)0;
+                    dst[i] = (uint8_t)(hi | lo);
+                }
+            }
+            if (window & 1) dst[nb - 1] &= 0xF0;  // the unused low nibble of the last byte is zero, as in a BAM record
+        } else {
+            memcpy(seq4 + byte_off, r.seq, nb);
+        }
+        seq_off[out] = byte_off; len[out] = keep;
         ref_idx[out] = unmapped ? -1 : r.ref_id;
         unclipped_start[out] = unmapped ? 0 : us; unclipped_end[out] = unmapped ? 0 : ue;
         flags[out] = f;
@@ -145,6 +169,20 @@ int idp_bam_to_batch(const uint8_t *bam, size_t n_bytes, uint8_t *seq4, uint64_t
         group.push_back({r, ord});
     }
     return flush();
+}
+
+int idp_bam_to_batch(const uint8_t *bam, size_t n_bytes, uint8_t *seq4, uint64_t *seq_off, int32_t *len, int32_t *ref_idx,
+                     int32_t *unclipped_start, int32_t *unclipped_end, uint16_t *flags, int32_t *rec_index) {
+    return bam_to_batch(bam, n_bytes, seq4, seq_off, len, ref_idx, unclipped_start, unclipped_end, flags, rec_index, 0);
+}
+
+// The same with every read cut down to the bases the 5' matchers can reach (see idp_panel_window): results of
+// idp_match_batch are identical, the batch is a fraction of the size (150 bp reads against 30 bp primers: 18 of 75 bytes).
+int idp_bam_to_batch_window(const idp_panel *panel, const uint8_t *bam, size_t n_bytes, uint8_t *seq4, uint64_t *seq_off, int32_t *len,
+                            int32_t *ref_idx, int32_t *unclipped_start, int32_t *unclipped_end, uint16_t *flags, int32_t *rec_index) {
+    const int32_t w = idp_panel_window(panel);
+    if (w <= 0) { idp::set_error("idp_bam_to_batch_window: the panel has --three-prime set (3' matching reads the whole read) or is NULL"); return IDP_ERR_ARG; }
+    return bam_to_batch(bam, n_bytes, seq4, seq_off, len, ref_idx, unclipped_start, unclipped_end, flags, rec_index, w);
 }
 
 // The three @CO header lines the tool adds (IdentifyPrimers.scala:243-250), '\n'-separated; returns the length.

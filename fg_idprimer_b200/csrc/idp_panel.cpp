@@ -426,6 +426,16 @@ int idp_panel_create(const idp_primer *primers, int32_t n, const idp_params *par
 
 void idp_panel_destroy(idp_panel *panel) { delete panel; }
 int32_t idp_panel_size(const idp_panel *panel) { return panel ? panel->n : 0; }
+// The leading bases (sequencing order) that can influence the 5' chain: the k-mer search window min(maxPrimerLength, len)
+// (PM:110), mismatchAlign's min(len, Primer.length) and numMismatches' min(len, sequence.length) (PM:130, 139), the gapped
+// target min(sequence.length + slop, len) (PM:293), and the `len < k` tests (PM:109).  A read cut to this many bases gives the
+// same results as the whole read.  -1 with --three-prime: matchThreePrime aligns against the whole read (IP:501-505).
+int32_t idp_panel_window(const idp_panel *panel) {
+    if (!panel || panel->params.three_prime >= 0) return -1;
+    int32_t w = std::max(panel->max_primer_length, panel->max_seq_len + std::max(panel->params.slop, 0));
+    w = std::max(w, std::max(panel->params.k_ungapped, panel->params.k_gapped));
+    return std::max(w, 1);
+}
 int32_t idp_panel_primer_length(const idp_panel *panel, int32_t i) { return (panel && i >= 0 && i < panel->n) ? panel->plen[i] : -1; }
 uint32_t idp_panel_primer_hash(const idp_panel *panel, int32_t i) { return (panel && i >= 0 && i < panel->n) ? panel->hash[i] : 0; }
 

@@ -214,6 +214,16 @@ int    idp_classify_templates(const idp_panel *panel, const uint16_t *flags, con
 int    idp_bam_scan(const uint8_t *bam, size_t n_bytes, int32_t *n_reads, uint64_t *seq_bytes);
 int    idp_bam_to_batch(const uint8_t *bam, size_t n_bytes, uint8_t *seq4, uint64_t *seq_off, int32_t *len, int32_t *ref_idx,
                         int32_t *unclipped_start, int32_t *unclipped_end, uint16_t *flags, int32_t *rec_index);
+/* Windowed ingest for 5'-only runs (--three-prime off).  idp_panel_window is the number of leading bases (sequencing order)
+ * that can influence the Location / Ungapped / Gapped chain: max(maxPrimerLength, longest primer sequence + slop, k, K)
+ * (PM:109-110, 130, 139, 293); it is -1 when the panel has --three-prime set, because matchThreePrime aligns against the
+ * whole read (IP:501-505).  idp_bam_to_batch_window fills the same arrays as idp_bam_to_batch but keeps only that many bases
+ * of every read -- the first ones, or the last ones of a mapped reverse-strand read, whose 5' end is the end of the stored
+ * bases (PM:39-45) -- so that idp_match_batch returns the same results from a batch a fraction of the size (150 bp reads
+ * against 30 bp primers: 18 instead of 75 bytes per read over PCIe).  Arrays are sized by idp_bam_scan as before. */
+int32_t idp_panel_window(const idp_panel *panel);
+int    idp_bam_to_batch_window(const idp_panel *panel, const uint8_t *bam, size_t n_bytes, uint8_t *seq4, uint64_t *seq_off, int32_t *len,
+                               int32_t *ref_idx, int32_t *unclipped_start, int32_t *unclipped_end, uint16_t *flags, int32_t *rec_index);
 /* Host egress: the records of the same bytes with the primer-match tags set as addTagsToPair / addTagsToFragment do
  * (IP:522-569): Z-type aux fields f5 / r5 (+ f3 / r3 when --three-prime >= 0) on the primary R1 / R2 of every template, the tag
  * strings being PrimerMatch.info / "none" (idp_format_info).  five / three are the idp_match_batch results of the batch

@@ -86,6 +86,17 @@ struct ReadBatch {  // structure of arrays in the layout of idp_reads; bases sta
                                b.flags.data(), rec_index ? rec_index->data() : nullptr));
         return b;
     }
+    // the same for a run without --three-prime: only the bases the 5' chain can reach are kept (idp_bam_to_batch_window)
+    static ReadBatch fromBamWindow(const idp_panel *panel, const uint8_t *bam, size_t n_bytes, std::vector<int32_t> *rec_index = nullptr) {
+        ReadBatch b; int32_t n = 0; uint64_t bytes = 0;
+        check(idp_bam_scan(bam, n_bytes, &n, &bytes));
+        b.seq4.resize(bytes); b.seq_off.resize(n); b.len.resize(n); b.ref_idx.resize(n); b.unclipped_start.resize(n); b.unclipped_end.resize(n); b.flags.resize(n);
+        if (rec_index) rec_index->resize(n);
+        check(idp_bam_to_batch_window(panel, bam, n_bytes, b.seq4.data(), b.seq_off.data(), b.len.data(), b.ref_idx.data(), b.unclipped_start.data(),
+                                      b.unclipped_end.data(), b.flags.data(), rec_index ? rec_index->data() : nullptr));
+        if (n > 0) b.seq4.resize(b.seq_off.back() + (size_t)((b.len.back() + 1) / 2));
+        return b;
+    }
     idp_reads view() const { return idp_reads{seq4.data(), seq_off.data(), len.data(), ref_idx.data(), unclipped_start.data(), unclipped_end.data(), flags.data(), 0}; }
 };
 

@@ -211,3 +211,122 @@ def test_bam_annotate_rejects_mismatched_inputs_and_header_comments():
     co = tool.header_comments()
     assert len(co) == 3 and co[0].startswith("The f5/r5/f3/r3 tags store") and "<pair_id>,<primer_id>,<ref_name>:<start>-<end>,<strand>,<read-num>" in co[1]
     tool.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# windowed ingest (idp_bam_to_batch_window): 5'-only runs ship only the bases the chain can reach
+# ------------------------------------------------------------------------------------------------------------------
+def _unpack(batch, i):
+    import ctypes as C
+    n = int(batch.len[i])
+    buf = C.create_string_buffer(max(n, 1))
+    L.lib().idp_unpack_bases(batch.seq4.ctypes.data + int(batch.seq_off[i]), n, buf)
+    return buf.raw[:n].decode()
+
+
+def _window_panel(rng, n_pairs, min_len, max_len):
+    primers = []
+    for i in range(n_pairs):
+        for positive in (True, False):
+            n = int(rng.integers(min_len, max_len + 1))
+            seq = "".join("ACGT"[x] for x in rng.integers(0, 4, n))
+            start = 1000 * (i + 1) + (0 if positive else 300)
+            primers.append(H.Primer(f"p{i}", f"p{i}{'F' if positive else 'R'}", seq, positive, f"chr{1 + i % 5}", start, start + n - 1, i % 5))
+    return primers
+
+
+def _window_reads(rng, primers, n_reads, read_len_choices):
+    """Reads that start (in sequencing order) with a primer carrying 0-3 edits or an indel, forward / reverse-strand mapped
+    near the primer or unmapped, of several lengths (odd and even, shorter and longer than the window)."""
+    recs = []
+    for j in range(n_reads):
+        p = primers[int(rng.integers(0, len(primers)))]
+        s = list(p.sequence)
+        for _ in range(int(rng.integers(0, 4))):
+            s[int(rng.integers(0, len(s)))] = "ACGTN"[int(rng.integers(0, 5))]
+        if rng.random() < 0.25:
+            k = int(rng.integers(2, len(s) - 2))
+            s = s[:k] + (["ACGT"[int(rng.integers(0, 4))]] if rng.random() < 0.5 else []) + s[k + (1 if rng.random() < 0.5 else 0):]
+        n = int(rng.choice(read_len_choices))
+        so = ("".join(s) + "".join("ACGT"[x] for x in rng.integers(0, 4, 200)))[:n]   # sequencing order
+        kind = j % 4
+        if kind == 0:
+            recs.append(H.Rec(so, unmapped=True))
+        elif kind == 1:
+            recs.append(H.Rec(so, unmapped=True, negative=True))                 # the strand bit of an unmapped read is ignored (PM:41)
+        elif p.positive_strand:
+            recs.append(H.Rec(so, False, False, p.ref_idx, p.start + int(rng.integers(-6, 7))))
+        else:
+            end = p.end + int(rng.integers(-6, 7))
+            recs.append(H.Rec(H.revcomp(so), False, True, p.ref_idx, end - n + 1))
+    return recs
+
+
+@pytest.mark.parametrize("max_len", [25, 26])   # windows of 30 and 31 bases: even and odd
+def test_windowed_ingest_keeps_the_reachable_bases(max_len):
+    rng = np.random.default_rng(5)
+    primers = _window_panel(rng, 6, 18, max_len)
+    tool = idp.IdentifyPrimers(primers, ref_names=H.DEFAULT_DICT, device=None, ungapped_kmer_length=6, gapped_kmer_length=10)
+    w = tool.window()
+    assert w == max(len(p.sequence) for p in primers) + 5                        # sequence + slop dominates here
+    recs = _window_reads(rng, primers, 400, [12, 29, 30, 31, 32, 33, 70, 71, 150])
+    bam = recs_to_bam(recs)
+    full, rec_full = idp.ReadBatch.from_bam(bam)
+    cut, rec_cut = idp.ReadBatch.from_bam(bam, window_for=tool)
+    assert np.array_equal(rec_full, rec_cut)
+    for a in ("ref_idx", "unclipped_start", "unclipped_end", "flags"):
+        assert np.array_equal(getattr(full, a), getattr(cut, a)), a
+    assert np.array_equal(cut.len, np.minimum(full.len, w))
+    assert cut.seq4.nbytes < full.seq4.nbytes
+    for i, r in enumerate(recs):
+        stored = r.bases
+        want = stored if len(stored) <= w else (stored[-w:] if (r.negative and not r.unmapped) else stored[:w])
+        assert _unpack(cut, i) == want, (i, r)
+        if len(want) % 2:                                                        # the spare nibble is zero, as in a BAM record
+            assert cut.seq4[int(cut.seq_off[i]) + len(want) // 2] & 0x0F == 0
+    tool.close()
+    with idp.IdentifyPrimers(primers, ref_names=H.DEFAULT_DICT, device=None, three_prime=5) as t3:   # 3' matching reads the whole read
+        assert t3.window() == -1
+        with pytest.raises(idp.IdpError):
+            idp.ReadBatch.from_bam(bam, window_for=t3)
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(ungapped_kmer_length=6, gapped_kmer_length=10), dict(ungapped_kmer_length=4, slop=2, max_mismatch_rate=0.1),
+                                  dict(gapped_kmer_length=8, slop=9)])
+def test_windowed_batch_gives_the_same_results(opts):
+    """The oracle (= the reference's chain) on the whole reads and on the windowed batch: every 5' result field, the metric
+    counter and the number of alignments are identical, so shipping the window is exact."""
+    from oracle import oracle_py as O
+    rng = np.random.default_rng(11)
+    primers = _window_panel(rng, 12, 18, 27)
+    primers[3] = H.Primer(primers[3].pair_id, primers[3].primer_id, primers[3].sequence, primers[3].positive_strand, primers[3].ref_name,
+                          primers[3].start, primers[3].start + 33, primers[3].ref_idx)   # Primer.length 34 > its sequence (PR:206)
+    recs = _window_reads(rng, primers, 1200, [8, 20, 33, 34, 35, 39, 40, 41, 75, 150])
+    for i in range(0, len(recs) - 1, 3):                                        # some templates are pairs
+        recs[i].paired = recs[i + 1].paired = True
+        recs[i].first, recs[i + 1].second, recs[i].mate_next = True, True, True
+    tool = idp.IdentifyPrimers(primers, ref_names=H.DEFAULT_DICT, device=None, **opts)
+    bam = recs_to_bam(recs)
+    full, _ = idp.ReadBatch.from_bam(bam)
+    cut, _ = idp.ReadBatch.from_bam(bam, window_for=tool)
+    w = tool.window()
+    assert w >= 34 + 0 and int(cut.len.max()) == w
+    params = O.make_params(slop=opts.get("slop", 5), max_mismatch_rate=opts.get("max_mismatch_rate", 0.05),
+                           k_ungapped=opts.get("ungapped_kmer_length"), k_gapped=opts.get("gapped_kmer_length"))
+    panel = O.Panel(primers, params)
+
+    def arrays(batch):
+        bases = "".join(_unpack(batch, i) for i in range(len(batch.len)))
+        off = np.zeros(len(batch.len) + 1, dtype=np.int64)
+        off[1:] = np.cumsum(batch.len)
+        return dict(bases=np.frombuffer(bases.encode(), dtype=np.uint8).copy(), off=off, ref_idx=batch.ref_idx, ustart=batch.unclipped_start,
+                    uend=batch.unclipped_end, flags=batch.flags)
+
+    want5, _, want_metrics, want_align = panel.process_batch(arrays(full), n_threads=4)
+    got5, _, got_metrics, got_align = panel.process_batch(arrays(cut), n_threads=4)
+    for f in want5.dtype.names:
+        assert np.array_equal(got5[f], want5[f]), f
+    assert np.array_equal(got_metrics, want_metrics) and got_align == want_align
+    types = set(int(t) for t in want5["type"])
+    assert {0, 1, 2, 3} <= types                                                 # none, location, ungapped and gapped all occur
+    tool.close()
