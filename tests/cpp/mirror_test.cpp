@@ -1,5 +1,6 @@
 // C++ host-mirror test, written the way the reference's own ScalaTest suites read (PrimerTest, PrimerMatcherTest,
 // PrimerMatchTest, IdentifyPrimersTest).  "host" mode needs no GPU; "gpu" mode runs the end-to-end known answers.
+#include <cstring>
 #include <algorithm>
 #include <cassert>
 #include <cstdio>
@@ -64,6 +65,25 @@ static void host_tests() {
     r.type = IDP_NONE;
     EXPECT(tool.info(r, 0) == "none");
     EXPECT(throws([&] { tool.processBatch(ReadBatch()); }));  // host-only: matching must fail loudly
+    // windowed ingest: 10-base primers (Primer.length 10), slop 5 -> the 5' chain reaches 15 bases of a read
+    EXPECT(idp_panel_window(tool.panel()) == 15);
+    {
+        // one unmapped 24-base record, built by hand (SAMv1 4.2): block_size, then the fixed fields, name, no cigar, seq, qual
+        const std::string bases = "ACGTACGTACGTACGTTTTTGGGG", name = "q";
+        std::vector<uint8_t> rec(4 + 32 + name.size() + 1 + (bases.size() + 1) / 2 + bases.size(), 0);
+        auto put32 = [&](size_t at, int32_t v) { std::memcpy(rec.data() + at, &v, 4); };
+        put32(0, (int32_t)rec.size() - 4); put32(4, -1); put32(8, -1);
+        rec[12] = (uint8_t)(name.size() + 1);
+        const uint16_t flag = 0x4; std::memcpy(rec.data() + 18, &flag, 2);
+        put32(20, (int32_t)bases.size()); put32(24, -1); put32(28, -1);
+        std::memcpy(rec.data() + 36, name.c_str(), name.size() + 1);
+        idp_pack_bases(bases.data(), (int32_t)bases.size(), rec.data() + 36 + name.size() + 1);
+        const ReadBatch whole = ReadBatch::fromBam(rec.data(), rec.size()), cut = ReadBatch::fromBamWindow(tool.panel(), rec.data(), rec.size());
+        EXPECT(whole.len[0] == 24 && cut.len[0] == 15 && cut.seq4.size() == 8 && cut.flags[0] == whole.flags[0]);
+        char back[16] = {0};
+        idp_unpack_bases(cut.seq4.data(), 15, back);
+        EXPECT(std::string(back, 15) == bases.substr(0, 15));
+    }
     std::puts("OK host");
 }
 
