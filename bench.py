@@ -160,6 +160,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=10_000_000, help="read pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gapped-stress", action="store_true")
+    ap.add_argument("--e2e-window", action="store_true",
+                    help="also time idp_match_batch on the windowed batch (idp_panel_window bases per read; 5'-only workloads)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = max(args.warmup, 1)
@@ -206,6 +208,13 @@ def main():
     h_loc = [torch.empty(n_reads, dtype=torch.int32, pin_memory=True) for _ in range(3)] if w["mapped"] else None
     h_five = torch.empty((n_reads, 32), dtype=torch.uint8, pin_memory=True)
     h_three = torch.empty((n_reads, 32), dtype=torch.uint8, pin_memory=True) if opts.get("three_prime", -1) >= 0 else None
+    # opt-in: the same reads cut to the bases the 5' chain can reach (what idp_bam_to_batch_window ships), for `e2e_window`
+    win = 0
+    if args.e2e_window and opts.get("three_prime", -1) < 0:
+        ks = [k for k in (opts.get("ungapped_kmer_length"), opts.get("gapped_kmer_length")) if k]
+        win = max([max(p.length for p in panel.primers), max(len(p.sequence) for p in panel.primers) + opts.get("slop", 5)] + ks)
+        win = min(win, 150)
+    h_win = torch.empty((n_reads, (win + 1) // 2), dtype=torch.uint8, pin_memory=True) if win else None
     t_gen = time.perf_counter()
     chunk = 1_000_000
     sample_reads = None
@@ -214,6 +223,10 @@ def main():
         rd = synth.make_reads(panel, n, w["read_seed"] + 1000 * rank + ci, indel_frac=w["indel_frac"], mapped_frac=w["mapped_frac"])
         h_seq4.numpy()[2 * lo:2 * (lo + n)] = rd.seq4()
         h_flags.numpy().view(np.uint16)[2 * lo:2 * (lo + n)] = rd.flags
+        if win:  # first `win` stored bases, or the last ones of a mapped reverse-strand read (PM:39-45)
+            from_end = ((rd.flags & 0x4) == 0) & ((rd.flags & 0x10) != 0)
+            cw = np.where(from_end[:, None], rd.codes[:, 150 - win:], rd.codes[:, :win])
+            h_win.numpy()[2 * lo:2 * (lo + n)] = synth.pack_fixed(cw)
         if h_loc is not None:
             for t, a in zip(h_loc, (rd.ref_idx, rd.ustart, rd.uend)):
                 t.numpy()[2 * lo:2 * (lo + n)] = a
@@ -345,6 +358,35 @@ def main():
     sw_ms = out["stages_ms"]["ms_sw_score"]
     if sw_ms > 0 and out["work"]["sw_cells"] > 0:
         out["gapped"] = {"gcups": out["work"]["sw_cells"] / (sw_ms / 1e3) / 1e9, "cells": out["work"]["sw_cells"], "sw_kernel_ms": sw_ms, "workload": args.workload}
+
+    if win:
+        try:
+            assert tool.window() == win, (tool.window(), win)
+            h_five_full = h_five.numpy().copy()
+            wb = idp.ReadBatch.__new__(idp.ReadBatch)
+            wb.seq4, wb.flags = h_win.numpy().reshape(-1), h_flags.numpy().view(np.uint16)
+            wb.seq_off = wb.len = None
+            wb.fixed_len = win
+            wb.ref_idx, wb.unclipped_start, wb.unclipped_end = ([t.numpy() for t in h_loc] if h_loc else [None] * 3)
+
+            def step_e2e_window():
+                keep = []
+                rs = wb.as_struct(keep)
+                metrics = np.zeros(160, dtype=np.int64)
+                n_align = np.zeros(1, dtype=np.int64)
+                L.check(L.lib().idp_match_batch(tool._ctx, C.byref(rs), n_reads, h_five.data_ptr(), None, metrics.ctypes.data, n_align.ctypes.data))
+                if world > 1:
+                    metrics_dev.copy_(torch.from_numpy(metrics))
+                    dist.all_reduce(metrics_dev)
+                return tool.timings()
+
+            ms_w, tm_w = timed(step_e2e_window, False)
+            out["e2e_window"] = {"value": world * n_pairs * args.steps / (ms_w / 1e3), "unit": UNIT, "window_bases": win,
+                                 "h2d_bytes_per_step": int(tm_w[-1]["h2d_bytes"]), "d2h_bytes_per_step": int(tm_w[-1]["d2h_bytes"]),
+                                 "ms_per_step": ms_w / args.steps,
+                                 "same_results_as_whole_reads": bool(np.array_equal(h_five.numpy(), h_five_full))}
+        except Exception as e:  # pragma: no cover
+            out["e2e_window"] = {"error": repr(e)}
 
     if rank == 0 and world == 1 and not args.no_gapped_stress:
         # gapped-alignment stress: no -K filter, every fall-through read aligns against all 2000 primers
