@@ -8,11 +8,12 @@
 // after the prologue.  The panel side sits in shared memory as far as it fits.
 //
 // Two ways to find the accepted primers of a read, both exact:
-//  * bit-sliced (DevPanel::bs_ok: every primer tolerates at most one mismatch): the read's first 16 bases index precomputed
+//  * bit-sliced (DevPanel::bs_ok: every primer tolerates at most one mismatch): the read's first 12 bases index precomputed
 //    32-primer mismatch bit-vectors; two bit planes (seen one / seen two mismatches) decide 32 primers per instruction with no
 //    divergence.  The few survivors get the full mismatchAlign.  The k-mer rule is then applied to what was ACCEPTED: no
 //    accepted primer -> no match whatever the candidates were; one -> it only has to be a candidate (a run of k equal
-//    letters on the diagonal proves it, else an exact membership walk); two or more -> the exact walk below decides order.
+//    letters on the diagonal proves it: looked up in DevPanel::diag by the position of the mismatch, or tested on the
+//    letters; else an exact membership walk); two or more -> the exact walk below decides order.
 //  * exact walk (any thresholds): read k-mers in order, posting lists in the reference's Set iteration order, an 8-byte
 //    posting head rejects most candidates, survivors are evaluated after the loop in first-hit order.
 #pragma once
