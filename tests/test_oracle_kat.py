@@ -211,3 +211,47 @@ def test_kmer_rule_follows_the_mismatch_position():
     five, _, _, _ = panel.process_batch(H.recs_to_arrays(recs), n_threads=1)
     got = [int(t) == 2 and int(p) == 0 for t, p in zip(five["type"], five["primer"])]   # 2 = ungapped match to p+
     assert got == expect
+
+
+def test_three_prime_candidate_rules_from_first_principles():
+    """matchThreePrime (IdentifyPrimers.scala:483-516), no GPU: which primers are aligned against the reverse complement of
+    the WHOLE read (the target-length quirk, :501-505) in Local mode -- the mate's 5' primer if it has one, else the opposite
+    strand primers of the read's own pair, else every primer -- on read-through amplicons where the answer is evident."""
+    rng = np.random.default_rng(3)
+
+    def rnd(n):
+        return "".join("ACGT"[x] for x in rng.integers(0, 4, n))
+
+    fwd = [rnd(22), rnd(24)]
+    rev = [rnd(23), rnd(21)]
+    primers = []
+    for i in range(2):
+        primers.append(H.Primer(f"a{i}", f"a{i}F", fwd[i], True))
+        primers.append(H.Primer(f"a{i}", f"a{i}R", rev[i], False))
+    panel = O.Panel(primers, O.make_params(three_prime=5))
+    insert = rnd(30)
+    r1 = fwd[0] + insert + H.revcomp(rev[0])                 # reads through the whole amplicon 0
+    r2 = rev[0] + H.revcomp(insert) + H.revcomp(fwd[0])
+    junk = rnd(len(r1))
+    tail_only = rnd(40) + H.revcomp(rev[1])                  # no 5' primer, the reverse primer of amplicon 1 at its 3' end
+    recs = [
+        H.Rec(r1, True, paired=True, first=True, mate_next=True), H.Rec(r2, True, paired=True, second=True),      # both 5' ends match
+        H.Rec(r1, True, paired=True, first=True, mate_next=True), H.Rec(junk, True, paired=True, second=True),    # only R1 matches
+        H.Rec(tail_only, True, paired=True, first=True, mate_next=True), H.Rec(junk, True, paired=True, second=True),  # neither
+        H.Rec(tail_only, True),                                                                                   # a fragment
+    ]
+    five, three, _, _ = panel.process_batch(H.recs_to_arrays(recs), n_threads=1)
+    F0, R0, F1, R1 = 0, 1, 2, 3
+    assert [int(p) for p in five["primer"]] == [F0, R0, F0, -1, -1, -1, -1]
+    # template 1: each read is checked against its MATE's 5' primer only, found at the start of the reversed read
+    assert (int(three["primer"][0]), int(three["raw_score"][0]), int(three["t_start"][0]), int(three["t_end"][0])) == (R0, len(rev[0]), 1, len(rev[0]))
+    assert (int(three["primer"][1]), int(three["raw_score"][1]), int(three["t_start"][1]), int(three["t_end"][1])) == (F0, len(fwd[0]), 1, len(fwd[0]))
+    assert int(three["multi"][0]) == 0 and int(three["multi"][1]) == 0
+    # template 2: R1 has no mate match -> the opposite-strand primer of its own pair; R2 -> its mate's primer (F0), which a
+    # random read only matches by chance: a short local hit, still reported (min rate 0.01)
+    assert int(three["primer"][2]) == R0 and int(three["raw_score"][2]) == len(rev[0])
+    assert int(three["primer"][3]) in (F0, -1) and int(three["raw_score"][3]) < 12
+    # template 3 and the fragment: nothing matched at 5' -> every primer is aligned; R1 of amplicon 1 wins with a full score
+    for i in (4, 6):
+        assert (int(three["primer"][i]), int(three["raw_score"][i]), int(three["t_start"][i]), int(three["t_end"][i])) == (R1, len(rev[1]), 1, len(rev[1]))
+        assert int(three["multi"][i]) == 1 and int(three["q_len"][i]) == len(rev[1])
