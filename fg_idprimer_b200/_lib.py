@@ -20,7 +20,7 @@ MODE_LOCAL, MODE_GLOCAL, MODE_GLOBAL = 0, 1, 3
 EXPORTS = ["idp_abi_version", "idp_last_error", "idp_device_count", "idp_panel_create", "idp_panel_destroy", "idp_panel_size",
            "idp_panel_primer_length", "idp_panel_primer_hash", "idp_panel_kmer_postings", "idp_ctx_create", "idp_ctx_destroy",
            "idp_ctx_set_stream", "idp_ctx_timings", "idp_host_alloc", "idp_host_free", "idp_match_batch", "idp_match_batch_device",
-           "idp_align_batch", "idp_result_score", "idp_result_second", "idp_metric_bin", "idp_summary_metrics", "idp_format_info",
+           "idp_match_batch16", "idp_match_batch16_device", "idp_result16_unpack", "idp_align_batch", "idp_result_score", "idp_result_second", "idp_metric_bin", "idp_summary_metrics", "idp_format_info",
            "idp_pack_bases", "idp_unpack_bases", "idp_classify_primer_pair", "idp_classify_templates", "idp_bam_scan", "idp_bam_to_batch", "idp_bam_to_batch_window", "idp_panel_window",
            "idp_bam_annotate", "idp_header_comments"]
 
@@ -45,13 +45,26 @@ class IdpTimings(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_scan", C.c_float), ("ms_gapped", C.c_float), ("ms_three_prime", C.c_float),
                 ("ms_sw_score", C.c_float), ("n_reads", C.c_int64), ("n_fallthrough", C.c_int64), ("n_alignments_5p", C.c_int64),
                 ("n_alignments_3p", C.c_int64), ("sw_cells", C.c_int64), ("scan_base_compares", C.c_int64),
-                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("n_scan_parked", C.c_int64)]
 
 
 RESULT_DTYPE = np.dtype([("primer", "<i4"), ("type", "u1"), ("status", "u1"), ("multi", "u1"), ("reserved", "u1"),
                          ("mm", "<i4"), ("next_mm", "<i4"), ("raw_score", "<i4"), ("raw_next", "<i4"),
                          ("q_len", "<i2"), ("q_len_next", "<i2"), ("t_start", "<i2"), ("t_end", "<i2")])
 assert RESULT_DTYPE.itemsize == 32
+# idp_result16: head = primer + 1 (bits 0..23) | type << 24 | multi << 26 | status << 27
+RESULT16_DTYPE = np.dtype([("head", "<u4"), ("a", "<i2"), ("b", "<i2"), ("q_len", "<u2"), ("q_len_next", "<u2"),
+                           ("t_start", "<u2"), ("t_end", "<u2")])
+assert RESULT16_DTYPE.itemsize == 16
+NEXT16_NA = 32767
+
+
+def unpack16(rows: np.ndarray) -> np.ndarray:
+    """idp_result16 rows -> idp_result rows (idp_result16_unpack)."""
+    rows = np.ascontiguousarray(rows, dtype=RESULT16_DTYPE)
+    out = np.zeros(len(rows), dtype=RESULT_DTYPE)
+    lib().idp_result16_unpack(rows.ctypes.data, len(rows), out.ctypes.data)
+    return out
 
 _lib = None
 
@@ -87,8 +100,10 @@ def lib() -> C.CDLL:
     L.idp_host_alloc.argtypes = [C.c_size_t]
     L.idp_host_alloc.restype = C.c_void_p
     L.idp_host_free.argtypes = [C.c_void_p]
-    for fn in (L.idp_match_batch, L.idp_match_batch_device):
+    for fn in (L.idp_match_batch, L.idp_match_batch_device, L.idp_match_batch16, L.idp_match_batch16_device):
         fn.argtypes = [C.c_void_p, C.POINTER(IdpReads), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.idp_result16_unpack.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    L.idp_result16_unpack.restype = None
     L.idp_align_batch.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p]
     L.idp_result_score.argtypes = [C.c_void_p]

@@ -200,7 +200,23 @@ class ReadBatch:
         return seq4.astype(np.uint8), boff[:-1].astype(np.uint64), lens.astype(np.int32)
 
     @classmethod
-    def from_ascii(cls, bases, off, flags, ref_idx=None, unclipped_start=None, unclipped_end=None) -> "ReadBatch":
+    def from_ascii(cls, bases, off, flags, ref_idx=None, unclipped_start=None, unclipped_end=None, window: int = 0) -> "ReadBatch":
+        """window > 0 (IdentifyPrimers.window() of a tool without --three-prime): keep only that many bases of every read --
+        the first ones, or the last ones of a mapped reverse-strand read, whose 5' end is the end of the stored bases
+        (PM:39-45) -- as idp_bam_to_batch_window does."""
+        if window > 0:
+            bases = np.asarray(bases, dtype=np.uint8)
+            off = np.asarray(off, dtype=np.int64)
+            fl = np.asarray(flags, dtype=np.uint16)
+            lens = np.diff(off)
+            keep = np.minimum(lens, window)
+            from_end = ((fl & L.F_UNMAPPED) == 0) & ((fl & L.F_REVERSE) != 0)
+            start = off[:-1] + np.where(from_end, lens - keep, 0)
+            new_off = np.zeros(len(lens) + 1, dtype=np.int64)
+            new_off[1:] = np.cumsum(keep)
+            read_of = np.repeat(np.arange(len(lens)), keep)
+            src = start[read_of] + (np.arange(int(new_off[-1])) - new_off[read_of])
+            bases, off = bases[src], new_off
         seq4, boff, lens = cls.pack(bases, off)
         return cls(seq4, flags, boff, lens, ref_idx, unclipped_start, unclipped_end)
 
@@ -322,25 +338,33 @@ class IdentifyPrimers:
         if not self._ctx.value:
             raise RuntimeError("this IdentifyPrimers was created with device=None (host-only panel); matching needs a GPU context")
 
-    def process_batch(self, reads: ReadBatch):
-        """processBatch (IP:381-436): returns (five, three) result arrays; adds to metric_counter / num_alignments."""
+    def process_batch(self, reads: ReadBatch, compact: bool = False):
+        """processBatch (IP:381-436): returns (five, three) result arrays; adds to metric_counter / num_alignments.
+        compact=True goes through idp_match_batch16 (16-byte records over the bus) and unpacks them on the host: the rows
+        returned are the same idp_result rows either way."""
         self._require_ctx()
         keep = []
         rs = reads.as_struct(keep)
         n = len(reads)
-        five = np.zeros(n, dtype=L.RESULT_DTYPE)
-        three = np.zeros(n, dtype=L.RESULT_DTYPE) if self.three_prime >= 0 else None
+        dt = L.RESULT16_DTYPE if compact else L.RESULT_DTYPE
+        five = np.zeros(n, dtype=dt)
+        three = np.zeros(n, dtype=dt) if self.three_prime >= 0 else None
         metrics = np.zeros(160, dtype=np.int64)
         n_align = np.zeros(1, dtype=np.int64)
-        L.check(L.lib().idp_match_batch(self._ctx, C.byref(rs), n, five.ctypes.data, None if three is None else three.ctypes.data,
-                                        metrics.ctypes.data, n_align.ctypes.data))
+        fn = L.lib().idp_match_batch16 if compact else L.lib().idp_match_batch
+        L.check(fn(self._ctx, C.byref(rs), n, five.ctypes.data, None if three is None else three.ctypes.data,
+                   metrics.ctypes.data, n_align.ctypes.data))
         self.metric_counter += metrics
         self.num_alignments += int(n_align[0])
+        if compact:
+            five, three = L.unpack16(five), (None if three is None else L.unpack16(three))
         return five, three
 
     def process_batch_device(self, n: int, seq4_ptr: int, flags_ptr: int, five_ptr: int, three_ptr: int = 0, fixed_len: int = 0,
-                             seq_off_ptr: int = 0, len_ptr: int = 0, ref_idx_ptr: int = 0, ustart_ptr: int = 0, uend_ptr: int = 0):
-        """The same with device-resident reads and results (raw device pointers, e.g. torch tensors' data_ptr())."""
+                             seq_off_ptr: int = 0, len_ptr: int = 0, ref_idx_ptr: int = 0, ustart_ptr: int = 0, uend_ptr: int = 0,
+                             compact: bool = False):
+        """The same with device-resident reads and results (raw device pointers, e.g. torch tensors' data_ptr());
+        compact=True: five_ptr / three_ptr receive idp_result16 records."""
         self._require_ctx()
         rs = L.IdpReads()
         rs.seq4, rs.seq_off, rs.len = seq4_ptr, seq_off_ptr or None, len_ptr or None
@@ -348,7 +372,8 @@ class IdentifyPrimers:
         rs.flags, rs.fixed_len = flags_ptr, fixed_len
         metrics = np.zeros(160, dtype=np.int64)
         n_align = np.zeros(1, dtype=np.int64)
-        L.check(L.lib().idp_match_batch_device(self._ctx, C.byref(rs), n, five_ptr, three_ptr or None, metrics.ctypes.data, n_align.ctypes.data))
+        fn = L.lib().idp_match_batch16_device if compact else L.lib().idp_match_batch_device
+        L.check(fn(self._ctx, C.byref(rs), n, five_ptr, three_ptr or None, metrics.ctypes.data, n_align.ctypes.data))
         self.metric_counter += metrics
         self.num_alignments += int(n_align[0])
         return metrics, int(n_align[0])

@@ -5,7 +5,7 @@
 #include <cstring>
 #include <vector>
 
-#include "idp_kernels.cuh"
+#include "idp_launch.h"
 
 namespace idp {
 
@@ -37,12 +37,17 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// Pageable host data -> device.  With a stream the copy is ordered on it (kernels launched there afterwards see the data);
+// without one it goes through the legacy default stream, which the contexts' non-blocking streams do NOT order against:
+// the caller then synchronises the device before anything is launched (upload_panel does).
 template <class T>
-static int upload(const std::vector<T> &v, DevBuf &b, size_t min_elems = 1) {
+static int upload(const std::vector<T> &v, DevBuf &b, size_t min_elems = 1, cudaStream_t st = nullptr, bool on_stream = false) {
     size_t n = std::max(v.size(), min_elems);
     int rc = b.ensure(n * sizeof(T));
     if (rc) return rc;
-    if (!v.empty()) CUDA_TRY(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (v.empty()) return IDP_OK;
+    if (on_stream) CUDA_TRY(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    else CUDA_TRY(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return IDP_OK;
 }
 
@@ -72,22 +77,24 @@ using namespace idp;
 
 struct idp_ctx {
     const idp_panel *panel = nullptr;
-    int device = 0, sm_count = 148;
-    DevPanel dp{};
-    DevBuf b_qbot, b_bylen, b_pmask, b_pinfo, b_positive, b_loc_key[2], b_loc_primer[2], b_mate_off, b_mate_idx, b_smat;
+    int device = 0;
+    LaunchCfg cfg{};
+    DevBuf b_fx, b_qbot, b_bylen, b_pmask, b_pinfo, b_positive, b_loc_key[2], b_loc_primer[2], b_mate_off, b_mate_idx, b_smat;
     DevBuf b_keys[2], b_offcnt[2], b_postings[2], b_heads[2], b_direct[2], b_bsmm, b_bsacc, b_seedtab, b_seedlist, b_diag;
     Slot slots[kSlots];
     cudaStream_t user_stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_finish = nullptr;  // first copy / last harvest of an idp_match_batch call
     idp_timings last{};
-    int rw = 4, nq = 32;
-    bool scan_stats = false;  // count base comparisons in the scan kernel (IDP_SCAN_STATS=1 when the context is created)
+    bool compact_ok = false;  // every value of this panel's results fits idp_result16
+    // idp_align_batch staging (device + pinned host), grown on demand and kept
+    DevBuf al_q, al_ql, al_t, al_to, al_tl, al_out;
 };
 
 namespace idp {
 
 static int upload_panel(idp_ctx *c) {
     const idp_panel &p = *c->panel;
-    DevPanel &d = c->dp;
+    DevPanel &d = c->cfg.dp;
     int rc;
     d.n_primers = p.n; d.ww = p.ww; d.window_bases = p.window_bases; d.max_seq_len = p.max_seq_len;
     if ((rc = upload(p.pmask, c->b_pmask))) return rc;
@@ -159,6 +166,11 @@ static int upload_panel(idp_ctx *c) {
         d.seed_tab = c->b_seedtab.as<uint32_t>(); d.seed_list = c->b_seedlist.as<uint32_t>();
         d.seed_ok = 1; d.seed_S = p.seed_S; d.seed_shift = p.seed_shift; d.seed_slots = p.seed_slots;
     }
+    d.fx_tab = nullptr; d.fx_shift = 0; d.fx_slots = 0; d.fx_mul = p.fx_mul;
+    if (!p.fx_tab.empty() && d.bs_ok) {
+        if ((rc = upload(p.fx_tab, c->b_fx))) return rc;
+        d.fx_tab = c->b_fx.as<uint16_t>(); d.fx_shift = p.fx_shift; d.fx_slots = p.fx_slots;
+    }
     if ((rc = upload(p.mate_off, c->b_mate_off))) return rc;
     if ((rc = upload(p.mate_idx, c->b_mate_idx))) return rc;
     d.mate_off = c->b_mate_off.as<int32_t>(); d.mate_idx = c->b_mate_idx.as<int32_t>();
@@ -184,14 +196,15 @@ static int upload_panel(idp_ctx *c) {
     d.slop = p.params.slop; d.three_prime = p.params.three_prime;
     d.max_mismatch_rate = p.params.max_mismatch_rate; d.min_alignment_score_rate = p.params.min_alignment_score_rate;
     const int wb = p.window_bases;
-    c->rw = wb <= 32 ? 4 : wb <= 40 ? 5 : wb <= 64 ? 8 : wb <= 128 ? 16 : 32;
-    c->nq = p.max_seq_len <= 32 ? 32 : p.max_seq_len <= 64 ? 64 : 0;
+    c->cfg.rw = wb <= 32 ? 4 : wb <= 40 ? 5 : wb <= 64 ? 8 : wb <= 128 ? 16 : 32;
+    c->cfg.nq = p.max_seq_len <= 32 ? 32 : p.max_seq_len <= 64 ? 64 : 0;
+    const int nq = c->cfg.nq;
     d.qbot = nullptr;
-    if (c->nq > 0) {  // primers bottom-aligned in nq rows for the register-resident aligners
-        const int words = c->nq / 8;
+    if (nq > 0) {  // primers bottom-aligned in nq rows for the register-resident aligners
+        const int words = nq / 8;
         std::vector<uint32_t> qbot((size_t)p.n * words, 0u);
         for (int i = 0; i < p.n; ++i) {
-            const int off = c->nq - p.seq_len[i];
+            const int off = nq - p.seq_len[i];
             for (int b = 0; b < p.seq_len[i]; ++b) {
                 const uint32_t nib = (p.pmask[(size_t)i * p.ww + b / 8] >> (4 * (b % 8))) & 15u;
                 qbot[(size_t)i * words + (off + b) / 8] |= nib << (4 * ((off + b) % 8));
@@ -207,137 +220,23 @@ static int upload_panel(idp_ctx *c) {
         if ((rc = upload(order, c->b_bylen))) return rc;
         d.by_len = c->b_bylen.as<uint32_t>();
     }
+    {   // idp_result16: scores in 16 bits, primer + 1 in 24 bits.  |Alignment.score| <= largest |score| * (rows + columns); the
+        // 5' target has at most max_seq_len + slop columns and a Local (3') score lies in [0, match * rows]
+        long maxabs = std::max<long>({std::labs(d.match_score), std::labs(d.mismatch_score), std::labs((long)d.gap_open + d.gap_extend), std::labs(d.gap_extend)});
+        for (int32_t v : p.smat16) if (v != INT32_MIN) maxabs = std::max<long>(maxabs, std::labs((long)v));
+        c->compact_ok = p.n < (1 << 24) - 1 && maxabs * (2L * p.max_seq_len + std::max(p.params.slop, 0) + 2L) < 32767L;
+    }
+    // the copies above went through the legacy default stream; the contexts' streams are non-blocking and do not order
+    // against it, so nothing may be launched before they have landed
+    CUDA_TRY(cudaDeviceSynchronize());
     return IDP_OK;
 }
 
-template <int RW, bool FAST>
-static int launch_scan_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp_result *five, uint8_t *rtype, unsigned *fall, Counters *ctr) {
-    // shared-memory plan: the per-warp read tiles first (two buffers each), then as much of the panel side as fits in half
-    // an SM (two CTAs per SM)
-    ScanLaunch S{};
-    const DevKmerIndex &ix = c->dp.kidx[0];
-    const size_t budget = (size_t)(224 * 1024 / kScanMinBlocks - 1024);
-    size_t used = 0;
-    S.stride = R.fixed_len > 0 ? (uint32_t)((R.fixed_len + 1) >> 1) : 0;
-    // a warp tile is 32 reads: 32 * stride bytes, always a multiple of 16 as the TMA bulk copy requires
-    S.stage_tile = R.fixed_len > 0 && (reinterpret_cast<uintptr_t>(R.seq4) & 15) == 0;
-    if (S.stage_tile) {
-        // 32 reads, slack for the last read's window words, then the tile's 32 flag words
-        S.flags_off = (uint32_t)((32 * (size_t)S.stride + 4 * RW + 16 + 15) & ~size_t(15));
-        S.tile_smem_bytes = S.flags_off + 64;
-        S.stage_flags = (reinterpret_cast<uintptr_t>(R.flags) & 15) == 0;
-        used = (size_t)S.tile_smem_bytes * 2 * kScanWarps;
-        if (used > budget - 16 * 1024) { S.stage_tile = 0; S.tile_smem_bytes = 0; used = 0; }
-    }
-    auto place = [&](size_t bytes, bool wanted, size_t align = 16) -> uint32_t {
-        bytes = (bytes + 15) & ~size_t(15);
-        const size_t at = (used + align - 1) & ~(align - 1);
-        if (!wanted || bytes == 0 || at + bytes > budget) return 0xFFFFFFFFu;
-        used = at + bytes;
-        return (uint32_t)at;
-    };
-    S.direct_entries = ix.direct ? (1u << (2 * ix.k)) : 0;
-    S.off_bsacc = place((size_t)c->dp.bs_groups * sizeof(uint2), FAST);
-    S.off_bsmm = place((size_t)c->dp.bs_groups * kBsStride * 16 * 4, FAST, 128);  // 128-byte aligned: table offsets are OR-ed in
-    S.off_seed = place((size_t)c->dp.seed_slots * 2 * 4, FAST && c->dp.seed_ok && c->dp.seed_slots <= 2048);
-    S.off_direct = place((size_t)S.direct_entries * 4, !FAST && ix.direct != nullptr);
-    S.off_diag = place((size_t)c->dp.n_primers * sizeof(uint2), FAST && c->dp.diag != nullptr);
-    S.off_pinfo = place((size_t)c->dp.n_primers * sizeof(int4), true);
-    S.off_pmask = place((size_t)c->dp.n_primers * c->dp.ww * 4, true);
-    S.off_heads = place((size_t)ix.n_postings * 8, !FAST && ix.k > 0);
-    const int n_tiles = (R.n + kScanThreads - 1) / kScanThreads;
-    const int grid = std::max(1, std::min(n_tiles, kScanMinBlocks * c->sm_count));
-    const bool onchip = FAST && S.stage_tile;
-    auto launch = [&](auto kernel) -> int {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(scan_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
-            return IDP_ERR_CUDA;
-        }
-        kernel<<<grid, kScanThreads, used, st>>>(c->dp, R, S, five, rtype, fall, ctr);
-        return IDP_OK;
-    };
-    if (c->scan_stats) {  // idp_timings.scan_base_compares wanted (IDP_SCAN_STATS=1): the counting variant of the kernel
-        if (FAST && onchip) return launch(scan_kernel<RW, FAST, FAST, true>);
-        return launch(scan_kernel<RW, FAST, false, true>);
-    }
-    if (FAST && onchip) return launch(scan_kernel<RW, FAST, FAST, false>);
-    return launch(scan_kernel<RW, FAST, false, false>);
-}
-template <int RW>
-static int launch_scan(const idp_ctx *c, cudaStream_t st, const DevReads &R, idp_result *five, uint8_t *rtype, unsigned *fall, Counters *ctr) {
-    if (RW <= 8 && c->dp.bs_ok && !getenv("IDP_SCAN_EXACT_WALK")) return launch_scan_t<(RW <= 8 ? RW : 8), true>(c, st, R, five, rtype, fall, ctr);
-    return launch_scan_t<RW, false>(c, st, R, five, rtype, fall, ctr);
-}
-
-// the pair kernel also produces the traceback-equivalent (start, end) when the packed register variant applies
-static bool pairs_trace(const idp_ctx *c) { return c->nq > 0 && c->dp.packed_trace_ok && c->dp.smat == nullptr; }
-
-template <bool LOCAL, bool SMAT>
-static void launch_sw_pairs_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, const unsigned *work_read, Counters *ctr,
-                              const unsigned *pw, const unsigned *pp, int *ps, unsigned *pse, unsigned cap) {
-    const int grid = c->sm_count * 8;
-    if (!SMAT && pairs_trace(c)) {
-        if (c->nq == 32) sw_pairs_kernel<32, LOCAL, false, true><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, pse, cap);
-        else sw_pairs_kernel<64, LOCAL, false, true><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, pse, cap);
-        return;
-    }
-    switch (c->nq) {
-        case 32: sw_pairs_kernel<32, LOCAL, SMAT, false><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, pse, cap); break;
-        case 64: sw_pairs_kernel<64, LOCAL, SMAT, false><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, pse, cap); break;
-        default: sw_pairs_kernel<0, LOCAL, SMAT, false><<<grid, 128, 0, st>>>(c->dp, R, work_read, ctr, pw, pp, ps, pse, cap); break;
-    }
-}
-static void launch_sw_pairs(const idp_ctx *c, cudaStream_t st, bool local, const DevReads &R, const unsigned *work_read, Counters *ctr,
-                            const unsigned *pw, const unsigned *pp, int *ps, unsigned *pse, unsigned cap) {
-    const bool smat = c->dp.smat != nullptr;
-    if (local) { if (smat) launch_sw_pairs_t<true, true>(c, st, R, work_read, ctr, pw, pp, ps, pse, cap); else launch_sw_pairs_t<true, false>(c, st, R, work_read, ctr, pw, pp, ps, pse, cap); }
-    else { if (smat) launch_sw_pairs_t<false, true>(c, st, R, work_read, ctr, pw, pp, ps, pse, cap); else launch_sw_pairs_t<false, false>(c, st, R, work_read, ctr, pw, pp, ps, pse, cap); }
-}
-
-template <bool LOCAL, bool SMAT>
-static void launch_sw_all_t(const idp_ctx *c, cudaStream_t st, const DevReads &R, const unsigned *work_read, const unsigned *n_work,
-                            Fin *fin, Counters *ctr, int as5) {
-    const int threads = c->dp.n_primers <= 32 ? 32 : c->dp.n_primers <= 64 ? 64 : 128;
-    const int grid = c->sm_count * (threads == 128 ? 8 : threads == 64 ? 16 : 32);
-    const bool packed = !SMAT && (LOCAL ? c->dp.fits16_local : c->dp.fits16_glocal);  // two alignments per register
-    switch (c->nq) {
-        case 32:
-            if (packed) sw_all_kernel<32, LOCAL, SMAT, !SMAT><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5);
-            else sw_all_kernel<32, LOCAL, SMAT, false><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5);
-            break;
-        case 64:
-            if (packed) sw_all_kernel<64, LOCAL, SMAT, !SMAT><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5);
-            else sw_all_kernel<64, LOCAL, SMAT, false><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5);
-            break;
-        default: sw_all_kernel<0, LOCAL, SMAT, false><<<grid, threads, 0, st>>>(c->dp, R, work_read, n_work, fin, ctr, as5); break;
-    }
-}
-static void launch_sw_all(const idp_ctx *c, cudaStream_t st, bool local, const DevReads &R, const unsigned *work_read, const unsigned *n_work,
-                          Fin *fin, Counters *ctr, int as5) {
-    const bool smat = c->dp.smat != nullptr;
-    if (local) { if (smat) launch_sw_all_t<true, true>(c, st, R, work_read, n_work, fin, ctr, as5); else launch_sw_all_t<true, false>(c, st, R, work_read, n_work, fin, ctr, as5); }
-    else { if (smat) launch_sw_all_t<false, true>(c, st, R, work_read, n_work, fin, ctr, as5); else launch_sw_all_t<false, false>(c, st, R, work_read, n_work, fin, ctr, as5); }
-}
-
-static void launch_finalize_pairs(const idp_ctx *c, cudaStream_t st, const DevReads &R, const unsigned *work_read, const unsigned *n_work_ptr,
-                                  unsigned n_work_fixed, const unsigned *seg_off, const int *seg_cnt, const unsigned *pp, const int *ps,
-                                  const unsigned *pse, idp_result *out, uint8_t *rtype, Counters *ctr, int three) {
-    const int grid = c->sm_count * 8;
-    if (!pairs_trace(c)) pse = nullptr;
-    if (c->dp.max_seq_len <= 64) finalize_pairs_kernel<64, 0><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, n_work_fixed, seg_off, seg_cnt, pp, ps, pse, out, rtype, ctr, three);
-    else finalize_pairs_kernel<kMaxPrimerBases, 0><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, n_work_fixed, seg_off, seg_cnt, pp, ps, pse, out, rtype, ctr, three);
-}
-static void launch_finalize_all(const idp_ctx *c, cudaStream_t st, const DevReads &R, const unsigned *work_read, const unsigned *n_work_ptr,
-                                const Fin *fin, idp_result *out, uint8_t *rtype, int three) {
-    const int grid = c->sm_count * 8;
-    if (c->nq == 32) finalize_all_kernel<64, 32><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, rtype, three);
-    else if (c->nq == 64) finalize_all_kernel<64, 64><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, rtype, three);
-    else finalize_all_kernel<kMaxPrimerBases, 0><<<grid, 128, 0, st>>>(c->dp, R, work_read, n_work_ptr, fin, out, rtype, three);
-}
-
 // Enqueue the whole matcher chain for reads already on the device.  Nothing here waits on the host.
-static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R, idp_result *five, idp_result *three) {
+// five / three: where the per-read records go, in either format (ResultOut).
+static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R, ResultOut five, ResultOut three) {
     const idp_panel &p = *c->panel;
+    const LaunchCfg &cfg = c->cfg;
     const size_t n = (size_t)R.n;
     int rc;
     const bool k_gapped = p.kidx[1].k > 0, do3 = p.params.three_prime >= 0;
@@ -358,58 +257,46 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
     CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(Counters), st));
     CUDA_TRY(cudaEventRecord(s.ev[EV_START], st));
     if (n > 0) {
-        switch (c->rw) {
-            case 4: rc = launch_scan<4>(c, st, R, five, rtype, fall, ctr); break;
-            case 5: rc = launch_scan<5>(c, st, R, five, rtype, fall, ctr); break;
-            case 8: rc = launch_scan<8>(c, st, R, five, rtype, fall, ctr); break;
-            case 16: rc = launch_scan<16>(c, st, R, five, rtype, fall, ctr); break;
-            default: rc = launch_scan<32>(c, st, R, five, rtype, fall, ctr); break;
-        }
-        if (rc) return rc;
+        if ((rc = launch_scan(cfg, st, R, five, rtype, fall, ctr))) return rc;
         ++s.launches;
     }
     CUDA_TRY(cudaEventRecord(s.ev[EV_SCAN], st));
     // ---- 5' gapped stage over the fall-through list ----
     if (n > 0) {
         if (k_gapped) {
-            const int words = (p.n + 31) / 32;
-            const size_t smem = (size_t)8 * words * 4;
-            cand5_thread_kernel<<<c->sm_count * 8, 256, 0, st>>>(c->dp, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(),
-                                                                  (unsigned)s.pair_cap, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(), s.spill.as<unsigned>());
-            cand5_kernel<<<c->sm_count * 4, 256, smem, st>>>(c->dp, R, fall, s.spill.as<unsigned>(), ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(),
-                                                            (unsigned)s.pair_cap, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>());
-            ++s.launches;
+            launch_cand5(cfg, st, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), (unsigned)s.pair_cap,
+                         s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(), s.spill.as<unsigned>());
             CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st));
-            launch_sw_pairs(c, st, false, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), (unsigned)s.pair_cap);
+            launch_sw_pairs(cfg, st, false, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), (unsigned)s.pair_cap);
             CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st));
-            launch_finalize_pairs(c, st, R, fall, &ctr->n_fall, 0u, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(),
+            launch_finalize_pairs(cfg, st, R, fall, &ctr->n_fall, 0u, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(),
                                   s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), five, rtype, ctr, 0);
-            s.launches += 3;
+            s.launches += 4;
         } else {
             CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st));
-            launch_sw_all(c, st, false, R, fall, &ctr->n_fall, s.fin.as<Fin>(), ctr, 1);
+            launch_sw_all(cfg, st, false, R, fall, &ctr->n_fall, s.fin.as<Fin>(), ctr, 1);
             CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st));
-            launch_finalize_all(c, st, R, fall, &ctr->n_fall, s.fin.as<Fin>(), five, rtype, 0);
+            launch_finalize_all(cfg, st, R, fall, &ctr->n_fall, s.fin.as<Fin>(), five, rtype, 0);
             s.launches += 2;
         }
     } else { CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st)); CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st)); }
     CUDA_TRY(cudaEventRecord(s.ev[EV_GAPPED], st));
     // ---- 3' stage (IP:483-516) ----
-    if (do3 && n > 0 && three) {
+    if (do3 && n > 0 && three.p) {
         CUDA_TRY(cudaMemsetAsync(&ctr->n_pairs, 0, sizeof(unsigned), st));
-        cand3_kernel<<<(R.n + 255) / 256, 256, 0, st>>>(c->dp, R, five, ctr, s.all_list.as<unsigned>(), s.pair_work.as<unsigned>(),
-                                                       s.pair_primer.as<unsigned>(), (unsigned)s.pair_cap, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>());
+        launch_cand3(cfg, st, R, five, ctr, s.all_list.as<unsigned>(), s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(),
+                     (unsigned)s.pair_cap, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>());
         CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_A], st));
-        launch_sw_pairs(c, st, true, R, nullptr, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), (unsigned)s.pair_cap);
-        launch_sw_all(c, st, true, R, s.all_list.as<unsigned>(), &ctr->n_all, s.fin.as<Fin>(), ctr, 0);
+        launch_sw_pairs(cfg, st, true, R, nullptr, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), (unsigned)s.pair_cap);
+        launch_sw_all(cfg, st, true, R, s.all_list.as<unsigned>(), &ctr->n_all, s.fin.as<Fin>(), ctr, 0);
         CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_B], st));
-        launch_finalize_pairs(c, st, R, nullptr, nullptr, (unsigned)R.n, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(),
+        launch_finalize_pairs(cfg, st, R, nullptr, nullptr, (unsigned)R.n, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(),
                               s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), three, nullptr, ctr, 1);
-        launch_finalize_all(c, st, R, s.all_list.as<unsigned>(), &ctr->n_all, s.fin.as<Fin>(), three, nullptr, 1);
+        launch_finalize_all(cfg, st, R, s.all_list.as<unsigned>(), &ctr->n_all, s.fin.as<Fin>(), three, nullptr, 1);
         s.launches += 5;
     } else { CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_A], st)); CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_B], st)); }
     CUDA_TRY(cudaEventRecord(s.ev[EV_THREE], st));
-    if (n > 0) { metrics_kernel<<<std::min<int>((R.n + 2047) / 2048, c->sm_count * 8), 256, 0, st>>>(R, rtype, ctr); ++s.launches; }
+    if (n > 0) { launch_metrics(cfg, st, R, rtype, ctr); ++s.launches; }
     CUDA_TRY(cudaMemcpyAsync(s.h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(s.ev[EV_END], st));
     CUDA_TRY(cudaGetLastError());
@@ -431,6 +318,166 @@ static void add_timings(idp_ctx *c, Slot &s, bool first) {
     t.sw_cells += (int64_t)s.h_ctr->sw_cells;
     t.scan_base_compares += (int64_t)s.h_ctr->base_compares;
     t.kernel_launches += s.launches;
+    t.n_scan_parked += (int64_t)s.h_ctr->n_parked;
+}
+
+// a failed call must not leave copies in flight into the caller's arrays, nor slots that a later call would harvest
+static void drain_slots(idp_ctx *c) {
+    for (Slot &s : c->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        s.busy = false;
+    }
+    cudaGetLastError();
+}
+
+static int check_reads(const idp_ctx *c, const idp_reads *reads, int32_t n_reads, const void *five, const void *three, bool compact) {
+    if (!c) { set_error("NULL context"); return IDP_ERR_ARG; }
+    if (!reads || n_reads < 0 || !five) { set_error("NULL reads / results or negative count"); return IDP_ERR_ARG; }
+    if (n_reads > 0 && (!reads->seq4 || !reads->flags)) { set_error("reads.seq4 and reads.flags are required"); return IDP_ERR_ARG; }
+    if (reads->fixed_len <= 0 && n_reads > 0 && (!reads->seq_off || !reads->len)) { set_error("reads.seq_off and reads.len are required unless fixed_len > 0"); return IDP_ERR_ARG; }
+    if (reads->fixed_len > kMaxReadLen) { set_error("reads longer than %d bases are not supported", kMaxReadLen); return IDP_ERR_UNSUPPORTED; }
+    if (c->panel->params.three_prime >= 0 && !three) { set_error("three_prime >= 0 needs a `three` result array"); return IDP_ERR_ARG; }
+    if (compact && !c->compact_ok) {
+        set_error("this panel's alignment scores or size do not fit the 16-byte record; use the 32-byte idp_match_batch calls");
+        return IDP_ERR_UNSUPPORTED;
+    }
+    return IDP_OK;
+}
+
+static int match_batch_device(idp_ctx *c, const idp_reads *reads, int32_t n_reads, void *five, void *three, bool compact,
+                              int64_t *metrics160, int64_t *n_gapped_alignments) {
+    int rc = check_reads(c, reads, n_reads, five, three, compact);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(c->device));
+    Slot &s = c->slots[0];
+    cudaStream_t st = c->user_stream ? c->user_stream : s.stream;
+    DevReads R{reads->seq4, reads->seq_off, reads->len, reads->ref_idx, reads->unclipped_start, reads->unclipped_end, reads->flags, reads->fixed_len, n_reads};
+    c->last = idp_timings{};
+    for (int attempt = 0;; ++attempt) {
+        if ((rc = enqueue_chain(c, s, st, R, ResultOut{five, compact}, ResultOut{three, compact}))) { cudaStreamSynchronize(st); cudaGetLastError(); return rc; }
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (s.h_ctr->overflow == 0) break;
+        if (attempt >= 6) { set_error("candidate pair buffer overflow persists after %d retries", attempt); return IDP_ERR_NOMEM; }
+        s.pair_cap *= 4;  // rare: a read listed far more -K candidates than budgeted; redo the batch with more room
+    }
+    c->last = idp_timings{};
+    add_timings(c, s, true);
+    float ms = 0; cudaEventElapsedTime(&ms, s.ev[EV_START], s.ev[EV_END]);
+    c->last.ms_total = ms; c->last.n_reads = n_reads;
+    if (metrics160) for (int i = 0; i < 160; ++i) metrics160[i] += (int64_t)s.h_ctr->metrics[i];
+    if (n_gapped_alignments) *n_gapped_alignments += (int64_t)s.h_ctr->n_align5;
+    return IDP_OK;
+}
+
+// host-pointer path: chunks of reads flow through kSlots streams so that H2D, kernels and D2H overlap
+static int match_batch_host(idp_ctx *c, const idp_reads *reads, int32_t n_reads, void *five, void *three, bool compact,
+                            int64_t *metrics160, int64_t *n_gapped_alignments) {
+    int rc = check_reads(c, reads, n_reads, five, three, compact);
+    if (rc) return rc;
+    const bool do3 = c->panel->params.three_prime >= 0;
+    const size_t rec = compact ? sizeof(idp_result16) : sizeof(idp_result);
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->last = idp_timings{};
+    c->last.n_reads = n_reads;
+    const char *env = getenv("IDP_CHUNK_READS");
+    int64_t chunk = env ? atoll(env) : (1 << 20);
+    if (chunk < 2) chunk = 2;
+    const bool have_loc = reads->ref_idx && reads->unclipped_start && reads->unclipped_end;
+    bool first = true;
+    int64_t total_metrics[160] = {0}, total_align = 0;
+    uint8_t *five_b = static_cast<uint8_t *>(five), *three_b = static_cast<uint8_t *>(three);
+
+    auto harvest = [&](Slot &s) -> int {
+        if (!s.busy) return IDP_OK;
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        s.busy = false;
+        for (int attempt = 0; s.h_ctr->overflow; ++attempt) {  // rare: redo this chunk (still resident in the slot) with more room
+            if (attempt >= 6) { set_error("candidate pair buffer overflow persists after %d retries", attempt); return IDP_ERR_NOMEM; }
+            s.pair_cap *= 4;
+            int rc2 = enqueue_chain(c, s, s.stream, s.R, ResultOut{s.five.p, compact}, ResultOut{do3 ? s.three.p : nullptr, compact});
+            if (rc2) return rc2;
+            CUDA_TRY(cudaMemcpyAsync(five_b + s.chunk_begin * rec, s.five.p, s.chunk_n * rec, cudaMemcpyDeviceToHost, s.stream));
+            if (do3) CUDA_TRY(cudaMemcpyAsync(three_b + s.chunk_begin * rec, s.three.p, s.chunk_n * rec, cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(cudaStreamSynchronize(s.stream));
+        }
+        add_timings(c, s, first);
+        first = false;
+        for (int i = 0; i < 160; ++i) total_metrics[i] += (int64_t)s.h_ctr->metrics[i];
+        total_align += (int64_t)s.h_ctr->n_align5;
+        return IDP_OK;
+    };
+
+    // one chunk: stage, run the chain, bring the records back -- all asynchronous on the slot's stream
+    auto submit = [&](Slot &s, int64_t b, int64_t e) -> int {
+        const int64_t cn = e - b;
+        cudaStream_t st = s.stream;
+        int rc2;
+        uint64_t byte0, byte1;  // byte range of this chunk's bases
+        if (reads->fixed_len > 0) { const uint64_t stride = (uint64_t)((reads->fixed_len + 1) >> 1); byte0 = (uint64_t)b * stride; byte1 = (uint64_t)e * stride; }
+        else {
+            byte0 = reads->seq_off[b]; byte1 = 0;
+            for (int64_t r = b; r < e; ++r) {
+                const int32_t len = reads->len[r];
+                if (len < 0 || len > kMaxReadLen) { set_error("read %lld: length %d outside [0, %d]", (long long)r, len, kMaxReadLen); return IDP_ERR_UNSUPPORTED; }
+                byte0 = std::min<uint64_t>(byte0, reads->seq_off[r]);
+                byte1 = std::max<uint64_t>(byte1, reads->seq_off[r] + (uint64_t)((len + 1) >> 1));
+            }
+            if (byte1 < byte0) byte1 = byte0;
+        }
+        if ((rc2 = s.seq4.ensure(byte1 - byte0 + 16)) || (rc2 = s.flags.ensure(cn * 2)) || (rc2 = s.five.ensure(cn * rec))) return rc2;
+        if (do3 && (rc2 = s.three.ensure(cn * rec))) return rc2;
+        CUDA_TRY(cudaMemcpyAsync(s.seq4.p, reads->seq4 + byte0, byte1 - byte0, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s.flags.p, reads->flags + b, cn * 2, cudaMemcpyHostToDevice, st));
+        c->last.h2d_bytes += (int64_t)(byte1 - byte0) + cn * 2;
+        DevReads R{};
+        R.n = (int32_t)cn; R.fixed_len = reads->fixed_len; R.flags = s.flags.as<uint16_t>();
+        R.seq4 = s.seq4.as<uint8_t>() - (reads->fixed_len > 0 ? 0 : byte0);
+        if (reads->fixed_len <= 0) {
+            if ((rc2 = s.seq_off.ensure(cn * 8)) || (rc2 = s.len.ensure(cn * 4))) return rc2;
+            CUDA_TRY(cudaMemcpyAsync(s.seq_off.p, reads->seq_off + b, cn * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(s.len.p, reads->len + b, cn * 4, cudaMemcpyHostToDevice, st));
+            R.seq_off = s.seq_off.as<uint64_t>(); R.len = s.len.as<int32_t>();
+            c->last.h2d_bytes += cn * 12;
+        }
+        if (have_loc) {
+            if ((rc2 = s.ref_idx.ensure(cn * 4)) || (rc2 = s.ustart.ensure(cn * 4)) || (rc2 = s.uend.ensure(cn * 4))) return rc2;
+            CUDA_TRY(cudaMemcpyAsync(s.ref_idx.p, reads->ref_idx + b, cn * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(s.ustart.p, reads->unclipped_start + b, cn * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(s.uend.p, reads->unclipped_end + b, cn * 4, cudaMemcpyHostToDevice, st));
+            R.ref_idx = s.ref_idx.as<int32_t>(); R.ustart = s.ustart.as<int32_t>(); R.uend = s.uend.as<int32_t>();
+            c->last.h2d_bytes += cn * 12;
+        }
+        s.R = R; s.chunk_begin = b; s.chunk_n = cn;
+        s.busy = true;  // from here on the slot has work in flight, whatever happens below
+        if ((rc2 = enqueue_chain(c, s, st, R, ResultOut{s.five.p, compact}, ResultOut{do3 ? s.three.p : nullptr, compact}))) return rc2;
+        CUDA_TRY(cudaMemcpyAsync(five_b + b * rec, s.five.p, cn * rec, cudaMemcpyDeviceToHost, st));
+        c->last.d2h_bytes += cn * (int64_t)rec;
+        if (do3) { CUDA_TRY(cudaMemcpyAsync(three_b + b * rec, s.three.p, cn * rec, cudaMemcpyDeviceToHost, st)); c->last.d2h_bytes += cn * (int64_t)rec; }
+        return IDP_OK;
+    };
+
+    int slot_i = 0;
+    bool began = false;
+    for (int64_t b = 0; b < n_reads;) {
+        int64_t e = std::min<int64_t>(b + chunk, n_reads);
+        if (e < n_reads && (reads->flags[e - 1] & IDP_F_MATE_NEXT)) ++e;  // never split a template
+        Slot &s = c->slots[slot_i];
+        slot_i = (slot_i + 1) % kSlots;
+        if ((rc = harvest(s))) { drain_slots(c); return rc; }
+        if (!began) { if (cudaEventRecord(c->ev_begin, s.stream) != cudaSuccess) { set_error("cudaEventRecord failed"); drain_slots(c); return IDP_ERR_CUDA; } began = true; }
+        if ((rc = submit(s, b, e))) { drain_slots(c); return rc; }
+        b = e;
+    }
+    for (int k = 0; k < kSlots; ++k) if ((rc = harvest(c->slots[k]))) { drain_slots(c); return rc; }
+    if (began) {
+        CUDA_TRY(cudaEventRecord(c->ev_finish, c->slots[0].stream));
+        CUDA_TRY(cudaEventSynchronize(c->ev_finish));
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev_begin, c->ev_finish);
+        c->last.ms_total = ms;
+    }
+    if (metrics160) for (int i = 0; i < 160; ++i) metrics160[i] += total_metrics[i];
+    if (n_gapped_alignments) *n_gapped_alignments += total_align;
+    return IDP_OK;
 }
 
 }  // namespace idp
@@ -458,12 +505,14 @@ int idp_ctx_create(const idp_panel *panel, int device, idp_ctx **out) {
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return IDP_ERR_CUDA; }
+    // the library holds sm_100a code only: architecture-specific cubins do not run on any other major version (nor on sm_12x)
+    if (prop.major != 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return IDP_ERR_CUDA; }
     auto *c = new idp_ctx();
-    c->panel = panel; c->device = device; c->sm_count = prop.multiProcessorCount;
-    c->scan_stats = getenv("IDP_SCAN_STATS") && atoi(getenv("IDP_SCAN_STATS")) != 0;
+    c->panel = panel; c->device = device; c->cfg.sm_count = prop.multiProcessorCount;
+    c->cfg.scan_stats = getenv("IDP_SCAN_STATS") && atoi(getenv("IDP_SCAN_STATS")) != 0;
     int rc = upload_panel(c);
     if (rc) { idp_ctx_destroy(c); return rc; }
+    if (cudaEventCreate(&c->ev_begin) != cudaSuccess || cudaEventCreate(&c->ev_finish) != cudaSuccess) { set_error("cudaEventCreate failed"); idp_ctx_destroy(c); return IDP_ERR_CUDA; }
     for (Slot &s : c->slots) {
         if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); idp_ctx_destroy(c); return IDP_ERR_CUDA; }
         for (auto &e : s.ev) if (cudaEventCreate(&e) != cudaSuccess) { set_error("cudaEventCreate failed"); idp_ctx_destroy(c); return IDP_ERR_CUDA; }
@@ -487,9 +536,12 @@ void idp_ctx_destroy(idp_ctx *c) {
         for (auto &e : s.ev) if (e) cudaEventDestroy(e);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
-    for (DevBuf *b : {&c->b_qbot, &c->b_bylen, &c->b_pmask, &c->b_pinfo, &c->b_positive, &c->b_loc_key[0], &c->b_loc_key[1], &c->b_loc_primer[0], &c->b_loc_primer[1],
+    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+    if (c->ev_finish) cudaEventDestroy(c->ev_finish);
+    for (DevBuf *b : {&c->b_fx, &c->b_qbot, &c->b_bylen, &c->b_pmask, &c->b_pinfo, &c->b_positive, &c->b_loc_key[0], &c->b_loc_key[1], &c->b_loc_primer[0], &c->b_loc_primer[1],
                       &c->b_mate_off, &c->b_mate_idx, &c->b_smat, &c->b_keys[0], &c->b_keys[1], &c->b_offcnt[0], &c->b_offcnt[1],
-                      &c->b_postings[0], &c->b_postings[1], &c->b_heads[0], &c->b_heads[1], &c->b_direct[0], &c->b_direct[1], &c->b_bsmm, &c->b_bsacc, &c->b_seedtab, &c->b_seedlist, &c->b_diag}) b->release();
+                      &c->b_postings[0], &c->b_postings[1], &c->b_heads[0], &c->b_heads[1], &c->b_direct[0], &c->b_direct[1], &c->b_bsmm, &c->b_bsacc, &c->b_seedtab, &c->b_seedlist, &c->b_diag,
+                      &c->al_q, &c->al_ql, &c->al_t, &c->al_to, &c->al_tl, &c->al_out}) b->release();
     delete c;
 }
 
@@ -505,152 +557,41 @@ int idp_ctx_timings(const idp_ctx *ctx, idp_timings *out) {
     return IDP_OK;
 }
 
-static int check_reads(const idp_reads *reads, int32_t n_reads, idp_result *five) {
-    if (!reads || n_reads < 0 || !five) { set_error("NULL reads / results or negative count"); return IDP_ERR_ARG; }
-    if (n_reads > 0 && (!reads->seq4 || !reads->flags)) { set_error("reads.seq4 and reads.flags are required"); return IDP_ERR_ARG; }
-    if (reads->fixed_len <= 0 && n_reads > 0 && (!reads->seq_off || !reads->len)) { set_error("reads.seq_off and reads.len are required unless fixed_len > 0"); return IDP_ERR_ARG; }
-    if (reads->fixed_len > kMaxReadLen) { set_error("reads longer than %d bases are not supported", kMaxReadLen); return IDP_ERR_UNSUPPORTED; }
-    return IDP_OK;
-}
-
 int idp_match_batch_device(idp_ctx *c, const idp_reads *reads, int32_t n_reads, idp_result *five, idp_result *three,
                            int64_t *metrics160, int64_t *n_gapped_alignments) {
-    if (!c) { set_error("NULL context"); return IDP_ERR_ARG; }
-    int rc = check_reads(reads, n_reads, five);
-    if (rc) return rc;
-    if (c->panel->params.three_prime >= 0 && !three) { set_error("three_prime >= 0 needs a `three` result array"); return IDP_ERR_ARG; }
-    CUDA_TRY(cudaSetDevice(c->device));
-    Slot &s = c->slots[0];
-    cudaStream_t st = c->user_stream ? c->user_stream : s.stream;
-    DevReads R{reads->seq4, reads->seq_off, reads->len, reads->ref_idx, reads->unclipped_start, reads->unclipped_end, reads->flags, reads->fixed_len, n_reads};
-    c->last = idp_timings{};
-    for (int attempt = 0;; ++attempt) {
-        if ((rc = enqueue_chain(c, s, st, R, five, three))) return rc;
-        CUDA_TRY(cudaStreamSynchronize(st));
-        if (s.h_ctr->overflow == 0) break;
-        if (attempt >= 6) { set_error("candidate pair buffer overflow persists after %d retries", attempt); return IDP_ERR_NOMEM; }
-        s.pair_cap *= 4;  // rare: a read listed far more -K candidates than budgeted; redo the batch with more room
-    }
-    c->last = idp_timings{};
-    add_timings(c, s, true);
-    float ms = 0; cudaEventElapsedTime(&ms, s.ev[EV_START], s.ev[EV_END]);
-    c->last.ms_total = ms; c->last.n_reads = n_reads;
-    if (metrics160) for (int i = 0; i < 160; ++i) metrics160[i] += (int64_t)s.h_ctr->metrics[i];
-    if (n_gapped_alignments) *n_gapped_alignments += (int64_t)s.h_ctr->n_align5;
-    return IDP_OK;
+    return match_batch_device(c, reads, n_reads, five, three, false, metrics160, n_gapped_alignments);
 }
-
-// host-pointer path: chunks of reads flow through kSlots streams so that H2D, kernels and D2H overlap
+int idp_match_batch16_device(idp_ctx *c, const idp_reads *reads, int32_t n_reads, idp_result16 *five, idp_result16 *three,
+                             int64_t *metrics160, int64_t *n_gapped_alignments) {
+    return match_batch_device(c, reads, n_reads, five, three, true, metrics160, n_gapped_alignments);
+}
 int idp_match_batch(idp_ctx *c, const idp_reads *reads, int32_t n_reads, idp_result *five, idp_result *three,
                     int64_t *metrics160, int64_t *n_gapped_alignments) {
-    if (!c) { set_error("NULL context"); return IDP_ERR_ARG; }
-    int rc = check_reads(reads, n_reads, five);
-    if (rc) return rc;
-    const bool do3 = c->panel->params.three_prime >= 0;
-    if (do3 && !three) { set_error("three_prime >= 0 needs a `three` result array"); return IDP_ERR_ARG; }
-    CUDA_TRY(cudaSetDevice(c->device));
-    c->last = idp_timings{};
-    c->last.n_reads = n_reads;
-    const char *env = getenv("IDP_CHUNK_READS");
-    int64_t chunk = env ? atoll(env) : (1 << 20);
-    if (chunk < 2) chunk = 2;
-    const bool have_loc = reads->ref_idx && reads->unclipped_start && reads->unclipped_end;
-    bool first = true;
-    int64_t total_metrics[160] = {0}, total_align = 0;
+    return match_batch_host(c, reads, n_reads, five, three, false, metrics160, n_gapped_alignments);
+}
+int idp_match_batch16(idp_ctx *c, const idp_reads *reads, int32_t n_reads, idp_result16 *five, idp_result16 *three,
+                      int64_t *metrics160, int64_t *n_gapped_alignments) {
+    return match_batch_host(c, reads, n_reads, five, three, true, metrics160, n_gapped_alignments);
+}
 
-    auto harvest = [&](Slot &s) -> int {
-        if (!s.busy) return IDP_OK;
-        CUDA_TRY(cudaStreamSynchronize(s.stream));
-        s.busy = false;
-        for (int attempt = 0; s.h_ctr->overflow; ++attempt) {  // rare: redo this chunk (still resident in the slot) with more room
-            if (attempt >= 6) { set_error("candidate pair buffer overflow persists after %d retries", attempt); return IDP_ERR_NOMEM; }
-            s.pair_cap *= 4;
-            int rc2 = enqueue_chain(c, s, s.stream, s.R, s.five.as<idp_result>(), do3 ? s.three.as<idp_result>() : nullptr);
-            if (rc2) return rc2;
-            CUDA_TRY(cudaMemcpyAsync(five + s.chunk_begin, s.five.p, s.chunk_n * sizeof(idp_result), cudaMemcpyDeviceToHost, s.stream));
-            if (do3) CUDA_TRY(cudaMemcpyAsync(three + s.chunk_begin, s.three.p, s.chunk_n * sizeof(idp_result), cudaMemcpyDeviceToHost, s.stream));
-            CUDA_TRY(cudaStreamSynchronize(s.stream));
-        }
-        add_timings(c, s, first);
-        first = false;
-        for (int i = 0; i < 160; ++i) total_metrics[i] += (int64_t)s.h_ctr->metrics[i];
-        total_align += (int64_t)s.h_ctr->n_align5;
-        return IDP_OK;
-    };
-
-    int slot_i = 0;
-    cudaEvent_t ev_begin, ev_finish;
-    CUDA_TRY(cudaEventCreate(&ev_begin));
-    CUDA_TRY(cudaEventCreate(&ev_finish));
-    bool began = false;
-    for (int64_t b = 0; b < n_reads;) {
-        int64_t e = std::min<int64_t>(b + chunk, n_reads);
-        if (e < n_reads && (reads->flags[e - 1] & IDP_F_MATE_NEXT)) ++e;  // never split a template
-        const int64_t cn = e - b;
-        Slot &s = c->slots[slot_i];
-        slot_i = (slot_i + 1) % kSlots;
-        if ((rc = harvest(s))) return rc;
-        cudaStream_t st = s.stream;
-        if (!began) { CUDA_TRY(cudaEventRecord(ev_begin, st)); began = true; }
-        // byte range of this chunk's bases
-        uint64_t byte0, byte1;
-        if (reads->fixed_len > 0) { const uint64_t stride = (uint64_t)((reads->fixed_len + 1) >> 1); byte0 = (uint64_t)b * stride; byte1 = (uint64_t)e * stride; }
-        else { byte0 = reads->seq_off[b]; byte1 = 0; for (int64_t r = b; r < e; ++r) byte1 = std::max<uint64_t>(byte1, reads->seq_off[r] + (uint64_t)((reads->len[r] + 1) >> 1)); if (byte1 < byte0) byte1 = byte0; }
-        if ((rc = s.seq4.ensure(byte1 - byte0 + 16)) || (rc = s.flags.ensure(cn * 2)) || (rc = s.five.ensure(cn * sizeof(idp_result)))) return rc;
-        if (do3 && (rc = s.three.ensure(cn * sizeof(idp_result)))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(s.seq4.p, reads->seq4 + byte0, byte1 - byte0, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(s.flags.p, reads->flags + b, cn * 2, cudaMemcpyHostToDevice, st));
-        c->last.h2d_bytes += (int64_t)(byte1 - byte0) + cn * 2;
-        DevReads R{};
-        R.n = (int32_t)cn; R.fixed_len = reads->fixed_len; R.flags = s.flags.as<uint16_t>();
-        R.seq4 = s.seq4.as<uint8_t>() - (reads->fixed_len > 0 ? 0 : byte0);
-        if (reads->fixed_len <= 0) {
-            if ((rc = s.seq_off.ensure(cn * 8)) || (rc = s.len.ensure(cn * 4))) return rc;
-            CUDA_TRY(cudaMemcpyAsync(s.seq_off.p, reads->seq_off + b, cn * 8, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(s.len.p, reads->len + b, cn * 4, cudaMemcpyHostToDevice, st));
-            R.seq_off = s.seq_off.as<uint64_t>(); R.len = s.len.as<int32_t>();
-            c->last.h2d_bytes += cn * 12;
-        }
-        if (have_loc) {
-            if ((rc = s.ref_idx.ensure(cn * 4)) || (rc = s.ustart.ensure(cn * 4)) || (rc = s.uend.ensure(cn * 4))) return rc;
-            CUDA_TRY(cudaMemcpyAsync(s.ref_idx.p, reads->ref_idx + b, cn * 4, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(s.ustart.p, reads->unclipped_start + b, cn * 4, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(s.uend.p, reads->unclipped_end + b, cn * 4, cudaMemcpyHostToDevice, st));
-            R.ref_idx = s.ref_idx.as<int32_t>(); R.ustart = s.ustart.as<int32_t>(); R.uend = s.uend.as<int32_t>();
-            c->last.h2d_bytes += cn * 12;
-        }
-        s.R = R; s.chunk_begin = b; s.chunk_n = cn;
-        if ((rc = enqueue_chain(c, s, st, R, s.five.as<idp_result>(), do3 ? s.three.as<idp_result>() : nullptr))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(five + b, s.five.p, cn * sizeof(idp_result), cudaMemcpyDeviceToHost, st));
-        c->last.d2h_bytes += cn * (int64_t)sizeof(idp_result);
-        if (do3) { CUDA_TRY(cudaMemcpyAsync(three + b, s.three.p, cn * sizeof(idp_result), cudaMemcpyDeviceToHost, st)); c->last.d2h_bytes += cn * (int64_t)sizeof(idp_result); }
-        s.busy = true;
-        b = e;
+void idp_result16_unpack(const idp_result16 *in, int64_t n, idp_result *out) {
+    for (int64_t i = 0; i < n; ++i) {
+        const idp_result16 r = in[i];
+        idp_result o;
+        memset(&o, 0, sizeof o);
+        o.primer = (int32_t)(r.head & 0xFFFFFFu) - 1;
+        o.type = (uint8_t)((r.head >> 24) & 3u);
+        o.multi = (uint8_t)((r.head >> 26) & 1u);
+        o.status = (uint8_t)((r.head >> 27) & 7u);
+        if (o.type == IDP_GAPPED) { o.raw_score = r.a; o.raw_next = r.b; }
+        else { o.mm = r.a; o.next_mm = r.b == IDP_NEXT16_NA ? IDP_NEXT_NA : r.b; }
+        o.q_len = (int16_t)r.q_len; o.q_len_next = (int16_t)r.q_len_next;
+        o.t_start = (int16_t)r.t_start; o.t_end = (int16_t)r.t_end;
+        out[i] = o;
     }
-    for (int k = 0; k < kSlots; ++k) if ((rc = harvest(c->slots[k]))) return rc;
-    if (began) {
-        CUDA_TRY(cudaEventRecord(ev_finish, c->slots[0].stream));
-        CUDA_TRY(cudaEventSynchronize(ev_finish));
-        float ms = 0; cudaEventElapsedTime(&ms, ev_begin, ev_finish);
-        c->last.ms_total = ms;
-    }
-    cudaEventDestroy(ev_begin); cudaEventDestroy(ev_finish);
-    if (metrics160) for (int i = 0; i < 160; ++i) metrics160[i] += total_metrics[i];
-    if (n_gapped_alignments) *n_gapped_alignments += total_align;
-    return IDP_OK;
 }
 
 // ---- batched AsyncAligner.align (AA:37-54) ----
-__global__ void align_kernel(DevPanel P, const uint32_t *__restrict__ qwords, int qw, const int32_t *__restrict__ qlen,
-                             const uint8_t *__restrict__ tseq4, const uint64_t *__restrict__ toff, const int32_t *__restrict__ tlen,
-                             int n, int mode, int32_t *__restrict__ score, int32_t *__restrict__ tstart, int32_t *__restrict__ tend) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Oriented T{tseq4 + toff[i], tlen[i], false};
-    const Traced tr = sw_trace<kMaxPrimerBases>(P, qwords + (size_t)i * qw, qlen[i], T, tlen[i], mode);
-    score[i] = tr.score; tstart[i] = tr.t_start; tend[i] = tr.t_end;
-}
-
 int idp_align_batch(idp_ctx *c, int mode, const char *queries, const int64_t *q_off, const char *targets, const int64_t *t_off,
                     int32_t n, int32_t *score, int32_t *target_start, int32_t *target_end) {
     if (!c || !queries || !q_off || !targets || !t_off || n < 0 || !score || !target_start || !target_end) { set_error("idp_align_batch: NULL argument"); return IDP_ERR_ARG; }
@@ -682,20 +623,21 @@ int idp_align_batch(idp_ctx *c, int mode, const char *queries, const int64_t *q_
     }
     if (!ok) { set_error("idp_align_batch: only upper-case IUPAC bases and '=' are supported"); return IDP_ERR_UNSUPPORTED; }
     if (tseq.empty()) tseq.push_back(0);
-    DevBuf d_q, d_ql, d_t, d_to, d_tl, d_out;
     int rc;
-    auto cleanup = [&]() { d_q.release(); d_ql.release(); d_t.release(); d_to.release(); d_tl.release(); d_out.release(); };
-    if ((rc = upload(qwords, d_q)) || (rc = upload(qlen, d_ql)) || (rc = upload(tseq, d_t)) || (rc = upload(toff, d_to)) || (rc = upload(tlen, d_tl)) ||
-        (rc = d_out.ensure((size_t)n * 12))) { cleanup(); return rc; }
-    int32_t *o = d_out.as<int32_t>();
     cudaStream_t st = c->user_stream ? c->user_stream : c->slots[0].stream;
-    align_kernel<<<(n + 127) / 128, 128, 0, st>>>(c->dp, d_q.as<uint32_t>(), qw, d_ql.as<int32_t>(), d_t.as<uint8_t>(), d_to.as<uint64_t>(), d_tl.as<int32_t>(),
-                                                 n, mode, o, o + n, o + 2 * (size_t)n);
+    // uploads ordered on the stream the kernel runs on (pageable sources: each call returns once its data is staged)
+    if ((rc = upload(qwords, c->al_q, 1, st, true)) || (rc = upload(qlen, c->al_ql, 1, st, true)) || (rc = upload(tseq, c->al_t, 1, st, true)) ||
+        (rc = upload(toff, c->al_to, 1, st, true)) || (rc = upload(tlen, c->al_tl, 1, st, true)) || (rc = c->al_out.ensure((size_t)n * 12))) {
+        cudaStreamSynchronize(st);
+        return rc;
+    }
+    int32_t *o = c->al_out.as<int32_t>();
+    launch_align(c->cfg, st, c->al_q.as<uint32_t>(), qw, c->al_ql.as<int32_t>(), c->al_t.as<uint8_t>(), c->al_to.as<uint64_t>(), c->al_tl.as<int32_t>(),
+                 n, mode, o, o + n, o + 2 * (size_t)n);
     cudaError_t e1 = cudaMemcpyAsync(score, o, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
     cudaError_t e2 = cudaMemcpyAsync(target_start, o + n, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
     cudaError_t e3 = cudaMemcpyAsync(target_end, o + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
     cudaError_t e4 = cudaStreamSynchronize(st);
-    cleanup();
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
         set_error("idp_align_batch: CUDA failure: %s", cudaGetErrorString(e4 != cudaSuccess ? e4 : (e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3))));
         return IDP_ERR_CUDA;

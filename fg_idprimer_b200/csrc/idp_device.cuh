@@ -1,0 +1,160 @@
+// Device-side data model and helpers shared by every kernel of the IdentifyPrimers matching path (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "idp_internal.h"
+
+namespace idp {
+
+struct DevReads {
+    const uint8_t *seq4;
+    const uint64_t *seq_off;
+    const int32_t *len;
+    const int32_t *ref_idx;
+    const int32_t *ustart;
+    const int32_t *uend;
+    const uint16_t *flags;
+    int32_t fixed_len;
+    int32_t n;
+};
+
+// device-side counters of one batch (one per stream slot)
+struct Counters {
+    unsigned int n_fall;          // reads that fell through to the gapped stage
+    unsigned int n_pairs;         // (read, primer) pairs emitted for sw_pairs_kernel
+    unsigned int n_all;           // 3' reads that take every primer
+    unsigned int overflow;        // pair buffer too small: number of work items not emitted
+    unsigned int n_spill;         // fall-through reads with more -K candidates than the per-thread list holds
+    unsigned int n_parked;        // reads the scan kernel parked for the filter pass (not decided by the exact-prefix table)
+    unsigned long long n_align5;  // alignments performed by the 5' aligner (IP:424)
+    unsigned long long n_align3;
+    unsigned long long sw_cells;
+    unsigned long long base_compares;
+    unsigned long long metrics[160];
+};
+
+// the winner (and runner-up) of one read's gapped candidates, before traceback
+struct Fin {
+    int32_t primer, raw, raw_next;
+    int16_t qlen, qlen_next;
+    int32_t count;  // number of candidates aligned; 0 = none
+};
+
+__device__ __forceinline__ void read_geom(const DevReads &R, int r, const uint8_t *&s, int &len) {
+    if (R.fixed_len > 0) { len = R.fixed_len; s = R.seq4 + (size_t)r * (size_t)((R.fixed_len + 1) >> 1); }
+    else { len = R.len[r]; s = R.seq4 + R.seq_off[r]; }
+}
+__device__ __forceinline__ uint32_t stored_nib(const uint8_t *s, int i) {
+    uint32_t b = __ldg(s + (i >> 1));
+    return (i & 1) ? (b & 15u) : (b >> 4);
+}
+// htsjdk 2.16 SequenceUtil.complement touches only A<->T, C<->G (nibbles 1<->8, 2<->4); every other code is kept (PM:42)
+__device__ __forceinline__ uint32_t comp_nib(uint32_t x) { return (uint32_t)(0xFEDCBA9176523480ull >> (4 * x)) & 15u; }
+
+// 8 BAM bytes-order nibbles (first base in the HIGH nibble of each byte) -> base i in nibble i
+__device__ __forceinline__ uint32_t nibswap(uint32_t x) { return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu); }
+// 1 in the low bit of every nibble that is non-zero
+__device__ __forceinline__ uint32_t nib_nonzero(uint32_t x) {
+    x |= x >> 1;
+    x |= x >> 2;
+    return x & 0x11111111u;
+}
+// bits 0,4,...,28 -> bits 0..7
+__device__ __forceinline__ uint32_t gather_nibble_bits(uint32_t z) {
+    z = (z | (z >> 3)) & 0x03030303u;
+    z = (z | (z >> 6)) & 0x000F000Fu;
+    return (z | (z >> 12)) & 0xFFu;
+}
+
+// a read viewed in a given orientation: forward = as stored, rc = reverse-complemented
+struct Oriented {
+    const uint8_t *s;
+    int len;
+    bool rc;
+    __device__ __forceinline__ uint32_t nib(int j) const { return rc ? comp_nib(stored_nib(s, len - 1 - j)) : stored_nib(s, j); }
+    // same through a generic pointer (the bases may sit in shared memory)
+    __device__ __forceinline__ uint32_t nib_generic(int j) const {
+        const int i = rc ? len - 1 - j : j;
+        const uint32_t b = s[i >> 1];
+        const uint32_t v = (i & 1) ? (b & 15u) : (b >> 4);
+        return rc ? comp_nib(v) : v;
+    }
+};
+// sequential access to an oriented read through a one-word cache: one 32-bit load per 8 bases instead of a byte load per base
+struct TargetStream {
+    const uint8_t *s;
+    int len;
+    bool rc;
+    const uint32_t *curp;
+    uint32_t word;
+    __device__ __forceinline__ explicit TargetStream(const Oriented &o) : s(o.s), len(o.len), rc(o.rc), curp(nullptr), word(0) {}
+    __device__ __forceinline__ uint32_t nib(int j) {
+        const int i = rc ? len - 1 - j : j;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(s) + (uintptr_t)(i >> 1);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+        if (wp != curp) { curp = wp; word = __ldg(wp); }
+        const uint32_t b = (word >> (8 * (int)(a & 3))) & 0xFFu;
+        const uint32_t v = (i & 1) ? (b & 15u) : (b >> 4);
+        return rc ? comp_nib(v) : v;
+    }
+};
+// sequencing order (PM:39-45): raw when unmapped or positive strand, else reverse complement
+__device__ __forceinline__ bool seq_order_is_rc(uint16_t fl) { return !(fl & IDP_F_UNMAPPED) && (fl & IDP_F_REVERSE); }
+
+// where a kernel writes (and cand3_kernel reads) the per-read PrimerMatch records: idp_result (32 B) or idp_result16
+struct ResultOut {
+    void *p;
+    int32_t compact;  // 1: idp_result16
+};
+__device__ __forceinline__ uint4 pack_result16(const idp_result &v) {
+    uint4 w;
+    w.x = ((uint32_t)(v.primer + 1) & 0xFFFFFFu) | ((uint32_t)v.type << 24) | ((uint32_t)(v.multi != 0) << 26) | ((uint32_t)v.status << 27);
+    const bool gapped = v.type == IDP_GAPPED;
+    const int a = gapped ? v.raw_score : v.mm;
+    const int b = gapped ? v.raw_next : (v.next_mm == IDP_NEXT_NA ? IDP_NEXT16_NA : v.next_mm);
+    w.y = ((uint32_t)a & 0xFFFFu) | ((uint32_t)b << 16);
+    w.z = ((uint32_t)(uint16_t)v.q_len) | ((uint32_t)(uint16_t)v.q_len_next << 16);
+    w.w = ((uint32_t)(uint16_t)v.t_start) | ((uint32_t)(uint16_t)v.t_end << 16);
+    return w;
+}
+__device__ __forceinline__ void write_result(const ResultOut &o, int r, const idp_result &v) {
+    if (o.compact) {
+        reinterpret_cast<uint4 *>(o.p)[r] = pack_result16(v);
+    } else {
+        const uint4 *src = reinterpret_cast<const uint4 *>(&v);
+        uint4 *d = reinterpret_cast<uint4 *>(o.p) + 2 * (size_t)r;
+        d[0] = src[0];
+        d[1] = src[1];
+    }
+}
+// match type and primer of a record already written (what matchThreePrime needs of the 5' results, IP:490-499)
+__device__ __forceinline__ void read_type_primer(const ResultOut &o, int r, int &type, int &primer) {
+    if (o.compact) {
+        const uint32_t h = reinterpret_cast<const uint32_t *>(o.p)[4 * (size_t)r];
+        type = (int)((h >> 24) & 3u);
+        primer = (int)(h & 0xFFFFFFu) - 1;
+    } else {
+        const idp_result *q = reinterpret_cast<const idp_result *>(o.p) + r;
+        type = q->type;
+        primer = q->primer;
+    }
+}
+__device__ __forceinline__ idp_result none_result() {
+    idp_result r;
+    r.primer = -1; r.type = IDP_NONE; r.status = 0; r.multi = 0; r.reserved = 0;
+    r.mm = 0; r.next_mm = 0; r.raw_score = 0; r.raw_next = 0; r.q_len = 0; r.q_len_next = 0; r.t_start = 0; r.t_end = 0;
+    return r;
+}
+
+__device__ __forceinline__ bool kmer_lookup(const DevKmerIndex &ix, uint64_t key, OffCnt &oc) {
+    if (key == 0) return false;
+    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> ix.shift);
+    for (;;) {
+        const uint64_t kk = __ldg(&ix.keys[h]);
+        if (kk == key) { oc = ix.off_cnt[h]; return true; }
+        if (kk == 0) return false;
+        h = (h + 1) & ix.slot_mask;
+    }
+}
+
+}  // namespace idp

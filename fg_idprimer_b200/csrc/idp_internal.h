@@ -13,10 +13,16 @@ namespace idp {
 
 constexpr int kMaxPrimerBases = 256;   // longest primer sequence the kernels cover
 constexpr int kMaxK = 16;              // k-mer key = 4 bits/base in a 64-bit word
+constexpr int kFxBases = 12;           // read bases hashed by the exact-prefix table
 constexpr int kMaxReadLen = 4095;      // target start/end are carried in 12 bits next to the score
 constexpr int32_t kNegInf = INT32_MIN / 2;  // fgbio Aligner.MinStartScore
 
 void set_error(const char *fmt, ...);
+// slot of a 12-base read prefix in the exact-prefix table: w0 = bases 0..7, w1 = bases 8..15 (base i in nibble i % 8)
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t fx_hash(uint32_t w0, uint32_t w1, uint32_t mul, int shift) { return ((w0 * mul) ^ ((w1 & 0xFFFFu) * 0x85EBCA6Bu)) >> shift; }
 
 struct OffCnt { uint32_t off, cnt; };
 
@@ -70,6 +76,13 @@ struct DevPanel {
     const uint32_t *seed_tab;
     const uint32_t *seed_list;
     int32_t seed_ok, seed_S, seed_shift, seed_slots;
+    // exact-prefix table (the scan kernel's common case): fx_tab[hash(first 12 read bases)] = primer + 1 for a primer that
+    // (a) this spelling matches without a mismatch on its first 12 bases and (b) is ISOLATED: every other primer differs from
+    // it in at least two of those positions whatever the spelling, so no other primer can be accepted with <= 1 mismatch.
+    // The kernel verifies (a) itself (a slot may be a hash collision); 0 = no entry.  NULL when the panel is not eligible.
+    const uint16_t *fx_tab;
+    int32_t fx_shift, fx_slots;
+    uint32_t fx_mul;           // the multiplier of fx_hash chosen for this panel
     // pair_id groups for 3' matching (IP:496): opposite-strand primers of the same pair, file order
     const int32_t *mate_off;   // [n+1]
     const int32_t *mate_idx;
@@ -116,5 +129,8 @@ struct idp_panel {
     int32_t acc_max = -1;
     std::vector<uint32_t> seed_tab, seed_list;  // seed index (see DevPanel); empty when the panel is not eligible
     int32_t seed_S = 0, seed_shift = 0, seed_slots = 0;
+    std::vector<uint16_t> fx_tab;             // exact-prefix table (see DevPanel); empty when the panel is not eligible
+    int32_t fx_shift = 0, fx_slots = 0;
+    uint32_t fx_mul = 0x9E3779B1u;
     idp::KmerIndexHost kidx[2];
 };

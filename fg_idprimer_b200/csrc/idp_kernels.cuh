@@ -21,137 +21,15 @@
 //                      tracking + finalizedGappedAlignment (IP:459-471)
 //   metrics_kernel     TemplateType + TemplateTypeMetric counter (TemplateType.scala:52-63, IP:413)
 #pragma once
-#include <cuda_runtime.h>
-
-#include "idp_internal.h"
-
+#include "idp_device.cuh"
 
 namespace idp {
-
-struct DevReads {
-    const uint8_t *seq4;
-    const uint64_t *seq_off;
-    const int32_t *len;
-    const int32_t *ref_idx;
-    const int32_t *ustart;
-    const int32_t *uend;
-    const uint16_t *flags;
-    int32_t fixed_len;
-    int32_t n;
-};
-
-// device-side counters of one batch (one per stream slot)
-struct Counters {
-    unsigned int n_fall;          // reads that fell through to the gapped stage
-    unsigned int n_pairs;         // (read, primer) pairs emitted for sw_pairs_kernel
-    unsigned int n_all;           // 3' reads that take every primer
-    unsigned int overflow;        // pair buffer too small: number of work items not emitted
-    unsigned int n_spill;         // fall-through reads with more -K candidates than the per-thread list holds
-    unsigned int pad0;
-    unsigned long long n_align5;  // alignments performed by the 5' aligner (IP:424)
-    unsigned long long n_align3;
-    unsigned long long sw_cells;
-    unsigned long long base_compares;
-    unsigned long long metrics[160];
-};
-
-// the winner (and runner-up) of one read's gapped candidates, before traceback
-struct Fin {
-    int32_t primer, raw, raw_next;
-    int16_t qlen, qlen_next;
-    int32_t count;  // number of candidates aligned; 0 = none
-};
-
-__device__ __forceinline__ void read_geom(const DevReads &R, int r, const uint8_t *&s, int &len) {
-    if (R.fixed_len > 0) { len = R.fixed_len; s = R.seq4 + (size_t)r * (size_t)((R.fixed_len + 1) >> 1); }
-    else { len = R.len[r]; s = R.seq4 + R.seq_off[r]; }
-}
-__device__ __forceinline__ uint32_t stored_nib(const uint8_t *s, int i) {
-    uint32_t b = __ldg(s + (i >> 1));
-    return (i & 1) ? (b & 15u) : (b >> 4);
-}
-// htsjdk 2.16 SequenceUtil.complement touches only A<->T, C<->G (nibbles 1<->8, 2<->4); every other code is kept (PM:42)
-__device__ __forceinline__ uint32_t comp_nib(uint32_t x) { return (uint32_t)(0xFEDCBA9176523480ull >> (4 * x)) & 15u; }
-
-// 8 BAM bytes-order nibbles (first base in the HIGH nibble of each byte) -> base i in nibble i
-__device__ __forceinline__ uint32_t nibswap(uint32_t x) { return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu); }
-// 1 in the low bit of every nibble that is non-zero
-__device__ __forceinline__ uint32_t nib_nonzero(uint32_t x) {
-    x |= x >> 1;
-    x |= x >> 2;
-    return x & 0x11111111u;
-}
-// bits 0,4,...,28 -> bits 0..7
-__device__ __forceinline__ uint32_t gather_nibble_bits(uint32_t z) {
-    z = (z | (z >> 3)) & 0x03030303u;
-    z = (z | (z >> 6)) & 0x000F000Fu;
-    return (z | (z >> 12)) & 0xFFu;
-}
-
-// a read viewed in a given orientation: forward = as stored, rc = reverse-complemented
-struct Oriented {
-    const uint8_t *s;
-    int len;
-    bool rc;
-    __device__ __forceinline__ uint32_t nib(int j) const { return rc ? comp_nib(stored_nib(s, len - 1 - j)) : stored_nib(s, j); }
-    // same through a generic pointer (the bases may sit in shared memory)
-    __device__ __forceinline__ uint32_t nib_generic(int j) const {
-        const int i = rc ? len - 1 - j : j;
-        const uint32_t b = s[i >> 1];
-        const uint32_t v = (i & 1) ? (b & 15u) : (b >> 4);
-        return rc ? comp_nib(v) : v;
-    }
-};
-// sequential access to an oriented read through a one-word cache: one 32-bit load per 8 bases instead of a byte load per base
-struct TargetStream {
-    const uint8_t *s;
-    int len;
-    bool rc;
-    const uint32_t *curp;
-    uint32_t word;
-    __device__ __forceinline__ explicit TargetStream(const Oriented &o) : s(o.s), len(o.len), rc(o.rc), curp(nullptr), word(0) {}
-    __device__ __forceinline__ uint32_t nib(int j) {
-        const int i = rc ? len - 1 - j : j;
-        const uintptr_t a = reinterpret_cast<uintptr_t>(s) + (uintptr_t)(i >> 1);
-        const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
-        if (wp != curp) { curp = wp; word = __ldg(wp); }
-        const uint32_t b = (word >> (8 * (int)(a & 3))) & 0xFFu;
-        const uint32_t v = (i & 1) ? (b & 15u) : (b >> 4);
-        return rc ? comp_nib(v) : v;
-    }
-};
-// sequencing order (PM:39-45): raw when unmapped or positive strand, else reverse complement
-__device__ __forceinline__ bool seq_order_is_rc(uint16_t fl) { return !(fl & IDP_F_UNMAPPED) && (fl & IDP_F_REVERSE); }
-
-__device__ __forceinline__ void write_result(idp_result *dst, const idp_result &v) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(&v);
-    uint4 *d = reinterpret_cast<uint4 *>(dst);
-    d[0] = src[0];
-    d[1] = src[1];
-}
-__device__ __forceinline__ idp_result none_result() {
-    idp_result r;
-    r.primer = -1; r.type = IDP_NONE; r.status = 0; r.multi = 0; r.reserved = 0;
-    r.mm = 0; r.next_mm = 0; r.raw_score = 0; r.raw_next = 0; r.q_len = 0; r.q_len_next = 0; r.t_start = 0; r.t_end = 0;
-    return r;
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Candidate emission for the 5' gapped stage under -K, common case: one THREAD per fall-through read keeps up to
 // kCandLocal distinct candidates in registers (first-hit order, PM:112-114).  Reads with more go to the spill list and
 // are handled by the warp kernel below.  Thousands of independent lookup chains in flight hide the table latency.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool kmer_lookup(const DevKmerIndex &ix, uint64_t key, OffCnt &oc) {
-    if (key == 0) return false;
-    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> ix.shift);
-    for (;;) {
-        const uint64_t kk = __ldg(&ix.keys[h]);
-        if (kk == key) { oc = ix.off_cnt[h]; return true; }
-        if (kk == 0) return false;
-        h = (h + 1) & ix.slot_mask;
-    }
-}
-
 constexpr int kCandLocal = 8;
 
 __global__ void __launch_bounds__(256) cand5_thread_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ fall,
@@ -346,7 +224,7 @@ __device__ __forceinline__ int mate_of(const DevReads &R, int r) {
     return -1;
 }
 
-__global__ void __launch_bounds__(256) cand3_kernel(DevPanel P, DevReads R, const idp_result *__restrict__ five,
+__global__ void __launch_bounds__(256) cand3_kernel(DevPanel P, DevReads R, const ResultOut five,
                                                     Counters *__restrict__ ctr, unsigned int *__restrict__ all_list,
                                                     unsigned int *__restrict__ pair_work, unsigned int *__restrict__ pair_primer,
                                                     unsigned int pair_cap, unsigned int *__restrict__ seg_off, int *__restrict__ seg_cnt) {
@@ -355,9 +233,9 @@ __global__ void __launch_bounds__(256) cand3_kernel(DevPanel P, DevReads R, cons
     int count = 0, first = -1, mode = 0;  // mode 0: nothing, 1: single primer, 2: mates of own primer, 3: all primers
     if (r < R.n) {
         const int mate = mate_of(R, r);
-        const int own_type = five[r].type, own_primer = five[r].primer;
-        int other_type = IDP_NONE, other_primer = -1;
-        if (mate >= 0) { other_type = five[mate].type; other_primer = five[mate].primer; }
+        int own_type, own_primer, other_type = IDP_NONE, other_primer = -1;
+        read_type_primer(five, r, own_type, own_primer);
+        if (mate >= 0) read_type_primer(five, mate, other_type, other_primer);
         if (other_type != IDP_NONE) { mode = 1; count = 1; first = other_primer; }                       // IP:495
         else if (own_type != IDP_NONE) { mode = 2; first = own_primer; count = P.mate_off[own_primer + 1] - P.mate_off[own_primer]; }  // IP:496
         else mode = 3;                                                                                   // IP:497
@@ -1173,7 +1051,7 @@ __device__ Traced sw_trace(const DevPanel &P, const uint32_t *__restrict__ qword
 // NQ > 0 selects the register-resident re-alignment, otherwise the generic one with TN rows in local memory.
 template <int TN, int NQ>
 __device__ void finish_gapped(const DevPanel &P, const DevReads &R, int r, const Fin &f, bool three_prime, const TracedReg *pre,
-                              idp_result *__restrict__ out, uint8_t *__restrict__ rtype) {
+                              const ResultOut &out, uint8_t *__restrict__ rtype) {
     idp_result res = none_result();
     if (f.count > 0) {
         if (f.raw == kScoreMissing) res.status = IDP_STATUS_SCORE_MISSING;
@@ -1206,7 +1084,7 @@ __device__ void finish_gapped(const DevPanel &P, const DevReads &R, int r, const
             if (!(rate >= P.min_alignment_score_rate)) { const uint8_t st = res.status; res = none_result(); res.status = st; }
         }
     }
-    write_result(&out[r], res);
+    write_result(out, r, res);
     if (rtype != nullptr && res.type != IDP_NONE) rtype[r] = res.type;  // the scan kernel left IDP_NONE there
 }
 
@@ -1216,7 +1094,7 @@ __global__ void __launch_bounds__(128) finalize_pairs_kernel(DevPanel P, DevRead
                                                              const unsigned int *__restrict__ n_work_ptr, unsigned int n_work_fixed,
                                                              const unsigned int *__restrict__ seg_off, const int *__restrict__ seg_cnt,
                                                              const unsigned int *__restrict__ pair_primer, const int *__restrict__ pair_score,
-                                                             const unsigned int *__restrict__ pair_se, idp_result *__restrict__ out,
+                                                             const unsigned int *__restrict__ pair_se, const ResultOut out,
                                                              uint8_t *__restrict__ rtype, Counters *__restrict__ ctr_out, int three_prime) {
     const unsigned n_work = n_work_ptr ? *n_work_ptr : n_work_fixed;
     unsigned long long aligned = 0;
@@ -1252,7 +1130,7 @@ __global__ void __launch_bounds__(128) finalize_pairs_kernel(DevPanel P, DevRead
 template <int TN, int NQ>
 __global__ void __launch_bounds__(128) finalize_all_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
                                                            const unsigned int *__restrict__ n_work_ptr, const Fin *__restrict__ fin,
-                                                           idp_result *__restrict__ out, uint8_t *__restrict__ rtype, int three_prime) {
+                                                           const ResultOut out, uint8_t *__restrict__ rtype, int three_prime) {
     const unsigned n_work = *n_work_ptr;
     for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x)
         finish_gapped<TN, NQ>(P, R, (int)work_read[w], fin[w], three_prime != 0, nullptr, out, rtype);
@@ -1325,4 +1203,3 @@ __global__ void __launch_bounds__(256) metrics_kernel(DevReads R, const uint8_t 
 
 }  // namespace idp
 
-#include "idp_scan.cuh"

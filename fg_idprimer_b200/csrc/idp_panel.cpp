@@ -384,6 +384,73 @@ int idp_panel_create(const idp_primer *primers, int32_t n, const idp_params *par
             }
         }
     }
+    // exact-prefix table for the scan kernel's common case (DevPanel::fx_tab): every spelling of the first 12 bases of every
+    // ISOLATED primer.  Isolated = every other primer q has at least two positions among the first 12 whose codes share no
+    // base with this primer's: then no read that spells this prefix without a mismatch can be within one mismatch of q
+    // (PM:143: a read code must be a subset of the primer code to match), so the primer is the only one mismatchAlign can
+    // accept whenever every primer tolerates at most one mismatch (acc_max <= 1).
+    {
+        int min_len = INT32_MAX;
+        for (int i = 0; i < n; ++i) min_len = std::min(min_len, p->seq_len[i]);
+        const bool ok = p->acc_max <= 1 && min_len >= kFxBases && n <= 16384 && n < 65535;
+        if (ok) {
+            std::vector<uint32_t> a0(n), a1(n);
+            for (int i = 0; i < n; ++i) { a0[i] = p->pmask[(size_t)i * p->ww]; a1[i] = p->pmask[(size_t)i * p->ww + 1] | 0xFFFF0000u; }
+            auto zero_nibbles = [](uint32_t x) { x |= x >> 1; x |= x >> 2; return __builtin_popcount(~x & 0x11111111u); };
+            std::vector<uint8_t> isolated(n, 1);
+            for (int i = 0; i < n; ++i)
+                for (int j = i + 1; j < n; ++j)
+                    if (zero_nibbles(a0[i] & a0[j]) + zero_nibbles(a1[i] & a1[j]) < 2) isolated[i] = isolated[j] = 0;
+            // spellings in A/C/G/T only: a read with an ambiguity code in its first 12 bases takes the filter instead
+            std::vector<std::array<uint32_t, 3>> ent;  // (w0, w1 low half, primer)
+            for (int i = 0; i < n; ++i) {
+                if (!isolated[i]) continue;
+                uint32_t codes[kFxBases], sub[kFxBases];
+                size_t variants = 1;
+                for (int j = 0; j < kFxBases; ++j) {
+                    codes[j] = ((j < 8 ? a0[i] : a1[i]) >> (4 * (j & 7))) & 15u;
+                    variants *= (size_t)__builtin_popcount(codes[j]);
+                    if (variants > 256) break;
+                }
+                if (variants == 0 || variants > 256) continue;  // such a read falls back to the filter, which is exact for every read
+                for (int j = 0; j < kFxBases; ++j) sub[j] = codes[j] & (~codes[j] + 1u);  // lowest base of every position
+                for (;;) {
+                    uint32_t w0 = 0, w1 = 0;
+                    for (int j = 0; j < 8; ++j) w0 |= sub[j] << (4 * j);
+                    for (int j = 8; j < kFxBases; ++j) w1 |= sub[j] << (4 * (j - 8));
+                    ent.push_back({w0, w1, (uint32_t)i});
+                    int j = 0;  // odometer over the single bases of every position
+                    for (; j < kFxBases; ++j) {
+                        const uint32_t rest = codes[j] & ~((sub[j] << 1) - 1u);  // bases above the current one
+                        if (rest != 0) { sub[j] = rest & (~rest + 1u); break; }
+                        sub[j] = codes[j] & (~codes[j] + 1u);
+                    }
+                    if (j == kFxBases) break;
+                }
+            }
+            if (!ent.empty() && ent.size() <= (size_t(1) << 16)) {
+                int bits = 10;
+                while ((size_t(1) << bits) < 8 * ent.size()) ++bits;
+                p->fx_slots = 1 << bits; p->fx_shift = 32 - bits;
+                // a slot holds one spelling; a spelling that loses its slot sends its reads through the filter (still exact), so
+                // the multiplier with the fewest collisions among a few candidates is kept
+                size_t best_lost = ent.size() + 1;
+                std::vector<uint8_t> used;
+                for (uint32_t t = 0; t < 32 && best_lost > 0; ++t) {
+                    const uint32_t mul = 0x9E3779B1u + 2u * t * 0x632BE5ABu;
+                    used.assign((size_t)p->fx_slots, 0);
+                    size_t lost = 0;
+                    for (auto &e : ent) { uint8_t &u = used[fx_hash(e[0], e[1], mul, p->fx_shift)]; lost += u; u = 1; }
+                    if (lost < best_lost) { best_lost = lost; p->fx_mul = mul; }
+                }
+                p->fx_tab.assign((size_t)p->fx_slots, 0);
+                for (auto &e : ent) {
+                    uint16_t &slot = p->fx_tab[fx_hash(e[0], e[1], p->fx_mul, p->fx_shift)];
+                    if (slot == 0) slot = (uint16_t)(e[2] + 1);
+                }
+            }
+        }
+    }
     // location matcher (PM:162-172): one sorted array per strand
     for (int strand = 0; strand < 2; ++strand) {  // 0 = positive, 1 = negative
         std::vector<int> ids;

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define IDP_ABI_VERSION 1
+#define IDP_ABI_VERSION 2
 
 /* ---- return codes ---- */
 #define IDP_OK               0
@@ -119,6 +119,21 @@ typedef struct {
     int16_t t_end;        /* gapped: Alignment.targetEnd                                                      */
 } idp_result;             /* 32 bytes */
 
+/* The same PrimerMatch in 16 bytes: the record the windowed / compact entry points (idp_match_batch16*) write, half the
+ * device->host bytes of idp_result.  A type-tagged union: `a` / `b` are numMismatches / nextNumMismatches for Location and
+ * Ungapped matches (PMa:96-104; b = IDP_NEXT16_NA renders "na") and Alignment.score of the best / runner-up candidate for
+ * Gapped ones (PM:315-322).  idp_result16_unpack() gives back the 32-byte record bit for bit. */
+#define IDP_NEXT16_NA 32767
+typedef struct {
+    uint32_t head;        /* bits 0..23 primer index + 1 (0 = no match), 24..25 type, 26 multi, 27..29 status             */
+    int16_t  a;           /* location / ungapped: mm;       gapped: raw_score                                          */
+    int16_t  b;           /* ungapped: next_mm or IDP_NEXT16_NA; gapped: raw_next; else 0                              */
+    uint16_t q_len;       /* gapped: as in idp_result                                                                  */
+    uint16_t q_len_next;
+    uint16_t t_start;
+    uint16_t t_end;
+} idp_result16;           /* 16 bytes */
+
 /* device-side timing and work counters of the last idp_match_batch*() call on a context */
 typedef struct {
     float    ms_total;            /* first H2D/kernel to last D2H/kernel, CUDA events                          */
@@ -136,6 +151,7 @@ typedef struct {
                                    * of the scan kernel is 3 % slower), else 0                                    */
     int64_t  kernel_launches;     /* kernels of this library launched by the call                              */
     int64_t  h2d_bytes, d2h_bytes;
+    int64_t  n_scan_parked;       /* reads the exact-prefix table of the scan kernel did not decide (they took the filter pass) */
 } idp_timings;
 
 typedef struct idp_panel idp_panel;  /* immutable after create; shareable across threads and devices           */
@@ -178,6 +194,17 @@ int idp_match_batch(idp_ctx *ctx, const idp_reads *reads, int32_t n_reads, idp_r
  * (metrics160 / n_gapped_alignments stay host pointers).  No host<->device copy of reads or results happens. */
 int idp_match_batch_device(idp_ctx *ctx, const idp_reads *reads, int32_t n_reads, idp_result *five, idp_result *three,
                            int64_t *metrics160, int64_t *n_gapped_alignments);
+
+/* The same two calls writing 16-byte records (idp_result16).  This is what a caller that ships windowed batches
+ * (idp_bam_to_batch_window) should use: 18 B of bases + 2 B of flags in and 16 B out per 150 bp read instead of 77 B in and
+ * 32 B out.  IDP_ERR_UNSUPPORTED when the panel's scores or size do not fit the record (|alignment score| >= 32767 possible,
+ * or 2^24 - 1 primers or more): use the 32-byte calls then. */
+int idp_match_batch16(idp_ctx *ctx, const idp_reads *reads, int32_t n_reads, idp_result16 *five, idp_result16 *three,
+                      int64_t *metrics160, int64_t *n_gapped_alignments);
+int idp_match_batch16_device(idp_ctx *ctx, const idp_reads *reads, int32_t n_reads, idp_result16 *five, idp_result16 *three,
+                             int64_t *metrics160, int64_t *n_gapped_alignments);
+/* host: n 16-byte records -> the 32-byte records idp_match_batch would have written (pure function) */
+void idp_result16_unpack(const idp_result16 *in, int64_t n, idp_result *out);
 
 /* ---- the aligner seam: a batched AsyncAligner.align (AA:37-54) ----
  * queries/targets are ASCII, concatenated, with n+1 offsets; outputs are Alignment.score, targetStart and

@@ -59,13 +59,35 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def use_fast_build() -> str:
+    """bench.py's reference arm / cpu_baseline only: switch this process to a -O3 -march=native build of the same source
+    (BASELINE.md section 2), compiled on the machine that runs it (the file name carries a hash of the CPU's flags, so a
+    copy built elsewhere is never loaded).  The checker keeps the -O2 -g build."""
+    global _LIB_PATH, _lib
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as fh:
+            flags = next((ln for ln in fh if ln.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    tag = hashlib.sha1(flags.encode()).hexdigest()[:10]
+    path = os.path.join(_HERE, f"libidp_oracle_fast_{tag}.so")
+    src = os.path.join(_HERE, "idp_oracle.c")
+    if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "idp_oracle.h"))):
+        subprocess.check_call([os.environ.get("CC", "gcc"), "-O3", "-march=native", "-fPIC", "-std=gnu11", "-pthread", "-shared", "-o", path, src, "-lm", "-lpthread"])
+    if path != _LIB_PATH:
+        _LIB_PATH, _lib = path, None
+    return path
+
+
 _lib = None
 
 
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        build()
+        if os.path.basename(_LIB_PATH) == "libidp_oracle.so":
+            build()
         L = C.CDLL(_LIB_PATH)
         L.orc_panel_create.restype = C.c_void_p
         L.orc_panel_create.argtypes = [C.POINTER(OrcPrimer), C.c_int, C.POINTER(OrcParams)]

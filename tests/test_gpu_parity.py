@@ -1,5 +1,7 @@
 """GPU parity: the CUDA path (through the C-ABI, host buffers) against the CPU oracle on the same inputs, bit-exact on
 every result field, the 160-bin metric counter and the alignment count; plus the reference's own known-answer numbers."""
+import os
+
 import numpy as np
 import pytest
 
@@ -50,7 +52,26 @@ def run_both(primers, arrays, ref_names=H.DEFAULT_DICT, oracle_threads=8, **opts
         assert tool.num_alignments == want_align
         t = tool.timings()
         assert t["kernel_launches"] > 0
-        return got5, got3, tool.summary(), t
+        summary = tool.summary()
+        # the same batch through the 16-byte records (idp_match_batch16), with the scan kernel's exact-prefix shortcut switched
+        # off: the rows unpack to the very same bytes, and the counters double
+        os.environ["IDP_SCAN_NO_FX"] = "1"
+        try:
+            c5, c3 = tool.process_batch(batch, compact=True)
+        finally:
+            del os.environ["IDP_SCAN_NO_FX"]
+        assert c5.tobytes() == got5.tobytes(), "16-byte records / filter path differ (5')"
+        if got3 is not None:
+            assert c3.tobytes() == got3.tobytes(), "16-byte records / filter path differ (3')"
+        assert np.array_equal(tool.metric_counter, 2 * want_metrics) and tool.num_alignments == 2 * want_align
+        if opts.get("three_prime", -1) < 0:
+            # and cut to the bases the 5' chain can reach (what idp_bam_to_batch_window ships): same rows again
+            cut = idp.ReadBatch.from_ascii(arrays["bases"], arrays["off"], arrays["flags"], arrays["ref_idx"], arrays["ustart"], arrays["uend"],
+                                           window=tool.window())
+            w5, _ = tool.process_batch(cut, compact=True)
+            assert w5.tobytes() == got5.tobytes(), "windowed batch differs"
+            assert np.array_equal(tool.metric_counter, 3 * want_metrics) and tool.num_alignments == 3 * want_align
+        return got5, got3, summary, t
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.idp_abi_version() == 1
+    assert lib.idp_abi_version() == 2
 
 
 def test_no_gpu_means_loud_failure_not_fallback():
