@@ -21,7 +21,7 @@ EXPORTS = ["idp_abi_version", "idp_last_error", "idp_device_count", "idp_panel_c
            "idp_panel_primer_length", "idp_panel_primer_hash", "idp_panel_kmer_postings", "idp_ctx_create", "idp_ctx_destroy",
            "idp_ctx_set_stream", "idp_ctx_timings", "idp_host_alloc", "idp_host_free", "idp_match_batch", "idp_match_batch_device",
            "idp_match_batch16", "idp_match_batch16_device", "idp_result16_unpack", "idp_align_batch", "idp_result_score", "idp_result_second", "idp_metric_bin", "idp_summary_metrics", "idp_format_info",
-           "idp_pack_bases", "idp_unpack_bases", "idp_classify_primer_pair", "idp_classify_templates", "idp_bam_scan", "idp_bam_to_batch", "idp_bam_to_batch_window", "idp_panel_window",
+           "idp_pack_bases", "idp_unpack_bases", "idp_classify_primer_pair", "idp_classify_templates", "idp_classify_batch_device", "idp_ctx_set_classify", "idp_bam_scan", "idp_bam_to_batch", "idp_bam_to_batch_window", "idp_panel_window",
            "idp_bam_annotate", "idp_header_comments"]
 
 
@@ -105,7 +105,7 @@ def lib() -> C.CDLL:
     L.idp_result16_unpack.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     L.idp_result16_unpack.restype = None
     L.idp_align_batch.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int32,
-                                  C.c_void_p, C.c_void_p, C.c_void_p]
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.idp_result_score.argtypes = [C.c_void_p]
     L.idp_result_score.restype = C.c_double
     L.idp_result_second.argtypes = [C.c_void_p]
@@ -115,6 +115,8 @@ def lib() -> C.CDLL:
     L.idp_format_info.argtypes = [C.c_void_p, C.c_void_p, C.c_uint16, C.c_char_p, C.c_int32]
     L.idp_classify_primer_pair.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     L.idp_classify_templates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.idp_classify_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.idp_ctx_set_classify.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     L.idp_bam_scan.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.idp_bam_to_batch.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 8
     L.idp_bam_to_batch_window.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t] + [C.c_void_p] * 8

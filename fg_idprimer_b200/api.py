@@ -352,6 +352,7 @@ class IdentifyPrimers:
         metrics = np.zeros(160, dtype=np.int64)
         n_align = np.zeros(1, dtype=np.int64)
         fn = L.lib().idp_match_batch16 if compact else L.lib().idp_match_batch
+        self._arm_classify(n, device=False)
         L.check(fn(self._ctx, C.byref(rs), n, five.ctypes.data, None if three is None else three.ctypes.data,
                    metrics.ctypes.data, n_align.ctypes.data))
         self.metric_counter += metrics
@@ -373,6 +374,7 @@ class IdentifyPrimers:
         metrics = np.zeros(160, dtype=np.int64)
         n_align = np.zeros(1, dtype=np.int64)
         fn = L.lib().idp_match_batch16_device if compact else L.lib().idp_match_batch_device
+        self._arm_classify(n, device=True)
         L.check(fn(self._ctx, C.byref(rs), n, five_ptr, three_ptr or None, metrics.ctypes.data, n_align.ctypes.data))
         self.metric_counter += metrics
         self.num_alignments += int(n_align[0])
@@ -473,6 +475,36 @@ class IdentifyPrimers:
                                                cls.ctypes.data, counts.ctypes.data))
         return cls, dict(zip(self.CLASS_NAMES, counts.tolist()))
 
+    def set_classify(self, min_insert_length: int = 50, max_insert_length: int = 250, enable: bool = True, cls_ptr: int = 0):
+        """Device epilogue (idp_ctx_set_classify): every later process_batch* call also classifies the templates on the GPU.
+        `class_counts` accumulates the six counts; process_batch() returns the per-read classes in `last_classes`;
+        process_batch_device() writes them to the device array at cls_ptr (0 = counts only)."""
+        self._require_ctx()
+        self.class_counts = np.zeros(6, dtype=np.int64)
+        self._cls_on, self._cls_dev_ptr, self._cls_args = enable, cls_ptr, (min_insert_length, max_insert_length)
+        self.last_classes = None
+        if not enable:
+            L.check(L.lib().idp_ctx_set_classify(self._ctx, -1, 0, None, None))
+
+    def _arm_classify(self, n: int, device: bool):
+        if not getattr(self, "_cls_on", False):
+            return
+        if device:
+            ptr = self._cls_dev_ptr or None
+        else:
+            self.last_classes = np.zeros(n, dtype=np.uint8)
+            ptr = self.last_classes.ctypes.data
+        L.check(L.lib().idp_ctx_set_classify(self._ctx, self._cls_args[0], self._cls_args[1], ptr, self.class_counts.ctypes.data))
+
+    def classify_batch_device(self, flags_ptr: int, five_ptr: int, n: int, compact: bool, cls_ptr: int = 0, min_insert_length: int = 50,
+                              max_insert_length: int = 250):
+        """idp_classify_batch_device on device-resident flags and 5' records -> dict of the six counts."""
+        self._require_ctx()
+        counts = np.zeros(6, dtype=np.int64)
+        L.check(L.lib().idp_classify_batch_device(self._ctx, flags_ptr, five_ptr, 1 if compact else 0, n, min_insert_length, max_insert_length,
+                                                  cls_ptr or None, counts.ctypes.data))
+        return dict(zip(self.CLASS_NAMES, counts.tolist()))
+
     # ---- metrics (TemplateTypeMetric.scala:34-56, IdentifyPrimersMetric.scala:34-89) ----
     def summary(self) -> dict:
         out = np.zeros(17, dtype=np.int64)
@@ -504,15 +536,19 @@ class AsyncCudaAligner:
         self.mode = mode
         self.num_aligned = 0
 
-    def align(self, queries: Sequence[bytes], targets: Sequence[bytes]):
+    def align(self, queries: Sequence[bytes], targets: Sequence[bytes], query_coordinates: bool = False):
+        """-> (score, target_start, target_end) arrays, plus (query_start, query_end) when query_coordinates is set."""
         n = len(queries)
         q_off = np.zeros(n + 1, dtype=np.int64); q_off[1:] = np.cumsum([len(q) for q in queries])
         t_off = np.zeros(n + 1, dtype=np.int64); t_off[1:] = np.cumsum([len(t) for t in targets])
         score = np.zeros(n, dtype=np.int32); ts = np.zeros(n, dtype=np.int32); te = np.zeros(n, dtype=np.int32)
+        qs = np.zeros(n, dtype=np.int32) if query_coordinates else None
+        qe = np.zeros(n, dtype=np.int32) if query_coordinates else None
         L.check(L.lib().idp_align_batch(self._tool._ctx, self.mode, b"".join(queries), q_off.ctypes.data, b"".join(targets),
-                                        t_off.ctypes.data, n, score.ctypes.data, ts.ctypes.data, te.ctypes.data))
+                                        t_off.ctypes.data, n, score.ctypes.data, ts.ctypes.data, te.ctypes.data,
+                                        qs.ctypes.data if query_coordinates else None, qe.ctypes.data if query_coordinates else None))
         self.num_aligned += n
-        return score, ts, te
+        return (score, ts, te, qs, qe) if query_coordinates else (score, ts, te)
 
     def close(self):
         self._tool.close()

@@ -59,7 +59,7 @@ struct Slot {
     // staging for the host-pointer path
     DevBuf seq4, seq_off, len, ref_idx, ustart, uend, flags, five, three;
     // scratch of the chain
-    DevBuf fall, rtype, spill, all_list, seg_off, seg_cnt, pair_work, pair_primer, pair_score, pair_se, fin;
+    DevBuf fall, parked, masks, rtype, cls, spill, all_list, seg_off, seg_cnt, pair_work, pair_primer, pair_score, pair_se, fin;
     Counters *d_ctr = nullptr, *h_ctr = nullptr;
     size_t pair_cap = 0;
     bool busy = false;
@@ -79,15 +79,20 @@ struct idp_ctx {
     const idp_panel *panel = nullptr;
     int device = 0;
     LaunchCfg cfg{};
-    DevBuf b_fx, b_qbot, b_bylen, b_pmask, b_pinfo, b_positive, b_loc_key[2], b_loc_primer[2], b_mate_off, b_mate_idx, b_smat;
-    DevBuf b_keys[2], b_offcnt[2], b_postings[2], b_heads[2], b_direct[2], b_bsmm, b_bsacc, b_seedtab, b_seedlist, b_diag;
+    DevBuf b_fx, b_pm4, b_dfx, b_cinfo, b_cspan, b_qbot, b_bylen, b_pmask, b_pinfo, b_positive, b_loc_key[2], b_loc_primer[2], b_mate_off, b_mate_idx, b_smat;
+    DevBuf b_keys[2], b_offcnt[2], b_postings[2], b_heads[2], b_direct[2], b_dbits[2], b_bsmm, b_bsacc, b_seedtab, b_seedlist, b_diag;
     Slot slots[kSlots];
     cudaStream_t user_stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_finish = nullptr;  // first copy / last harvest of an idp_match_batch call
     idp_timings last{};
     bool compact_ok = false;  // every value of this panel's results fits idp_result16
+    // classification epilogue (idp_ctx_set_classify)
+    bool cls_on = false;
+    int32_t cls_min = 0, cls_max = 0;
+    uint8_t *cls_user = nullptr;    // host (idp_match_batch*) or device (*_device) array of the caller
+    int64_t *cls_counts = nullptr;  // host, added to
     // idp_align_batch staging (device + pinned host), grown on demand and kept
-    DevBuf al_q, al_ql, al_t, al_to, al_tl, al_out;
+    DevBuf al_q, al_ql, al_t, al_to, al_tl, al_tp, al_out;  // ASCII queries, query offsets, ASCII targets, query words, target offsets, packed targets, results
 };
 
 namespace idp {
@@ -118,7 +123,7 @@ static int upload_panel(idp_ctx *c) {
         k.k = h.k > 0 ? h.k : -1;
         k.window = p.max_primer_length;
         k.slot_mask = 0; k.shift = 63; k.keys = nullptr; k.off_cnt = nullptr; k.postings = nullptr;
-        k.heads = nullptr; k.direct = nullptr; k.n_postings = 0;
+        k.heads = nullptr; k.direct = nullptr; k.direct_bits = nullptr; k.n_postings = 0;
         if (h.k > 0) {
             std::vector<OffCnt> oc(h.keys.size());
             for (size_t i = 0; i < oc.size(); ++i) oc[i] = OffCnt{h.off[i], h.cnt[i]};
@@ -131,7 +136,16 @@ static int upload_panel(idp_ctx *c) {
             k.keys = c->b_keys[w].as<uint64_t>(); k.off_cnt = c->b_offcnt[w].as<OffCnt>(); k.postings = c->b_postings[w].as<uint32_t>();
             if ((rc = upload(h.heads, c->b_heads[w]))) return rc;
             k.heads = c->b_heads[w].as<uint2>(); k.n_postings = (uint32_t)h.postings.size();
-            if (!h.direct.empty()) { if ((rc = upload(h.direct, c->b_direct[w]))) return rc; k.direct = c->b_direct[w].as<uint32_t>(); }
+            if (!h.direct.empty()) {
+                if ((rc = upload(h.direct, c->b_direct[w]))) return rc;
+                k.direct = c->b_direct[w].as<uint32_t>();
+                if (h.k <= 10) {  // presence bits of the direct table, for cand5_thread_kernel's shared-memory prefilter
+                    std::vector<uint32_t> bits((h.direct.size() + 31) / 32, 0u);
+                    for (size_t i = 0; i < h.direct.size(); ++i) if (h.direct[i]) bits[i >> 5] |= 1u << (i & 31);
+                    if ((rc = upload(bits, c->b_dbits[w]))) return rc;
+                    k.direct_bits = c->b_dbits[w].as<uint32_t>();
+                }
+            }
         }
     }
     if ((rc = upload(p.bs_mm, c->b_bsmm)) || (rc = upload(p.bs_acc, c->b_bsacc))) return rc;
@@ -170,6 +184,43 @@ static int upload_panel(idp_ctx *c) {
     if (!p.fx_tab.empty() && d.bs_ok) {
         if ((rc = upload(p.fx_tab, c->b_fx))) return rc;
         d.fx_tab = c->b_fx.as<uint16_t>(); d.fx_shift = p.fx_shift; d.fx_slots = p.fx_slots;
+    }
+    c->cfg.pm4 = nullptr; c->cfg.rule_fx = nullptr;
+    if (d.fx_tab != nullptr && p.ww <= 4) {
+        // scan_fx_kernel's copies, in the nibble order of the stored rows (base i of a word in nibble i ^ 1): the masks padded to
+        // four words per primer (one 16-byte load), and the k-mer rule table with its bits where the kernel's mismatch flags are
+        auto stored = [](uint32_t x) { return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu); };
+        std::vector<uint4> pm4(p.n);
+        std::vector<uint2> dfx(p.n, make_uint2(0u, 0u));  // FxLaunch::rule
+        const int k = p.kidx[0].k;
+        for (int i = 0; i < p.n; ++i) {
+            uint32_t w[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+            for (int t = 0; t < p.ww; ++t) w[t] = stored(p.pmask[(size_t)i * p.ww + t]);
+            pm4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+            if (k > 0) {  // as DevPanel::diag above: a run of k non-degenerate primer letters that avoids position b
+                const int L = std::min(p.max_primer_length, p.seq_len[i]);
+                uint32_t plain = 0;
+                for (int b = 0; b < L && b < 32; ++b) {
+                    const uint32_t code = (p.pmask[(size_t)i * p.ww + b / 8] >> (4 * (b % 8))) & 15u;
+                    if (__builtin_popcount(code) == 1) plain |= 1u << b;
+                }
+                auto has_run = [&](uint32_t e) { uint32_t r = e; for (int t = 1; t < k; ++t) r &= e >> t; return k <= 32 && r != 0u; };
+                uint32_t ok = 0;
+                for (int b = 0; b < 32; ++b) if (has_run(plain & ~(1u << b))) ok |= 1u << fx_where_bit(b / 8, (b % 8) ^ 1);
+                dfx[i] = make_uint2(has_run(plain) ? 1u << 30 : 0u, ok);
+            }
+            dfx[i].x |= (uint32_t)p.plen[i] | ((uint32_t)std::min(p.cap_full[i], 1023) << 10) | ((uint32_t)std::max(p.acc_full[i], 0) << 20);
+        }
+        if ((rc = upload(pm4, c->b_pm4)) || (rc = upload(dfx, c->b_dfx))) return rc;
+        c->cfg.pm4 = c->b_pm4.as<uint4>();
+        c->cfg.rule_fx = c->b_dfx.as<uint2>();
+    }
+    {   // downstream classification tables
+        std::vector<int4> ci(p.n);
+        std::vector<int2> cs(p.n);
+        for (int i = 0; i < p.n; ++i) { ci[i] = make_int4(p.pair_of[i], p.primer_id_key[i], p.ref_name_key[i], p.positive[i]); cs[i] = make_int2(p.start[i], p.end[i]); }
+        if ((rc = upload(ci, c->b_cinfo)) || (rc = upload(cs, c->b_cspan))) return rc;
+        d.cls_info = c->b_cinfo.as<int4>(); d.cls_span = c->b_cspan.as<int2>();
     }
     if ((rc = upload(p.mate_off, c->b_mate_off))) return rc;
     if ((rc = upload(p.mate_idx, c->b_mate_idx))) return rc;
@@ -234,13 +285,13 @@ static int upload_panel(idp_ctx *c) {
 
 // Enqueue the whole matcher chain for reads already on the device.  Nothing here waits on the host.
 // five / three: where the per-read records go, in either format (ResultOut).
-static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R, ResultOut five, ResultOut three) {
+static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R, ResultOut five, ResultOut three, uint8_t *cls_dev) {
     const idp_panel &p = *c->panel;
     const LaunchCfg &cfg = c->cfg;
     const size_t n = (size_t)R.n;
     int rc;
     const bool k_gapped = p.kidx[1].k > 0, do3 = p.params.three_prime >= 0;
-    if ((rc = s.fall.ensure(n * 4))) return rc;
+    if ((rc = s.fall.ensure(n * 4)) || (rc = s.parked.ensure(n * 4)) || (rc = s.masks.ensure(((n + 31) / 32) * 8 + 8))) return rc;
     if (k_gapped && (rc = s.spill.ensure(n * 4))) return rc;
     if (k_gapped || do3) {
         if (s.pair_cap < 2 * n + 4096) s.pair_cap = 2 * n + 4096;
@@ -257,8 +308,7 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
     CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(Counters), st));
     CUDA_TRY(cudaEventRecord(s.ev[EV_START], st));
     if (n > 0) {
-        if ((rc = launch_scan(cfg, st, R, five, rtype, fall, ctr))) return rc;
-        ++s.launches;
+        if ((rc = launch_scan(cfg, st, R, five, rtype, fall, s.parked.as<unsigned>(), s.masks.as<uint32_t>(), ctr, &s.launches))) return rc;
     }
     CUDA_TRY(cudaEventRecord(s.ev[EV_SCAN], st));
     // ---- 5' gapped stage over the fall-through list ----
@@ -280,6 +330,10 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
             s.launches += 2;
         }
     } else { CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st)); CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st)); }
+    if (c->cls_on && n > 0) {  // classification epilogue on the finished 5' records
+        launch_classify(cfg, st, R.flags, five, R.n, c->cls_min, c->cls_max, cls_dev, ctr);
+        ++s.launches;
+    }
     CUDA_TRY(cudaEventRecord(s.ev[EV_GAPPED], st));
     // ---- 3' stage (IP:483-516) ----
     if (do3 && n > 0 && three.p) {
@@ -354,7 +408,7 @@ static int match_batch_device(idp_ctx *c, const idp_reads *reads, int32_t n_read
     DevReads R{reads->seq4, reads->seq_off, reads->len, reads->ref_idx, reads->unclipped_start, reads->unclipped_end, reads->flags, reads->fixed_len, n_reads};
     c->last = idp_timings{};
     for (int attempt = 0;; ++attempt) {
-        if ((rc = enqueue_chain(c, s, st, R, ResultOut{five, compact}, ResultOut{three, compact}))) { cudaStreamSynchronize(st); cudaGetLastError(); return rc; }
+        if ((rc = enqueue_chain(c, s, st, R, ResultOut{five, compact}, ResultOut{three, compact}, c->cls_user))) { cudaStreamSynchronize(st); cudaGetLastError(); return rc; }
         CUDA_TRY(cudaStreamSynchronize(st));
         if (s.h_ctr->overflow == 0) break;
         if (attempt >= 6) { set_error("candidate pair buffer overflow persists after %d retries", attempt); return IDP_ERR_NOMEM; }
@@ -366,6 +420,7 @@ static int match_batch_device(idp_ctx *c, const idp_reads *reads, int32_t n_read
     c->last.ms_total = ms; c->last.n_reads = n_reads;
     if (metrics160) for (int i = 0; i < 160; ++i) metrics160[i] += (int64_t)s.h_ctr->metrics[i];
     if (n_gapped_alignments) *n_gapped_alignments += (int64_t)s.h_ctr->n_align5;
+    if (c->cls_on && c->cls_counts) for (int i = 0; i < 6; ++i) c->cls_counts[i] += (int64_t)s.h_ctr->classes[i];
     return IDP_OK;
 }
 
@@ -384,7 +439,8 @@ static int match_batch_host(idp_ctx *c, const idp_reads *reads, int32_t n_reads,
     if (chunk < 2) chunk = 2;
     const bool have_loc = reads->ref_idx && reads->unclipped_start && reads->unclipped_end;
     bool first = true;
-    int64_t total_metrics[160] = {0}, total_align = 0;
+    int64_t total_metrics[160] = {0}, total_align = 0, total_classes[6] = {0};
+    const bool cls_bytes = c->cls_on && c->cls_user != nullptr;
     uint8_t *five_b = static_cast<uint8_t *>(five), *three_b = static_cast<uint8_t *>(three);
 
     auto harvest = [&](Slot &s) -> int {
@@ -394,8 +450,9 @@ static int match_batch_host(idp_ctx *c, const idp_reads *reads, int32_t n_reads,
         for (int attempt = 0; s.h_ctr->overflow; ++attempt) {  // rare: redo this chunk (still resident in the slot) with more room
             if (attempt >= 6) { set_error("candidate pair buffer overflow persists after %d retries", attempt); return IDP_ERR_NOMEM; }
             s.pair_cap *= 4;
-            int rc2 = enqueue_chain(c, s, s.stream, s.R, ResultOut{s.five.p, compact}, ResultOut{do3 ? s.three.p : nullptr, compact});
+            int rc2 = enqueue_chain(c, s, s.stream, s.R, ResultOut{s.five.p, compact}, ResultOut{do3 ? s.three.p : nullptr, compact}, cls_bytes ? s.cls.as<uint8_t>() : nullptr);
             if (rc2) return rc2;
+            if (cls_bytes) CUDA_TRY(cudaMemcpyAsync(c->cls_user + s.chunk_begin, s.cls.p, s.chunk_n, cudaMemcpyDeviceToHost, s.stream));
             CUDA_TRY(cudaMemcpyAsync(five_b + s.chunk_begin * rec, s.five.p, s.chunk_n * rec, cudaMemcpyDeviceToHost, s.stream));
             if (do3) CUDA_TRY(cudaMemcpyAsync(three_b + s.chunk_begin * rec, s.three.p, s.chunk_n * rec, cudaMemcpyDeviceToHost, s.stream));
             CUDA_TRY(cudaStreamSynchronize(s.stream));
@@ -404,6 +461,7 @@ static int match_batch_host(idp_ctx *c, const idp_reads *reads, int32_t n_reads,
         first = false;
         for (int i = 0; i < 160; ++i) total_metrics[i] += (int64_t)s.h_ctr->metrics[i];
         total_align += (int64_t)s.h_ctr->n_align5;
+        for (int i = 0; i < 6; ++i) total_classes[i] += (int64_t)s.h_ctr->classes[i];
         return IDP_OK;
     };
 
@@ -426,6 +484,7 @@ static int match_batch_host(idp_ctx *c, const idp_reads *reads, int32_t n_reads,
         }
         if ((rc2 = s.seq4.ensure(byte1 - byte0 + 16)) || (rc2 = s.flags.ensure(cn * 2)) || (rc2 = s.five.ensure(cn * rec))) return rc2;
         if (do3 && (rc2 = s.three.ensure(cn * rec))) return rc2;
+        if (cls_bytes && (rc2 = s.cls.ensure(cn))) return rc2;
         CUDA_TRY(cudaMemcpyAsync(s.seq4.p, reads->seq4 + byte0, byte1 - byte0, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(s.flags.p, reads->flags + b, cn * 2, cudaMemcpyHostToDevice, st));
         c->last.h2d_bytes += (int64_t)(byte1 - byte0) + cn * 2;
@@ -449,8 +508,9 @@ static int match_batch_host(idp_ctx *c, const idp_reads *reads, int32_t n_reads,
         }
         s.R = R; s.chunk_begin = b; s.chunk_n = cn;
         s.busy = true;  // from here on the slot has work in flight, whatever happens below
-        if ((rc2 = enqueue_chain(c, s, st, R, ResultOut{s.five.p, compact}, ResultOut{do3 ? s.three.p : nullptr, compact}))) return rc2;
+        if ((rc2 = enqueue_chain(c, s, st, R, ResultOut{s.five.p, compact}, ResultOut{do3 ? s.three.p : nullptr, compact}, cls_bytes ? s.cls.as<uint8_t>() : nullptr))) return rc2;
         CUDA_TRY(cudaMemcpyAsync(five_b + b * rec, s.five.p, cn * rec, cudaMemcpyDeviceToHost, st));
+        if (cls_bytes) { CUDA_TRY(cudaMemcpyAsync(c->cls_user + b, s.cls.p, cn, cudaMemcpyDeviceToHost, st)); c->last.d2h_bytes += cn; }
         c->last.d2h_bytes += cn * (int64_t)rec;
         if (do3) { CUDA_TRY(cudaMemcpyAsync(three_b + b * rec, s.three.p, cn * rec, cudaMemcpyDeviceToHost, st)); c->last.d2h_bytes += cn * (int64_t)rec; }
         return IDP_OK;
@@ -477,6 +537,7 @@ static int match_batch_host(idp_ctx *c, const idp_reads *reads, int32_t n_reads,
     }
     if (metrics160) for (int i = 0; i < 160; ++i) metrics160[i] += total_metrics[i];
     if (n_gapped_alignments) *n_gapped_alignments += total_align;
+    if (c->cls_on && c->cls_counts) for (int i = 0; i < 6; ++i) c->cls_counts[i] += total_classes[i];
     return IDP_OK;
 }
 
@@ -529,7 +590,7 @@ void idp_ctx_destroy(idp_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (Slot &s : c->slots) {
-        for (DevBuf *b : {&s.seq4, &s.seq_off, &s.len, &s.ref_idx, &s.ustart, &s.uend, &s.flags, &s.five, &s.three, &s.fall, &s.spill, &s.all_list,
+        for (DevBuf *b : {&s.seq4, &s.seq_off, &s.len, &s.ref_idx, &s.ustart, &s.uend, &s.flags, &s.five, &s.three, &s.fall, &s.parked, &s.masks, &s.cls, &s.spill, &s.all_list,
                           &s.seg_off, &s.seg_cnt, &s.pair_work, &s.pair_primer, &s.pair_score, &s.pair_se, &s.fin, &s.rtype}) b->release();
         if (s.d_ctr) cudaFree(s.d_ctr);
         if (s.h_ctr) cudaFreeHost(s.h_ctr);
@@ -538,10 +599,10 @@ void idp_ctx_destroy(idp_ctx *c) {
     }
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_finish) cudaEventDestroy(c->ev_finish);
-    for (DevBuf *b : {&c->b_fx, &c->b_qbot, &c->b_bylen, &c->b_pmask, &c->b_pinfo, &c->b_positive, &c->b_loc_key[0], &c->b_loc_key[1], &c->b_loc_primer[0], &c->b_loc_primer[1],
+    for (DevBuf *b : {&c->b_fx, &c->b_pm4, &c->b_dfx, &c->b_cinfo, &c->b_cspan, &c->b_qbot, &c->b_bylen, &c->b_pmask, &c->b_pinfo, &c->b_positive, &c->b_loc_key[0], &c->b_loc_key[1], &c->b_loc_primer[0], &c->b_loc_primer[1],
                       &c->b_mate_off, &c->b_mate_idx, &c->b_smat, &c->b_keys[0], &c->b_keys[1], &c->b_offcnt[0], &c->b_offcnt[1],
-                      &c->b_postings[0], &c->b_postings[1], &c->b_heads[0], &c->b_heads[1], &c->b_direct[0], &c->b_direct[1], &c->b_bsmm, &c->b_bsacc, &c->b_seedtab, &c->b_seedlist, &c->b_diag,
-                      &c->al_q, &c->al_ql, &c->al_t, &c->al_to, &c->al_tl, &c->al_out}) b->release();
+                      &c->b_postings[0], &c->b_postings[1], &c->b_heads[0], &c->b_heads[1], &c->b_direct[0], &c->b_direct[1], &c->b_dbits[0], &c->b_dbits[1], &c->b_bsmm, &c->b_bsacc, &c->b_seedtab, &c->b_seedlist, &c->b_diag,
+                      &c->al_q, &c->al_ql, &c->al_t, &c->al_to, &c->al_tl, &c->al_tp, &c->al_out}) b->release();
     delete c;
 }
 
@@ -574,6 +635,31 @@ int idp_match_batch16(idp_ctx *c, const idp_reads *reads, int32_t n_reads, idp_r
     return match_batch_host(c, reads, n_reads, five, three, true, metrics160, n_gapped_alignments);
 }
 
+int idp_ctx_set_classify(idp_ctx *c, int32_t min_insert_length, int32_t max_insert_length, uint8_t *cls_per_read, int64_t *counts6) {
+    if (!c) { set_error("idp_ctx_set_classify: NULL context"); return IDP_ERR_ARG; }
+    c->cls_on = min_insert_length >= 0;
+    c->cls_min = min_insert_length; c->cls_max = max_insert_length;
+    c->cls_user = c->cls_on ? cls_per_read : nullptr;
+    c->cls_counts = c->cls_on ? counts6 : nullptr;
+    return IDP_OK;
+}
+
+int idp_classify_batch_device(idp_ctx *c, const uint16_t *flags, const void *five, int compact, int32_t n_reads, int32_t min_insert_length,
+                              int32_t max_insert_length, uint8_t *cls_per_read, int64_t *counts6) {
+    if (!c || n_reads < 0 || (n_reads > 0 && (!flags || !five))) { set_error("idp_classify_batch_device: NULL argument"); return IDP_ERR_ARG; }
+    if (n_reads == 0) return IDP_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    Slot &s = c->slots[0];
+    cudaStream_t st = c->user_stream ? c->user_stream : s.stream;
+    CUDA_TRY(cudaMemsetAsync(s.d_ctr->classes, 0, sizeof(s.d_ctr->classes), st));
+    launch_classify(c->cfg, st, flags, ResultOut{const_cast<void *>(five), compact != 0}, n_reads, min_insert_length, max_insert_length, cls_per_read, s.d_ctr);
+    CUDA_TRY(cudaMemcpyAsync(s.h_ctr->classes, s.d_ctr->classes, sizeof(s.d_ctr->classes), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    if (counts6) for (int i = 0; i < 6; ++i) counts6[i] += (int64_t)s.h_ctr->classes[i];
+    return IDP_OK;
+}
+
 void idp_result16_unpack(const idp_result16 *in, int64_t n, idp_result *out) {
     for (int64_t i = 0; i < n; ++i) {
         const idp_result16 r = in[i];
@@ -592,56 +678,59 @@ void idp_result16_unpack(const idp_result16 *in, int64_t n, idp_result *out) {
 }
 
 // ---- batched AsyncAligner.align (AA:37-54) ----
+// Persistent per-context device buffers, every copy and kernel on the context's stream; the ASCII is packed and validated on
+// the GPU (align_pack_kernel), queries of up to 64 bases run on the register-resident aligners.
 int idp_align_batch(idp_ctx *c, int mode, const char *queries, const int64_t *q_off, const char *targets, const int64_t *t_off,
-                    int32_t n, int32_t *score, int32_t *target_start, int32_t *target_end) {
+                    int32_t n, int32_t *score, int32_t *target_start, int32_t *target_end, int32_t *query_start, int32_t *query_end) {
     if (!c || !queries || !q_off || !targets || !t_off || n < 0 || !score || !target_start || !target_end) { set_error("idp_align_batch: NULL argument"); return IDP_ERR_ARG; }
+    if ((query_start == nullptr) != (query_end == nullptr)) { set_error("idp_align_batch: query_start and query_end go together"); return IDP_ERR_ARG; }
     if (mode != IDP_MODE_LOCAL && mode != IDP_MODE_GLOCAL && mode != IDP_MODE_GLOBAL) { set_error("unknown alignment mode %d", mode); return IDP_ERR_ARG; }
     if (n == 0) return IDP_OK;
     CUDA_TRY(cudaSetDevice(c->device));
     int maxq = 1;
+    if (q_off[0] != 0 || t_off[0] != 0) { set_error("idp_align_batch: offsets must start at 0"); return IDP_ERR_ARG; }
     for (int i = 0; i < n; ++i) {
         const int64_t ql = q_off[i + 1] - q_off[i], tl = t_off[i + 1] - t_off[i];
         if (ql < 1 || ql > kMaxPrimerBases) { set_error("query %d: length %lld outside [1, %d]", i, (long long)ql, kMaxPrimerBases); return IDP_ERR_UNSUPPORTED; }
         if (tl < 0 || tl > kMaxReadLen) { set_error("target %d: length %lld outside [0, %d]", i, (long long)tl, kMaxReadLen); return IDP_ERR_UNSUPPORTED; }
         maxq = std::max<int>(maxq, (int)ql);
     }
-    const int qw = (maxq + 7) / 8;
-    std::vector<uint32_t> qwords((size_t)n * qw, 0);
-    std::vector<int32_t> qlen(n), tlen(n);
-    std::vector<uint64_t> toff(n);
-    std::vector<uint8_t> tseq;
-    auto code = [](char ch, bool &ok) { int v = base_to_nibble((unsigned char)ch); if (v == 15 && ch != 'N') ok = false; if (ch >= 'a' && ch <= 'z') ok = false; return v; };
-    bool ok = true;
-    for (int i = 0; i < n; ++i) {
-        qlen[i] = (int32_t)(q_off[i + 1] - q_off[i]); tlen[i] = (int32_t)(t_off[i + 1] - t_off[i]);
-        for (int b = 0; b < qlen[i]; ++b) qwords[(size_t)i * qw + b / 8] |= (uint32_t)code(queries[q_off[i] + b], ok) << (4 * (b % 8));
-        toff[i] = tseq.size();
-        for (int b = 0; b < tlen[i]; b += 2) {
-            const int hi = code(targets[t_off[i] + b], ok), lo = b + 1 < tlen[i] ? code(targets[t_off[i] + b + 1], ok) : 0;
-            tseq.push_back((uint8_t)((hi << 4) | lo));
-        }
-    }
-    if (!ok) { set_error("idp_align_batch: only upper-case IUPAC bases and '=' are supported"); return IDP_ERR_UNSUPPORTED; }
-    if (tseq.empty()) tseq.push_back(0);
+    const int64_t q_bytes = q_off[n], t_bytes = t_off[n];
+    const size_t off_bytes = (size_t)(n + 1) * 8;
+    const size_t words = (size_t)n * std::max(8, (maxq + 7) / 8);
     int rc;
+    if ((rc = c->al_q.ensure((size_t)q_bytes + 16)) || (rc = c->al_t.ensure((size_t)t_bytes + 16)) || (rc = c->al_ql.ensure(off_bytes)) ||
+        (rc = c->al_tl.ensure(off_bytes)) || (rc = c->al_to.ensure(words * 4)) || (rc = c->al_tp.ensure(align_target_bytes(t_bytes, n))) ||
+        (rc = c->al_out.ensure((size_t)n * 20 + 16))) return rc;
     cudaStream_t st = c->user_stream ? c->user_stream : c->slots[0].stream;
-    // uploads ordered on the stream the kernel runs on (pageable sources: each call returns once its data is staged)
-    if ((rc = upload(qwords, c->al_q, 1, st, true)) || (rc = upload(qlen, c->al_ql, 1, st, true)) || (rc = upload(tseq, c->al_t, 1, st, true)) ||
-        (rc = upload(toff, c->al_to, 1, st, true)) || (rc = upload(tlen, c->al_tl, 1, st, true)) || (rc = c->al_out.ensure((size_t)n * 12))) {
-        cudaStreamSynchronize(st);
-        return rc;
-    }
     int32_t *o = c->al_out.as<int32_t>();
-    launch_align(c->cfg, st, c->al_q.as<uint32_t>(), qw, c->al_ql.as<int32_t>(), c->al_t.as<uint8_t>(), c->al_to.as<uint64_t>(), c->al_tl.as<int32_t>(),
-                 n, mode, o, o + n, o + 2 * (size_t)n);
-    cudaError_t e1 = cudaMemcpyAsync(score, o, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
-    cudaError_t e2 = cudaMemcpyAsync(target_start, o + n, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
-    cudaError_t e3 = cudaMemcpyAsync(target_end, o + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
-    cudaError_t e4 = cudaStreamSynchronize(st);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
-        set_error("idp_align_batch: CUDA failure: %s", cudaGetErrorString(e4 != cudaSuccess ? e4 : (e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3))));
+    unsigned *bad = reinterpret_cast<unsigned *>(o + 5 * (size_t)n);
+    cudaError_t e = cudaMemsetAsync(bad, 0, 4, st);
+    // uploads ordered on the stream the kernels run on (a pageable source is staged before each call returns)
+    if (e == cudaSuccess && q_bytes) e = cudaMemcpyAsync(c->al_q.p, queries, (size_t)q_bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && t_bytes) e = cudaMemcpyAsync(c->al_t.p, targets, (size_t)t_bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->al_ql.p, q_off, off_bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->al_tl.p, t_off, off_bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        launch_align(c->cfg, st, mode, c->al_q.as<char>(), c->al_ql.as<int64_t>(), c->al_t.as<char>(), c->al_tl.as<int64_t>(), n, maxq,
+                     c->al_to.as<uint32_t>(), c->al_tp.as<uint8_t>(), bad, o, o + n, o + 2 * (size_t)n,
+                     query_start ? o + 3 * (size_t)n : nullptr, query_start ? o + 4 * (size_t)n : nullptr);
+        e = cudaGetLastError();
+    }
+    unsigned h_bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(score, o, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(target_start, o + n, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(target_end, o + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && query_start) e = cudaMemcpyAsync(query_start, o + 3 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && query_end) e = cudaMemcpyAsync(query_end, o + 4 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st);
+    const cudaError_t es = cudaStreamSynchronize(st);  // always: nothing may stay in flight into the caller's arrays
+    if (e != cudaSuccess || es != cudaSuccess) {
+        set_error("idp_align_batch: CUDA failure: %s", cudaGetErrorString(e != cudaSuccess ? e : es));
+        cudaGetLastError();
         return IDP_ERR_CUDA;
     }
+    if (h_bad) { set_error("idp_align_batch: only upper-case IUPAC bases and '=' are supported"); return IDP_ERR_UNSUPPORTED; }
     return IDP_OK;
 }
 

@@ -1,5 +1,7 @@
 // Device-side data model and helpers shared by every kernel of the IdentifyPrimers matching path (sm_100a).
 #pragma once
+#include <cstddef>
+
 #include <cuda_runtime.h>
 
 #include "idp_internal.h"
@@ -21,17 +23,19 @@ struct DevReads {
 // device-side counters of one batch (one per stream slot)
 struct Counters {
     unsigned int n_fall;          // reads that fell through to the gapped stage
+    unsigned int n_parked;        // reads scan_fx_kernel left to scan_kernel; MUST follow n_fall (one 64-bit atomic bumps both)
     unsigned int n_pairs;         // (read, primer) pairs emitted for sw_pairs_kernel
     unsigned int n_all;           // 3' reads that take every primer
     unsigned int overflow;        // pair buffer too small: number of work items not emitted
     unsigned int n_spill;         // fall-through reads with more -K candidates than the per-thread list holds
-    unsigned int n_parked;        // reads the scan kernel parked for the filter pass (not decided by the exact-prefix table)
     unsigned long long n_align5;  // alignments performed by the 5' aligner (IP:424)
     unsigned long long n_align3;
     unsigned long long sw_cells;
     unsigned long long base_compares;
     unsigned long long metrics[160];
+    unsigned long long classes[6];  // templates per IDP_CLASS_* (classify_kernel; only templates whose first record is read 1)
 };
+static_assert(offsetof(Counters, n_parked) == offsetof(Counters, n_fall) + 4 && offsetof(Counters, n_fall) % 8 == 0, "n_fall / n_parked share one 64-bit word");
 
 // the winner (and runner-up) of one read's gapped candidates, before traceback
 struct Fin {
@@ -144,6 +148,88 @@ __device__ __forceinline__ idp_result none_result() {
     r.primer = -1; r.type = IDP_NONE; r.status = 0; r.multi = 0; r.reserved = 0;
     r.mm = 0; r.next_mm = 0; r.raw_score = 0; r.raw_next = 0; r.q_len = 0; r.q_len_next = 0; r.t_start = 0; r.t_end = 0;
     return r;
+}
+
+// ---- read window loaders: basesInSequencingOrder (PM:39-45), only the prefix the matchers can look at ----
+// reverse the 8 nibbles of a word
+__device__ __forceinline__ uint32_t rev8nib(uint32_t x) { return nibswap(__byte_perm(x, 0u, 0x0123)); }
+// htsjdk 2.16 SequenceUtil.complement on 8 codes at once: A<->T, C<->G (a nibble with exactly one bit set is bit-reversed),
+// every other code is kept (PM:42)
+__device__ __forceinline__ uint32_t comp8nib(uint32_t x) {
+    const uint32_t c = (x & 0x55555555u) + ((x >> 1) & 0x55555555u);
+    const uint32_t d = (c & 0x33333333u) + ((c >> 2) & 0x33333333u);   // bits set per nibble
+    const uint32_t one = (~nib_nonzero(d ^ 0x11111111u) & 0x11111111u) * 15u;  // nibbles holding exactly one bit
+    const uint32_t rev = ((x & 0x11111111u) << 3) | ((x & 0x22222222u) << 1) | ((x >> 1) & 0x22222222u) | ((x >> 3) & 0x11111111u);
+    return (x & ~one) | (rev & one);
+}
+template <int RW>
+__device__ __forceinline__ void mask_window(uint32_t (&win)[RW], int len) {
+    if (len < RW * 8) {
+#pragma unroll
+        for (int w = 0; w < RW; ++w) {
+            const int rem = len - w * 8;
+            if (rem < 8) win[w] = rem <= 0 ? 0u : (win[w] & ((1u << (4 * rem)) - 1u));
+        }
+    }
+}
+// wp: 4-byte aligned word pointer at or below the read's first byte (shared or global), bo: the read's byte offset from it
+// (0..3).  The caller guarantees that RW + 1 words (forward) / the words around the read's end (reverse, len >= 8 * RW) may be
+// read.  Forward: the first 8 * RW bases.  Reverse: the reverse complement of the last 8 * RW stored bases.
+template <int RW>
+__device__ __forceinline__ void window_from_words(const uint32_t *wp, int bo, int len, bool rc, uint32_t (&win)[RW]) {
+    if (!rc) {
+        const int sh = bo * 8;
+        uint32_t prev = wp[0];
+#pragma unroll
+        for (int w = 0; w < RW; ++w) {
+            const uint32_t next = wp[w + 1];
+            win[w] = nibswap(__funnelshift_r(prev, next, sh));
+            prev = next;
+        }
+        mask_window<RW>(win, len);
+    } else {
+        // stored base k sits at nibble 2 * bo + k of the stream whose word t is nibswap(wp[t]); window word w wants stored
+        // bases len - 8 - 8w .. len - 1 - 8w, reversed and complemented
+        const int n0 = 2 * bo + len - 8;
+        const int t0 = n0 >> 3, sh = 4 * (n0 & 7);
+        uint32_t hi = nibswap(wp[t0 + 1]);
+#pragma unroll
+        for (int w = 0; w < RW; ++w) {
+            const uint32_t lo = nibswap(wp[t0 - w]);
+            win[w] = comp8nib(rev8nib(__funnelshift_r(lo, hi, sh)));
+            hi = lo;
+        }
+    }
+}
+// the slow, always safe form: base by base through a generic pointer
+template <int RW>
+__device__ __forceinline__ void window_by_bases(const uint8_t *sp, int len, bool rc, uint32_t (&win)[RW]) {
+    Oriented o{sp, len, rc};
+    const int nb = min(len, RW * 8);
+#pragma unroll
+    for (int w = 0; w < RW; ++w) {
+        uint32_t v = 0;
+        for (int b = 0; b < 8; ++b) {
+            const int i = w * 8 + b;
+            if (i < nb) v |= o.nib_generic(i) << (4 * b);
+        }
+        win[w] = v;
+    }
+}
+// from global memory.  The word form reads up to 4 * RW + 7 bytes from the aligned address below the read (forward) or up
+// to 7 bytes past its last byte (reverse): allowed when the batch is fixed-length (rows are contiguous) and the read is not
+// among the last few, or when the read itself is long enough (forward only)
+template <int RW>
+__device__ __forceinline__ void window_from_global(const DevReads &R, int r, const uint8_t *s, int len, bool rc, uint32_t (&win)[RW]) {
+    const int bytes = (len + 1) >> 1;
+    const bool roomy = R.fixed_len > 0 && (size_t)(R.n - 1 - r) * (size_t)bytes >= (size_t)(4 * RW + 8);
+    const bool word_ok = rc ? (roomy && len >= 8 * RW) : (roomy || bytes >= 4 * RW + 4);
+    if (word_ok) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+        window_from_words<RW>(reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3)), (int)(a & 3), len, rc, win);
+    } else {
+        window_by_bases<RW>(s, len, rc, win);
+    }
 }
 
 __device__ __forceinline__ bool kmer_lookup(const DevKmerIndex &ix, uint64_t key, OffCnt &oc) {

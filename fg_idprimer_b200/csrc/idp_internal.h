@@ -18,11 +18,14 @@ constexpr int kMaxReadLen = 4095;      // target start/end are carried in 12 bit
 constexpr int32_t kNegInf = INT32_MIN / 2;  // fgbio Aligner.MinStartScore
 
 void set_error(const char *fmt, ...);
-// slot of a 12-base read prefix in the exact-prefix table: w0 = bases 0..7, w1 = bases 8..15 (base i in nibble i % 8)
+// slot of a 12-base read prefix in the exact-prefix table: w0 = bases 0..7, w1 = bases 8..15, as STORED in the row (base i of a
+// word in nibble i ^ 1); only the low half of w1 (bases 8..11) takes part
 #ifdef __CUDACC__
 __host__ __device__
 #endif
 inline uint32_t fx_hash(uint32_t w0, uint32_t w1, uint32_t mul, int shift) { return ((w0 * mul) ^ ((w1 & 0xFFFFu) * 0x85EBCA6Bu)) >> shift; }
+// bit of scan_fx_kernel's mismatch-flag word that stands for nibble `nibble` of window word `word` (idp_scanfx.cuh)
+inline int fx_where_bit(int word, int nibble) { return 4 * nibble + ((word & 1) << 1 | (word >> 1)); }
 
 struct OffCnt { uint32_t off, cnt; };
 
@@ -37,6 +40,7 @@ struct DevKmerIndex {
     const uint32_t *postings;  // primer indices in the iteration order of the reference's Set[Primer]
     const uint2 *heads;        // per posting {id | (accept+1) << 24, mask of the first 8 primer bases}
     const uint32_t *direct;    // NULL, or 4^k entries (2 bits per base, all-ACGT k-mers): posting offset | count << 20
+    const uint32_t *direct_bits;  // NULL, or 4^k bits: entry of `direct` is non-zero (k <= 10: the 128 KB map fits shared memory)
     uint32_t n_postings;
 };
 
@@ -76,7 +80,7 @@ struct DevPanel {
     const uint32_t *seed_tab;
     const uint32_t *seed_list;
     int32_t seed_ok, seed_S, seed_shift, seed_slots;
-    // exact-prefix table (the scan kernel's common case): fx_tab[hash(first 12 read bases)] = primer + 1 for a primer that
+    // exact-prefix table (scan_fx_kernel): fx_tab[hash(first 12 read bases)] = primer + 1 for a primer that
     // (a) this spelling matches without a mismatch on its first 12 bases and (b) is ISOLATED: every other primer differs from
     // it in at least two of those positions whatever the spelling, so no other primer can be accepted with <= 1 mismatch.
     // The kernel verifies (a) itself (a slot may be a hash collision); 0 = no entry.  NULL when the panel is not eligible.
@@ -86,6 +90,10 @@ struct DevPanel {
     // pair_id groups for 3' matching (IP:496): opposite-strand primers of the same pair, file order
     const int32_t *mate_off;   // [n+1]
     const int32_t *mate_idx;
+    // downstream classification (scripts/post_process_bam.py:56-78): per primer {pair index, primer_id key, ref_name key,
+    // positive_strand} and {start, end}
+    const int4 *cls_info;
+    const int2 *cls_span;
     // scoring (IP:364-372)
     int32_t match_score, mismatch_score, gap_open, gap_extend;
     const int32_t *smat;       // NULL or [16*16] primer nibble x read nibble, INT32_MIN = missing
@@ -117,6 +125,7 @@ struct idp_panel {
     std::vector<int32_t> score_matrix;        // 128*128 copy or empty
     std::vector<std::string> pair_id, primer_id, sequence, ref_name;
     std::vector<int32_t> ref_idx, start, end, seq_len, plen, pair_of, cap_full, acc_full;
+    std::vector<int32_t> primer_id_key, ref_name_key;  // equal strings <=> equal keys (the classification compares names)
     std::vector<uint8_t> positive;
     std::vector<uint32_t> hash;
     int32_t ww = 0, window_bases = 0, max_seq_len = 0, max_primer_length = 0;

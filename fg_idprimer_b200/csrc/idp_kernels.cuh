@@ -32,13 +32,26 @@ namespace idp {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kCandLocal = 8;
 
-__global__ void __launch_bounds__(256) cand5_thread_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ fall,
+// bm_words > 0: the presence bits of the direct table (DevKmerIndex::direct_bits, at most 128 KB) sit in shared memory and
+// answer most lookups -- the fall-through reads are mostly off-target templates whose k-mers are not on the panel, and the
+// 4^k-entry table itself lives in L2, where one 4-byte probe costs a whole sector (the kernel was bound by exactly that).
+constexpr int kCand5Threads = 1024;
+__global__ void __launch_bounds__(kCand5Threads) cand5_thread_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ fall,
                                                            Counters *__restrict__ ctr, unsigned int *__restrict__ pair_work,
                                                            unsigned int *__restrict__ pair_primer, unsigned int pair_cap,
                                                            unsigned int *__restrict__ seg_off, int *__restrict__ seg_cnt,
-                                                           unsigned int *__restrict__ spill) {
+                                                           unsigned int *__restrict__ spill, unsigned int bm_words) {
+    extern __shared__ uint32_t cand5_bm[];
     const DevKmerIndex &ix = P.kidx[1];
     const unsigned n_work = ctr->n_fall;
+    if (bm_words) {
+        if (blockIdx.x * blockDim.x >= n_work) return;  // nothing for this block: skip the copy
+        const uint4 *src = reinterpret_cast<const uint4 *>(ix.direct_bits);
+        uint4 *dst = reinterpret_cast<uint4 *>(cand5_bm);
+        for (unsigned i = threadIdx.x; i < bm_words / 4; i += blockDim.x) dst[i] = src[i];
+        for (unsigned i = (bm_words & ~3u) + threadIdx.x; i < bm_words; i += blockDim.x) cand5_bm[i] = ix.direct_bits[i];
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const uint64_t kmask = ix.k >= 16 ? ~0ull : ((1ull << (4 * ix.k)) - 1ull);
     const uint32_t kmask2 = ix.k >= 16 ? ~0u : ((1u << (2 * ix.k)) - 1u);
@@ -66,6 +79,7 @@ __global__ void __launch_bounds__(256) cand5_thread_kernel(DevPanel P, DevReads 
                 OffCnt oc;
                 if (i < ix.k - 1) return true;
                 if (ix.direct != nullptr && bad == 0) {  // one load, no probing: the lanes of a warp stay together
+                    if (bm_words && !((cand5_bm[key2 >> 5] >> (key2 & 31u)) & 1u)) return true;
                     const uint32_t e = __ldg(&ix.direct[key2]);
                     if (!e) return true;
                     oc.off = e & 0xFFFFFu; oc.cnt = e >> 20;
@@ -83,20 +97,11 @@ __global__ void __launch_bounds__(256) cand5_thread_kernel(DevPanel P, DevReads 
                 }
                 return true;
             };
-            if (!rc && n_bases <= 32 && ((len + 1) >> 1) >= 20) {
-                // forward read, window of at most 32 bases: five aligned words give the window as a 4-word shift register
-                // (base i in nibble i), so a base costs a handful of register operations instead of a byte fetch
-                const uintptr_t a = reinterpret_cast<uintptr_t>(s);
-                const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
-                const int sh = (int)(a & 3) * 8;
+            if (n_bases <= 32) {
+                // a window of at most 32 bases comes in as a 4-word shift register (base i in nibble i: the word loaders of the
+                // scan kernel, forward or reverse complement), so a base costs a handful of register operations instead of a byte fetch
                 uint32_t sr[4];
-                uint32_t prev = __ldg(wp);
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const uint32_t next = __ldg(wp + w + 1);
-                    sr[w] = nibswap(__funnelshift_r(prev, next, sh));
-                    prev = next;
-                }
+                window_from_global<4>(R, r, s, len, rc, sr);
                 for (int i = 0; i < n_bases; ++i) {
                     const uint32_t nib = sr[0] & 15u;
                     sr[0] = __funnelshift_r(sr[0], sr[1], 4);
@@ -523,53 +528,81 @@ __device__ __forceinline__ void sw_score2_fast(const DevPanel &P, const uint32_t
     uint32_t edge = 0u;                                                                   // Glocal: -extend * j in both halves
     const uint32_t ne2 = pack16(-e);
     TargetStream ts(T);
-    for (int j = 1; j <= m; ++j) {
-        uint32_t t = ts.nib(j - 1);
-        asm volatile("" : "+r"(t));
-        const uint32_t trep = t * 0x11111111u;
-        uint32_t pk[NQ / 4];  // rows 4w..4w+3: mismatch flags of a at bits 0,4,8,12 and of b at bits 16,20,24,28
+    // TWO target columns per sweep, as in sw_trace_reg_glocal_shifted: stream A walks column j, stream B walks column j+1 one
+    // row behind it, so every step holds two independent max-plus chains and one hides the latency of the other.  An odd last
+    // column pairs with a dummy column (code 0: a mismatch in every row) whose end cell is not taken; in Local its Diagonal
+    // values stay below the running best (they are an earlier cell's value plus a mismatch), so `best` is unaffected.
+    for (int j = 1; j <= m; j += 2) {
+        uint32_t tA = ts.nib(j - 1), tB = j < m ? ts.nib(j) : 0u;
+        asm volatile("" : "+r"(tA), "+r"(tB));
+        const uint32_t trepA = tA * 0x11111111u, trepB = tB * 0x11111111u;
+        uint32_t pkA[NQ / 4], pkB[NQ / 4];  // rows 4w..4w+3: mismatch flags of a at bits 0,4,8,12 and of b at bits 16,20,24,28
 #pragma unroll
         for (int w = 0; w < NQ / 8; ++w) {
-            const uint32_t fa = nib_nonzero(qa[w] ^ trep), fb = nib_nonzero(qb[w] ^ trep);
-            pk[2 * w] = __byte_perm(fa, fb, 0x5410);
-            pk[2 * w + 1] = __byte_perm(fa, fb, 0x7632);
+            const uint32_t fa = nib_nonzero(qa[w] ^ trepA), fb = nib_nonzero(qb[w] ^ trepA);
+            pkA[2 * w] = __byte_perm(fa, fb, 0x5410);
+            pkA[2 * w + 1] = __byte_perm(fa, fb, 0x7632);
+            const uint32_t ga = nib_nonzero(qa[w] ^ trepB), gb = nib_nonzero(qb[w] ^ trepB);
+            pkB[2 * w] = __byte_perm(ga, gb, 0x5410);
+            pkB[2 * w + 1] = __byte_perm(ga, gb, 0x7632);
         }
-        uint32_t mdiag, d_up, u_up;
-        if (LOCAL) { mdiag = 0u; d_up = 0u; u_up = 0u; }
-        else { mdiag = edge; edge = __vadd2(edge, ne2); d_up = edge; u_up = edge; }  // row 0 is all zero: shifted by -extend*(0+j)
-#define IDP_CELL(r)                                                                                        \
-            const uint32_t mask = ((pk[(r) >> 2] >> (4 * ((r) & 3))) & 0x00010001u) * 0xFFFFu;               \
-            const uint32_t s2 = ma2 ^ (mask & selx);                                                       \
-            const uint32_t dn = LOCAL ? __viaddmax_s16x2_relu(mdiag, s2, 0u) : __vadd2(mdiag, s2);           \
-            const uint32_t un = LOCAL ? __viaddmax_s16x2(d_up, o2, __vadd2(u_up, e2)) : __viaddmax_s16x2(d_up, o2, u_up); \
-            const uint32_t ln = LN[(r)];                                                                   \
-            const uint32_t mold = M[(r)];                                                                  \
-            M[(r)] = __vimax3_s16x2(dn, ln, un);                                                           \
-            LN[(r)] = LOCAL ? __viaddmax_s16x2(dn, o2, __vadd2(ln, e2)) : __viaddmax_s16x2(dn, o2, ln);
+        uint32_t mdiagA, d_upA, u_upA, mdiagB, d_upB, u_upB;
+        if (LOCAL) { mdiagA = d_upA = u_upA = 0u; mdiagB = d_upB = u_upB = 0u; }
+        else {  // row 0 is all zero: shifted by -extend*(0+j)
+            mdiagA = edge; edge = __vadd2(edge, ne2); d_upA = edge; u_upA = edge;
+            mdiagB = edge; edge = __vadd2(edge, ne2); d_upB = edge; u_upB = edge;
+        }
+#define IDP_CELL2(r, S)                                                                                    \
+            const uint32_t mask##S = ((pk##S[(r) >> 2] >> (4 * ((r) & 3))) & 0x00010001u) * 0xFFFFu;         \
+            const uint32_t s2##S = ma2 ^ (mask##S & selx);                                                 \
+            const uint32_t dn##S = LOCAL ? __viaddmax_s16x2_relu(mdiag##S, s2##S, 0u) : __vadd2(mdiag##S, s2##S); \
+            const uint32_t un##S = LOCAL ? __viaddmax_s16x2(d_up##S, o2, __vadd2(u_up##S, e2)) : __viaddmax_s16x2(d_up##S, o2, u_up##S); \
+            const uint32_t ln##S = LN[(r)];                                                                \
+            const uint32_t mold##S = M[(r)];                                                               \
+            M[(r)] = __vimax3_s16x2(dn##S, ln##S, un##S);                                                  \
+            LN[(r)] = LOCAL ? __viaddmax_s16x2(dn##S, o2, __vadd2(ln##S, e2)) : __viaddmax_s16x2(dn##S, o2, ln##S);
+#define IDP_PREV(r) ((r) > 0 ? (r) - 1 : 0)
+#define IDP_ACT(r) ((((r) >= offa) ? 0x0000FFFFu : 0u) | (((r) >= offb) ? 0xFFFF0000u : 0u))
 #define IDP_ROW(r)                                                                                         \
     case (r): {                                                                                            \
-        if ((r) >= hi) break;                                                                              \
-        const uint32_t act = ((r) >= offa ? 0x0000FFFFu : 0u) | ((r) >= offb ? 0xFFFF0000u : 0u);            \
-        IDP_CELL(r)                                                                                        \
-        mdiag = (mold & act) | (mdiag & ~act); d_up = (dn & act) | (d_up & ~act); u_up = (un & act) | (u_up & ~act); \
-        if (LOCAL) best = __vmaxs2(best, dn & act);                                                        \
+        if ((r) > hi) break;                                                                               \
+        {                                                                                                  \
+            const uint32_t act = IDP_ACT(r);                                                               \
+            IDP_CELL2(r, A)                                                                                \
+            mdiagA = (moldA & act) | (mdiagA & ~act); d_upA = (dnA & act) | (d_upA & ~act); u_upA = (unA & act) | (u_upA & ~act); \
+            if (LOCAL) best = __vmaxs2(best, dnA & act);                                                   \
+        }                                                                                                  \
+        if ((r) > 0) {                                                                                     \
+            const uint32_t act = IDP_ACT(IDP_PREV(r));                                                     \
+            IDP_CELL2(IDP_PREV(r), B)                                                                      \
+            mdiagB = (moldB & act) | (mdiagB & ~act); d_upB = (dnB & act) | (d_upB & ~act); u_upB = (unB & act) | (u_upB & ~act); \
+            if (LOCAL) best = __vmaxs2(best, dnB & act);                                                   \
+        }                                                                                                  \
     }
         IDP_SWITCH_ROWS(NQ, lo)
 #undef IDP_ROW
 #define IDP_ROW(r)                                                                                         \
     case (r): {                                                                                            \
-        IDP_CELL(r)                                                                                        \
-        mdiag = mold; d_up = dn; u_up = un;                                                                \
-        if (LOCAL) best = __vmaxs2(best, dn);                                                              \
+        { IDP_CELL2(r, A) mdiagA = moldA; d_upA = dnA; u_upA = unA; if (LOCAL) best = __vmaxs2(best, dnA); } \
+        { IDP_CELL2(IDP_PREV(r), B) mdiagB = moldB; d_upB = dnB; u_upB = unB; if (LOCAL) best = __vmaxs2(best, dnB); } \
     }
-        IDP_SWITCH_ROWS(NQ, hi)
+        IDP_SWITCH_ROWS(NQ, hi + 1)
 #undef IDP_ROW
-#undef IDP_CELL
-        if (!LOCAL) {  // last query row, this column, back in true coordinates: M(n,j) = M'(n,j) + extend*(n+j)
+        { IDP_CELL2(NQ - 1, B) d_upB = dnB; u_upB = unB; (void)moldB; if (LOCAL) best = __vmaxs2(best, dnB); }
+#undef IDP_ACT
+#undef IDP_PREV
+#undef IDP_CELL2
+        if (!LOCAL) {  // last query row, these columns, back in true coordinates: M(n,j) = M'(n,j) + extend*(n+j)
+            // (d_up / u_up hold Diagonal / Up of the last row; Left there never exceeds an earlier column's Diagonal, and only the
+            // score matters here, so max(Diagonal, Up) is taken)
             conv = __vadd2(conv, e2);
-            const uint32_t upd = __viaddmax_s16x2(M[NQ - 1], conv, best);
-            const uint32_t in = (j <= m_a ? 0x0000FFFFu : 0u) | (j <= m_b ? 0xFFFF0000u : 0u);
-            best = (upd & in) | (best & ~in);
+            const uint32_t updA = __viaddmax_s16x2(__vmaxs2(d_upA, u_upA), conv, best);
+            const uint32_t inA = (j <= m_a ? 0x0000FFFFu : 0u) | (j <= m_b ? 0xFFFF0000u : 0u);
+            best = (updA & inA) | (best & ~inA);
+            conv = __vadd2(conv, e2);
+            const uint32_t updB = __viaddmax_s16x2(__vmaxs2(d_upB, u_upB), conv, best);
+            const uint32_t inB = (j + 1 <= m_a ? 0x0000FFFFu : 0u) | (j + 1 <= m_b ? 0xFFFF0000u : 0u);
+            best = (updB & inB) | (best & ~inB);
         }
     }
     score_a = (int)(int16_t)(best & 0xFFFFu);
@@ -682,12 +715,88 @@ __device__ __forceinline__ TracedReg sw_trace_reg_glocal_shifted(const DevPanel 
     return out;
 }
 
+// Local (3' matching, IP:509-513), traceback-equivalent, in plain coordinates.  Differences from the generic form below, all
+// to spend fewer instructions per cell (the kernel is bound by the ALU pipe):
+//  * the start column is stored INVERTED (4095 - start) in the low 12 bits, so the zero clamp of a Diagonal cell is ONE max
+//    against "score 0, path starts after this column": a negative value loses, a positive one wins, and a cell whose score
+//    is exactly 0 keeps its own (earlier, hence larger when inverted) start -- fgbio clamps only scores below zero;
+//  * the best cell (highest score, then lowest row, then lowest column; only Diagonal values can win) is tracked as one
+//    key per column -- score bits | (NQ-1 - row), a LOP3 and a max per cell -- and compared with the running best once per
+//    column; the start bits of a new best cell are then read back from M[row]: at that cell the Diagonal value is the cell's
+//    maximum (Left / Up there are bounded by earlier Diagonal values minus a gap, and rank breaks a tie in its favour).
+template <int NQ>
+__device__ __forceinline__ TracedReg sw_trace_reg_local(const DevPanel &P, const uint32_t *__restrict__ qbot, int n, int lo, int hi, const Oriented &T, int m) {
+    constexpr int SH = 14, LOW = 0x3FFF, RANK = 0x3000, RD = 0x3000, RL = 0x2000, RU = 0x1000, INV = 0xFFF;
+    TracedReg out{0, 1, 0};
+    const int oe = P.tr_open_ext, e = P.tr_ext;  // constant-bank operands
+    const unsigned am = __activemask();
+    const int self = (int)(threadIdx.x & 31u);
+    const int ma = __shfl_sync(am, P.tr_match, self), mi = __shfl_sync(am, P.tr_mismatch, self), keep = __shfl_sync(am, ~RANK, self);  // registers
+    const int keeplow = __shfl_sync(am, ~LOW, self);
+    const int off = NQ - n;
+    uint32_t q[NQ / 8];
+#pragma unroll
+    for (int w = 0; w < NQ / 8; ++w) q[w] = __ldg(&qbot[w]);
+    int LN[NQ], M[NQ];  // LN[r] = Left(r, next column), stamped
+#pragma unroll
+    for (int r = 0; r < NQ; ++r) { LN[r] = (__viaddmax_s32(RD | INV, oe, (RL | INV) + e) & ~RANK) | RL; M[r] = RD | INV; }  // column 0: all zero, start 0
+    int best = RD | INV, bestkey = INT_MIN, bj = 0;
+    TargetStream ts(T);
+    for (int j = 1; j <= m; ++j) {
+        uint32_t t = ts.nib(j - 1);
+        asm volatile("" : "+r"(t));
+        const uint32_t trep = t * 0x11111111u;
+        uint32_t ne[NQ / 8];
+#pragma unroll
+        for (int w = 0; w < NQ / 8; ++w) ne[w] = nib_nonzero(q[w] ^ trep);
+        const int fresh = RD | (INV - j);  // score 0, Diagonal, the path starts after this column
+        int mdiag = INV + 1 - j, d_up = fresh, u_up = RU | (INV - j);  // row 0: score 0, path starts at this column
+        int colmax = INT_MIN;
+#define IDP_CELL(r)                                                                                              \
+            int dn = ((mdiag + ((ne[(r) >> 3] & (1u << (4 * ((r) & 7)))) ? mi : ma)) & ~RANK) | RD;               \
+            dn = max(dn, fresh); /* the clamp at zero, see above */                                               \
+            const int un = (__viaddmax_s32(d_up, oe, u_up + e) & keep) | RU; /* equal scores: opened from Diagonal */ \
+            const int ln = LN[(r)];                                                                               \
+            const int mold = M[(r)];                                                                              \
+            M[(r)] = __vimax3_s32(dn, ln, un); /* equal scores: Diagonal, then Left, then Up */                   \
+            LN[(r)] = (__viaddmax_s32(dn, oe, ln + e) & keep) | RL;
+#define IDP_ROW(r)                                                                     \
+    case (r): {                                                                        \
+        if ((r) >= hi) break;                                                          \
+        const bool act = (r) >= off;                                                   \
+        IDP_CELL(r)                                                                    \
+        mdiag = act ? mold : mdiag; d_up = act ? dn : d_up; u_up = act ? un : u_up;    \
+        colmax = max(colmax, act ? ((dn & keeplow) | (NQ - 1 - (r))) : INT_MIN);       \
+    }
+        IDP_SWITCH_ROWS(NQ, lo)
+#undef IDP_ROW
+#define IDP_ROW(r)                                                                     \
+    case (r): {                                                                        \
+        IDP_CELL(r)                                                                    \
+        mdiag = mold; d_up = dn; u_up = un;                                            \
+        colmax = max(colmax, (dn & keeplow) | (NQ - 1 - (r)));                         \
+    }
+        IDP_SWITCH_ROWS(NQ, hi)
+#undef IDP_ROW
+#undef IDP_CELL
+        if (colmax > bestkey) {  // a new best cell in this column (rare after the first few columns): fetch its start bits
+            bestkey = colmax; bj = j;
+            const int row = NQ - 1 - (colmax & 63);
+#pragma unroll
+            for (int r = 0; r < NQ; ++r) best = r == row ? M[r] : best;
+        }
+    }
+    out.score = best >> SH; out.t_start = (INV - (best & INV)) + 1; out.t_end = bj;
+    return out;
+}
+
 template <int NQ, bool LOCAL>
 __device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint32_t *__restrict__ qbot, int n, int lo, int hi, const Oriented &T, int m) {
     static_assert(NQ == 32 || NQ == 64, "row count");
     TracedReg out{0, 1, 0};
     if (m == 0) { out.score = LOCAL ? 0 : P.gap_open + n * P.gap_extend; return out; }
     if constexpr (!LOCAL) return sw_trace_reg_glocal_shifted<NQ>(P, qbot, n, lo, hi, T, m);
+    if constexpr (LOCAL) return sw_trace_reg_local<NQ>(P, qbot, n, lo, hi, T, m);
     constexpr int SH = 14, LOW = 0x3FFF, RANK = 0x3000, RD = 0x3000, RL = 0x2000, RU = 0x1000;
     const int oe = P.tr_open_ext, e = P.tr_ext;  // constant-bank operands
     const unsigned am = __activemask();
@@ -993,26 +1102,30 @@ __global__ void __launch_bounds__(128, 4) sw_all_kernel(DevPanel P, DevReads R, 
 // Diagonal over Left over Up for the diagonal move, Diagonal over gap extension, strict '>' for the end cell scanning
 // target positions (and query rows in Local) in ascending order.  Returns score, targetStart (1-based), targetEnd.
 // ---------------------------------------------------------------------------------------------------------------
-struct Traced { int score, t_start, t_end; bool missing; };
+struct Traced { int score, t_start, t_end, q_start, q_end; bool missing; };
 
-template <int TN>
+// QS: also carry the query row at which the path started (Local only: in Glocal / Global the whole query is aligned)
+template <int TN, bool QS = false>
 __device__ Traced sw_trace(const DevPanel &P, const uint32_t *__restrict__ qwords, int n, const Oriented &T, int m, int mode) {
     const int oe = P.gap_open + P.gap_extend, e = P.gap_extend;
-    Traced out{0, 1, 0, false};
+    Traced out{0, 1, 0, 1, n, false};
     const bool local = mode == IDP_MODE_LOCAL, global = mode == IDP_MODE_GLOBAL;
-    if (m == 0) { out.score = local ? 0 : P.gap_open + n * P.gap_extend; return out; }
+    if (m == 0) { out.score = local ? 0 : P.gap_open + n * P.gap_extend; if (local) out.q_start = n + 1; return out; }  // Local: the empty alignment after the last query base
     int D[TN], L[TN], M[TN];
     short sD[TN], sL[TN], sM[TN];
+    short qD[QS ? TN : 1], qL[QS ? TN : 1], qM[QS ? TN : 1];  // 1-based row of the boundary / clamped cell the path left
     for (int i = 0; i < n; ++i) {
         sD[i] = 0; sL[i] = 0; sM[i] = 0;
+        if (QS) { qD[i] = (short)(i + 1); qL[i] = (short)(i + 1); qM[i] = (short)(i + 1); }
         if (local) { D[i] = 0; L[i] = 0; M[i] = 0; }
         else { D[i] = kNegInf; L[i] = kNegInf; M[i] = P.gap_open + (i + 1) * P.gap_extend; }
     }
-    int best = kNegInf, bi = 0, bj = 0, bstart = 0;
+    int best = kNegInf, bi = 0, bj = 0, bstart = 0, bq = 0;
     for (int j = 1; j <= m; ++j) {
         const uint32_t t = T.nib(j - 1);
         // row 0: all matrices zero / Done in Glocal and Local; Global has only Left = open + j*extend
         int mdiag, smdiag, d_up, sd_up, u_up, su_up;
+        int qmdiag = 0, qd_up = 0, qu_up = 0;
         if (!global) { mdiag = 0; smdiag = j - 1; d_up = 0; sd_up = j; u_up = 0; su_up = j; }
         else { mdiag = j == 1 ? 0 : P.gap_open + (j - 1) * P.gap_extend; smdiag = 0; d_up = kNegInf; sd_up = 0; u_up = kNegInf; su_up = 0; }
         for (int i = 0; i < n; ++i) {
@@ -1020,21 +1133,23 @@ __device__ Traced sw_trace(const DevPanel &P, const uint32_t *__restrict__ qword
             int s;
             if (P.smat) { s = __ldg(&P.smat[qc * 16 + t]); if (s == INT32_MIN) { out.missing = true; s = 0; } }
             else s = qc == t ? P.match_score : P.mismatch_score;
-            int dn = mdiag + s, sdn = smdiag;
-            if (local && dn < 0) { dn = 0; sdn = j; }
-            int un, sun, ln, sln;
-            { const int a = d_up + oe, b = u_up + e; if (a >= b) { un = a; sun = sd_up; } else { un = b; sun = su_up; } }
-            { const int a = D[i] + oe, b = L[i] + e; if (a >= b) { ln = a; sln = sD[i]; } else { ln = b; sln = sL[i]; } }
-            int mn = dn, smn = sdn;
-            if (ln > mn) { mn = ln; smn = sln; }
-            if (un > mn) { mn = un; smn = sun; }
+            int dn = mdiag + s, sdn = smdiag, qdn = qmdiag;
+            if (local && dn < 0) { dn = 0; sdn = j; qdn = i + 1; }
+            int un, sun, qun, ln, sln, qln;
+            { const int a = d_up + oe, b = u_up + e; if (a >= b) { un = a; sun = sd_up; qun = qd_up; } else { un = b; sun = su_up; qun = qu_up; } }
+            { const int a = D[i] + oe, b = L[i] + e; if (a >= b) { ln = a; sln = sD[i]; qln = QS ? qD[i] : 0; } else { ln = b; sln = sL[i]; qln = QS ? qL[i] : 0; } }
+            int mn = dn, smn = sdn, qmn = qdn;
+            if (ln > mn) { mn = ln; smn = sln; qmn = qln; }
+            if (un > mn) { mn = un; smn = sun; qmn = qun; }
             mdiag = M[i]; smdiag = sM[i];
+            if (QS) qmdiag = qM[i];
             D[i] = dn; sD[i] = (short)sdn; L[i] = ln; sL[i] = (short)sln; M[i] = mn; sM[i] = (short)smn;
-            d_up = dn; sd_up = sdn; u_up = un; su_up = sun;
+            if (QS) { qD[i] = (short)qdn; qL[i] = (short)qln; qM[i] = (short)qmn; }
+            d_up = dn; sd_up = sdn; u_up = un; su_up = sun; qd_up = qdn; qu_up = qun;
             if (local) {  // best over all cells: lowest row, then lowest column, then Diagonal / Left / Up
-                if (dn > best || (dn == best && i + 1 < bi)) { best = dn; bi = i + 1; bj = j; bstart = sdn; }
-                if (ln > best || (ln == best && i + 1 < bi)) { best = ln; bi = i + 1; bj = j; bstart = sln; }
-                if (un > best || (un == best && i + 1 < bi)) { best = un; bi = i + 1; bj = j; bstart = sun; }
+                if (dn > best || (dn == best && i + 1 < bi)) { best = dn; bi = i + 1; bj = j; bstart = sdn; bq = qdn; }
+                if (ln > best || (ln == best && i + 1 < bi)) { best = ln; bi = i + 1; bj = j; bstart = sln; bq = qln; }
+                if (un > best || (un == best && i + 1 < bi)) { best = un; bi = i + 1; bj = j; bstart = sun; bq = qun; }
             } else if (i == n - 1 && (!global || j == m)) {
                 if (dn > best) { best = dn; bj = j; bstart = sdn; }
                 if (ln > best) { best = ln; bj = j; bstart = sln; }
@@ -1043,6 +1158,7 @@ __device__ Traced sw_trace(const DevPanel &P, const uint32_t *__restrict__ qword
         }
     }
     out.score = best; out.t_start = bstart + 1; out.t_end = bj;
+    if (local) { out.q_start = bq + 1; out.q_end = bi; }
     return out;
 }
 
@@ -1199,6 +1315,54 @@ __global__ void __launch_bounds__(256) metrics_kernel(DevReads R, const uint8_t 
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 160; i += blockDim.x) if (hist[i]) atomicAdd(&ctr->metrics[i], (unsigned long long)hist[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Downstream classification of templates (scripts/post_process_bam.py:56-78) on the forward / reverse 5' slots of
+// addTagsToPair (IP:530-540), as an epilogue on the device-resident 5' records: one thread per read, the thread of a
+// template's first read does the work.  counts: one per template whose first record is read 1 (post_process_bam.py:159).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int classify_primer_pair(const DevPanel &P, int f5, int r5, int min_insert, int max_insert) {
+    if (f5 < 0 && r5 < 0) return IDP_CLASS_NO_MATCH;
+    if (f5 < 0 || r5 < 0) return IDP_CLASS_SINGLE;
+    const int4 a = __ldg(&P.cls_info[f5]), b = __ldg(&P.cls_info[r5]);  // {pair, primer_id key, ref_name key, positive}
+    if (a.x != b.x) {  // from different primer pairs
+        if (a.z != b.z) return IDP_CLASS_CROSS_DIMER;
+        const int2 sa = __ldg(&P.cls_span[f5]), sb = __ldg(&P.cls_span[r5]);
+        const int insert_length = max(sa.y, sb.y) - min(sa.x, sb.x) + 1;  // :47-53
+        return (insert_length < min_insert || max_insert < insert_length) ? IDP_CLASS_CROSS_DIMER : IDP_CLASS_NON_CANONICAL;
+    }
+    if (a.y == b.y) return IDP_CLASS_SELF_DIMER;
+    if (a.w == b.w) return IDP_CLASS_NON_CANONICAL;
+    return IDP_CLASS_CANONICAL;
+}
+
+__global__ void __launch_bounds__(256) classify_kernel(DevPanel P, const uint16_t *__restrict__ flags, const ResultOut five, int n, int min_insert,
+                                                       int max_insert, uint8_t *__restrict__ cls_per_read, Counters *__restrict__ ctr) {
+    __shared__ unsigned int hist[6];
+    if (threadIdx.x < 6) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        if (r > 0 && (flags[r - 1] & IDP_F_MATE_NEXT)) continue;  // an R2: its R1 speaks for the template
+        const uint16_t fl = flags[r];
+        const bool has_r2 = (fl & IDP_F_MATE_NEXT) && r + 1 < n;
+        int t1, p1, t2 = IDP_NONE, p2 = -1;
+        read_type_primer(five, r, t1, p1);
+        if (has_r2) read_type_primer(five, r + 1, t2, p2);
+        const int m1 = t1 != IDP_NONE ? p1 : -1, m2 = t2 != IDP_NONE ? p2 : -1;
+        int f5 = m1, r5 = m2;
+        if (has_r2) {  // forward / reverse slots (IP:530-540)
+            bool fwd_is_r1 = true;
+            if (m1 >= 0) fwd_is_r1 = __ldg(&P.cls_info[m1]).w != 0;
+            else if (m2 >= 0) fwd_is_r1 = __ldg(&P.cls_info[m2]).w == 0;
+            if (!fwd_is_r1) { f5 = m2; r5 = m1; }
+        }
+        const int cls = classify_primer_pair(P, f5, r5, min_insert, max_insert);
+        if (cls_per_read) { cls_per_read[r] = (uint8_t)cls; if (has_r2) cls_per_read[r + 1] = (uint8_t)cls; }
+        if (fl & IDP_F_FIRST) atomicAdd(&hist[cls], 1u);  // "do not double-count": only record.is_read1
+    }
+    __syncthreads();
+    if (threadIdx.x < 6 && hist[threadIdx.x]) atomicAdd(&ctr->classes[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
 }
 
 }  // namespace idp

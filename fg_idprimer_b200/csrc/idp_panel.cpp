@@ -274,6 +274,13 @@ int idp_panel_create(const idp_primer *primers, int32_t n, const idp_params *par
         p->max_seq_len = std::max(p->max_seq_len, (int32_t)seq.size());
         p->max_primer_length = std::max(p->max_primer_length, plen);
     }
+    {   // integer keys for the strings the downstream classification compares (post_process_bam.py:60-75)
+        std::map<std::string, int> ids, refs;
+        for (int i = 0; i < n; ++i) {
+            p->primer_id_key.push_back(ids.emplace(p->primer_id[i], (int)ids.size()).first->second);
+            p->ref_name_key.push_back(refs.emplace(p->ref_name[i], (int)refs.size()).first->second);
+        }
+    }
     {   // rows that are equal as case classes would collapse in the reference's Sets; refuse them
         std::map<std::array<std::string, 4>, std::vector<int>> seen;
         for (int i = 0; i < n; ++i) {
@@ -418,7 +425,9 @@ int idp_panel_create(const idp_primer *primers, int32_t n, const idp_params *par
                     uint32_t w0 = 0, w1 = 0;
                     for (int j = 0; j < 8; ++j) w0 |= sub[j] << (4 * j);
                     for (int j = 8; j < kFxBases; ++j) w1 |= sub[j] << (4 * (j - 8));
-                    ent.push_back({w0, w1, (uint32_t)i});
+                    // the table is keyed on the row words as STORED (first base of a byte in its high nibble): see idp_scanfx.cuh
+                    auto stored = [](uint32_t x) { return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu); };
+                    ent.push_back({stored(w0), stored(w1), (uint32_t)i});
                     int j = 0;  // odometer over the single bases of every position
                     for (; j < kFxBases; ++j) {
                         const uint32_t rest = codes[j] & ~((sub[j] << 1) - 1u);  // bases above the current one

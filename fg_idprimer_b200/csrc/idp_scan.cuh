@@ -34,9 +34,12 @@ struct ScanLaunch {
     int32_t stage_flags;       // 1: the tile's flag words ride along (16-byte aligned flags array), at flags_off in the tile buffer
     uint32_t flags_off;
     // byte offsets into dynamic shared memory, or 0xFFFFFFFF when the structure stays in global memory
-    uint32_t off_direct, off_heads, off_pmask, off_pinfo, off_bsmm, off_bsacc, off_seed, off_diag, off_fx, off_queue;
+    uint32_t off_direct, off_heads, off_pmask, off_pinfo, off_bsmm, off_bsacc, off_seed, off_diag;
     uint32_t direct_entries;
-    int32_t use_fx;            // 0: the exact-prefix shortcut is switched off (IDP_SCAN_NO_FX=1; A/B runs and tests of the filter path)
+    // list mode: the kernel works through `list[0 .. ctr->n_parked)` (the reads scan_fx_kernel could not decide) instead of
+    // reads 0 .. R.n; nothing is staged then, every lane fetches its own read
+    const unsigned int *list;
+    uint32_t *fall_mask;       // [ceil(R.n / 32)] bit i of word t: read 32 t + i fell through to the gapped stage (IP:444-450)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -323,103 +326,11 @@ __device__ __forceinline__ bool seed_filter(const DevPanel &P, ScanCtx<RW, ST> &
     return fits;
 }
 
-// ---- read window loaders: basesInSequencingOrder (PM:39-45), only the prefix the matchers can look at ----
-// reverse the 8 nibbles of a word
-__device__ __forceinline__ uint32_t rev8nib(uint32_t x) { return nibswap(__byte_perm(x, 0u, 0x0123)); }
-// htsjdk 2.16 SequenceUtil.complement on 8 codes at once: A<->T, C<->G (a nibble with exactly one bit set is bit-reversed),
-// every other code is kept (PM:42)
-__device__ __forceinline__ uint32_t comp8nib(uint32_t x) {
-    const uint32_t c = (x & 0x55555555u) + ((x >> 1) & 0x55555555u);
-    const uint32_t d = (c & 0x33333333u) + ((c >> 2) & 0x33333333u);   // bits set per nibble
-    const uint32_t one = (~nib_nonzero(d ^ 0x11111111u) & 0x11111111u) * 15u;  // nibbles holding exactly one bit
-    const uint32_t rev = ((x & 0x11111111u) << 3) | ((x & 0x22222222u) << 1) | ((x >> 1) & 0x22222222u) | ((x >> 3) & 0x11111111u);
-    return (x & ~one) | (rev & one);
-}
-template <int RW>
-__device__ __forceinline__ void mask_window(uint32_t (&win)[RW], int len) {
-    if (len < RW * 8) {
-#pragma unroll
-        for (int w = 0; w < RW; ++w) {
-            const int rem = len - w * 8;
-            if (rem < 8) win[w] = rem <= 0 ? 0u : (win[w] & ((1u << (4 * rem)) - 1u));
-        }
-    }
-}
-// wp: 4-byte aligned word pointer at or below the read's first byte (shared or global), bo: the read's byte offset from it
-// (0..3).  The caller guarantees that RW + 1 words (forward) / the words around the read's end (reverse, len >= 8 * RW) may be
-// read.  Forward: the first 8 * RW bases.  Reverse: the reverse complement of the last 8 * RW stored bases.
-template <int RW>
-__device__ __forceinline__ void window_from_words(const uint32_t *wp, int bo, int len, bool rc, uint32_t (&win)[RW]) {
-    if (!rc) {
-        const int sh = bo * 8;
-        uint32_t prev = wp[0];
-#pragma unroll
-        for (int w = 0; w < RW; ++w) {
-            const uint32_t next = wp[w + 1];
-            win[w] = nibswap(__funnelshift_r(prev, next, sh));
-            prev = next;
-        }
-        mask_window<RW>(win, len);
-    } else {
-        // stored base k sits at nibble 2 * bo + k of the stream whose word t is nibswap(wp[t]); window word w wants stored
-        // bases len - 8 - 8w .. len - 1 - 8w, reversed and complemented
-        const int n0 = 2 * bo + len - 8;
-        const int t0 = n0 >> 3, sh = 4 * (n0 & 7);
-        uint32_t hi = nibswap(wp[t0 + 1]);
-#pragma unroll
-        for (int w = 0; w < RW; ++w) {
-            const uint32_t lo = nibswap(wp[t0 - w]);
-            win[w] = comp8nib(rev8nib(__funnelshift_r(lo, hi, sh)));
-            hi = lo;
-        }
-    }
-}
-// the slow, always safe form: base by base through a generic pointer
-template <int RW>
-__device__ __forceinline__ void window_by_bases(const uint8_t *sp, int len, bool rc, uint32_t (&win)[RW]) {
-    Oriented o{sp, len, rc};
-    const int nb = min(len, RW * 8);
-#pragma unroll
-    for (int w = 0; w < RW; ++w) {
-        uint32_t v = 0;
-        for (int b = 0; b < 8; ++b) {
-            const int i = w * 8 + b;
-            if (i < nb) v |= o.nib_generic(i) << (4 * b);
-        }
-        win[w] = v;
-    }
-}
-// from global memory.  The word form reads up to 4 * RW + 7 bytes from the aligned address below the read (forward) or up
-// to 7 bytes past its last byte (reverse): allowed when the batch is fixed-length (rows are contiguous) and the read is not
-// among the last few, or when the read itself is long enough (forward only)
-template <int RW>
-__device__ __forceinline__ void window_from_global(const DevReads &R, int r, const uint8_t *s, int len, bool rc, uint32_t (&win)[RW]) {
-    const int bytes = (len + 1) >> 1;
-    const bool roomy = R.fixed_len > 0 && (size_t)(R.n - 1 - r) * (size_t)bytes >= (size_t)(4 * RW + 8);
-    const bool word_ok = rc ? (roomy && len >= 8 * RW) : (roomy || bytes >= 4 * RW + 4);
-    if (word_ok) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(s);
-        window_from_words<RW>(reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3)), (int)(a & 3), len, rc, win);
-    } else {
-        window_by_bases<RW>(s, len, rc, win);
-    }
-}
-
-constexpr int kScanQueueCap = 64;  // per warp; a warp drains 32 entries as soon as it holds that many, so at most 63 wait
-
 // ONCHIP: the read tiles are known at compile time to sit in shared memory, so the window loads are LDS rather than generic
 // loads; the unrolled bit-sliced filter addresses its tables as shared memory as well (the general loop does not)
-//
-// Two passes per tile.  Pass 0 takes the tile's 32 reads: window, location matcher, then the exact-prefix table
-// (DevPanel::fx_tab): a read whose first 12 bases spell an isolated primer without a mismatch has that primer as its only
-// possible ungapped match, so the whole candidate search is one table load and the lane goes straight to mismatchAlign.
-// The other reads (a sequencing error or an N in the first 12 bases, off-target templates: ~10 %) are parked in a per-warp
-// queue of read indices.  Pass 1 runs only when the warp holds 32 parked reads (or has no tiles left): every lane takes
-// one and runs the bit-sliced filter / seed index / exact walk.  The expensive search therefore always runs with full
-// lanes instead of being dragged through every tile by its unluckiest read.
 template <int RW, bool FAST, bool ONCHIP, bool ST>
 __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(const __grid_constant__ DevPanel P, const __grid_constant__ DevReads R, const __grid_constant__ ScanLaunch S, const ResultOut five,
-                                                               uint8_t *__restrict__ rtype, unsigned int *__restrict__ fall, Counters *__restrict__ ctr) {
+                                                               uint8_t *__restrict__ rtype, Counters *__restrict__ ctr) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t tile_bar[kScanWarps][2];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -474,16 +385,6 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
         for (int i = tid; i < 2 * P.seed_slots; i += blockDim.x) d[i] = P.seed_tab[i];
         seed_tab = d;
     }
-    const uint16_t *fx_tab = P.fx_tab;
-    if (FAST && P.fx_tab != nullptr && S.off_fx != 0xFFFFFFFFu) {
-        uint32_t *d = reinterpret_cast<uint32_t *>(smem + S.off_fx);  // slot counts are powers of two >= 1024: whole words
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(P.fx_tab);
-        for (int i = tid; i < P.fx_slots / 2; i += blockDim.x) d[i] = src[i];
-        fx_tab = reinterpret_cast<const uint16_t *>(d);
-    }
-    // the exact-prefix shortcut needs the parking queue and at least two window words (12 bases)
-    const bool use_fx = FAST && RW >= 2 && P.fx_tab != nullptr && S.off_queue != 0xFFFFFFFFu && S.use_fx;
-    uint2 *queue = reinterpret_cast<uint2 *>(smem + (use_fx ? S.off_queue : 0u)) + wib * kScanQueueCap;  // {read, flags}
     const bool bs_onchip = ONCHIP && S.off_bsmm != 0xFFFFFFFFu && S.off_bsacc != 0xFFFFFFFFu;  // large panels keep them in global memory
     const uint32_t tab_addr = bs_onchip ? smem_u32(smem) + S.off_bsmm : 0u, acc_addr = bs_onchip ? smem_u32(smem) + S.off_bsacc : 0u;
     const bool fixed_groups = bs_onchip && (tab_addr & 127u) == 0u && (acc_addr & 15u) == 0u && P.bs_groups >= 2 && P.bs_groups <= 8 && (P.bs_groups & 1) == 0;
@@ -496,7 +397,6 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
     // ---- every warp walks its own 32-read tiles: no CTA-wide barrier from here on ----
     auto wbuf = [&](int b) { return smem + (size_t)(2 * wib + b) * S.tile_smem_bytes; };  // two tile buffers per warp
     uint32_t phase = 0u;  // bit b: parity of the next completion of buffer b
-    const int n_wtiles = (R.n + 31) / 32;
     const int warps_total = gridDim.x * kScanWarps;
     unsigned long long compares_total = 0;
     auto issue_tile = [&](int wt, int b) {  // this warp's 32 reads: one TMA bulk copy + a tail shorter than 16 bytes
@@ -515,108 +415,66 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
             reinterpret_cast<uint16_t *>(wbuf(b) + S.flags_off)[lane] = R.flags[(size_t)wt * 32 + lane];
     };
     int cur = 0;
-    int qhead = 0, qcount = 0;  // the parking queue (warp-uniform)
-    unsigned parked_total = 0;
+    const int n_items = S.list != nullptr ? (int)ctr->n_parked : R.n;
+    const int n_wtiles = (n_items + 31) / 32;
     const int wt0 = blockIdx.x * kScanWarps + wib;
     if (S.stage_tile && wt0 < n_wtiles) issue_tile(wt0, 0);
     const bool flags_staged = S.stage_tile && S.stage_flags;
     for (int wt = wt0; wt < n_wtiles; wt += warps_total) {
-        const bool last_tile = wt + warps_total >= n_wtiles;
         if (S.stage_tile) {
-            if (!last_tile) issue_tile(wt + warps_total, cur ^ 1);  // prefetch; that buffer was released below
+            if (wt + warps_total < n_wtiles) issue_tile(wt + warps_total, cur ^ 1);  // prefetch; that buffer was released below
             mbar_wait(&tile_bar[wib][cur], (phase >> cur) & 1u);
             phase ^= 1u << cur;
             __syncwarp();  // tail bytes visible
         }
-#pragma unroll 1
-        for (int pass = 0;; ++pass) {
-            int r = -1;
+        {
+            const int item = wt * 32 + lane;
+            const bool active = item < n_items;
+            int r = item;
             uint16_t fl = 0;
-            bool active = false;   // this lane finishes a read in this pass
-            bool search = false;   // ... and it still needs the ungapped matcher
-            int cand = -1;         // the exact-prefix table's primer: the only possible ungapped match
+            bool search = false;   // this lane still needs the ungapped matcher
             idp_result res = none_result();
             c.compares = 0;
-            if (pass == 0) {
-                r = wt * 32 + lane;
-                active = r < R.n;
-                if (active) {
-                    fl = flags_staged ? reinterpret_cast<const uint16_t *>(smem + (size_t)(2 * wib + cur) * S.tile_smem_bytes + S.flags_off)[lane]
-                                      : R.flags[r];
-                    const uint8_t *s;
-                    read_geom(R, r, s, c.len);
-                    const bool rc = seq_order_is_rc(fl);
-                    if (ONCHIP) {  // index the shared array itself (16-byte aligned) so the loads stay LDS; the buffer has slack on both sides of what is read
-                        const uint32_t bo = (uint32_t)(2 * wib + cur) * S.tile_smem_bytes + (uint32_t)lane * S.stride;
-                        if (!rc || c.len >= 8 * RW) window_from_words<RW>(reinterpret_cast<const uint32_t *>(smem) + (bo >> 2), (int)(bo & 3u), c.len, rc, c.win);
-                        else window_by_bases<RW>(smem + bo, c.len, rc, c.win);
-                    } else if (S.stage_tile) {  // the same through a generic pointer
-                        const uintptr_t a = reinterpret_cast<uintptr_t>(wbuf(cur) + (size_t)lane * S.stride);
-                        if (!rc || c.len >= 8 * RW) window_from_words<RW>(reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3)), (int)(a & 3), c.len, rc, c.win);
-                        else window_by_bases<RW>(reinterpret_cast<const uint8_t *>(a), c.len, rc, c.win);
-                    } else {
-                        window_from_global<RW>(R, r, s, c.len, rc, c.win);
-                    }
-                    // ---- LocationBasedPrimerMatcher.find (PM:194-213) ----
-                    if (!(fl & IDP_F_UNMAPPED) && R.ref_idx != nullptr) {
-                        const int strand = (fl & IDP_F_REVERSE) ? 1 : 0;
-                        const int nl = P.n_loc[strand];
-                        const int pos = strand ? R.uend[r] : R.ustart[r];  // PM:180, 186
-                        const int ref = R.ref_idx[r];
-                        if (nl > 0 && ref >= 0 && pos + P.slop >= 1) {
-                            const int64_t lo = ((int64_t)ref << 32) | (uint32_t)max(pos - P.slop, 0);
-                            const int64_t hi = ((int64_t)ref << 32) | (uint32_t)(pos + P.slop);
-                            const int64_t *keys = P.loc_sortkey[strand];
-                            int a = 0, b = nl;
-                            while (a < b) { const int m = (a + b) >> 1; if (__ldg(&keys[m]) < lo) a = m + 1; else b = m; }
-                            // exactly one primer within slop, else "well I give up" (PM:198-206)
-                            if (a < nl && __ldg(&keys[a]) <= hi && !(a + 1 < nl && __ldg(&keys[a + 1]) <= hi)) {
-                                const int p = __ldg(&P.loc_primer[strand][a]);
-                                int mm, plen;
-                                if (mismatch_align<RW>(P, c, p, mm, plen)) { res.primer = p; res.type = IDP_LOCATION; res.mm = mm; }
-                            }
+            if (active) {
+                if (S.list != nullptr) r = (int)S.list[item];
+                fl = flags_staged ? reinterpret_cast<const uint16_t *>(smem + (size_t)(2 * wib + cur) * S.tile_smem_bytes + S.flags_off)[lane]
+                                  : R.flags[r];
+                const uint8_t *s;
+                read_geom(R, r, s, c.len);
+                const bool rc = seq_order_is_rc(fl);
+                if (ONCHIP && S.stage_tile) {  // index the shared array itself (16-byte aligned) so the loads stay LDS; the buffer has slack past what is read
+                    const uint32_t bo = (uint32_t)(2 * wib + cur) * S.tile_smem_bytes + (uint32_t)lane * S.stride;
+                    if (!rc || c.len >= 8 * RW) window_from_words<RW>(reinterpret_cast<const uint32_t *>(smem) + (bo >> 2), (int)(bo & 3u), c.len, rc, c.win);
+                    else window_by_bases<RW>(smem + bo, c.len, rc, c.win);
+                } else if (S.stage_tile) {  // the same through a generic pointer
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(wbuf(cur) + (size_t)lane * S.stride);
+                    if (!rc || c.len >= 8 * RW) window_from_words<RW>(reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3)), (int)(a & 3), c.len, rc, c.win);
+                    else window_by_bases<RW>(reinterpret_cast<const uint8_t *>(a), c.len, rc, c.win);
+                } else {
+                    window_from_global<RW>(R, r, s, c.len, rc, c.win);
+                }
+                // ---- LocationBasedPrimerMatcher.find (PM:194-213) ----
+                if (!(fl & IDP_F_UNMAPPED) && R.ref_idx != nullptr) {
+                    const int strand = (fl & IDP_F_REVERSE) ? 1 : 0;
+                    const int nl = P.n_loc[strand];
+                    const int pos = strand ? R.uend[r] : R.ustart[r];  // PM:180, 186
+                    const int ref = R.ref_idx[r];
+                    if (nl > 0 && ref >= 0 && pos + P.slop >= 1) {
+                        const int64_t lo = ((int64_t)ref << 32) | (uint32_t)max(pos - P.slop, 0);
+                        const int64_t hi = ((int64_t)ref << 32) | (uint32_t)(pos + P.slop);
+                        const int64_t *keys = P.loc_sortkey[strand];
+                        int a = 0, b = nl;
+                        while (a < b) { const int m = (a + b) >> 1; if (__ldg(&keys[m]) < lo) a = m + 1; else b = m; }
+                        // exactly one primer within slop, else "well I give up" (PM:198-206)
+                        if (a < nl && __ldg(&keys[a]) <= hi && !(a + 1 < nl && __ldg(&keys[a + 1]) <= hi)) {
+                            const int p = __ldg(&P.loc_primer[strand][a]);
+                            int mm, plen;
+                            if (mismatch_align<RW>(P, c, p, mm, plen)) { res.primer = p; res.type = IDP_LOCATION; res.mm = mm; }
                         }
                     }
-                    // UngappedAlignmentBasedPrimerMatcher.find (PM:230-248); a read shorter than k has no candidates (PM:109)
-                    search = res.type == IDP_NONE && !(ix.k > 0 && c.len < ix.k);
                 }
-                if (use_fx) {
-                    bool park = false;
-                    if (search) {
-                        const uint32_t w0 = c.win[0], w1 = c.win[RW >= 2 ? 1 : 0];
-                        // every one of the first 12 codes non-zero (a zero code -- '=' or past the read's end -- matches every primer)
-                        const uint32_t z = ((w0 - 0x11111111u) & ~w0 & 0x88888888u) | (((w1 | 0xFFFF0000u) - 0x11111111u) & ~w1 & 0x00008888u);
-                        const int e = z == 0u ? (int)fx_tab[fx_hash(w0, w1, P.fx_mul, P.fx_shift)] : 0;
-                        cand = e - 1;
-                        if (e != 0) {  // the slot may belong to another spelling: the primer must match these 12 bases itself
-                            const uint32_t *pm = c.pmask + (size_t)cand * P.ww;
-                            if (((w0 & ~pm[0]) | (w1 & ~pm[1] & 0xFFFFu)) != 0u) cand = -1;
-                        }
-                        park = cand < 0;
-                    }
-                    const unsigned pm_ballot = __ballot_sync(0xffffffffu, park);
-                    if (park) {
-                        queue[(qhead + qcount + __popc(pm_ballot & ((1u << lane) - 1u))) & (kScanQueueCap - 1)] = make_uint2((unsigned)r, (unsigned)fl);
-                        active = false; search = false;
-                    }
-                    qcount += __popc(pm_ballot);
-                    parked_total += __popc(pm_ballot);
-                }
-            } else {
-                if (!(use_fx && (qcount >= 32 || (last_tile && qcount > 0)))) break;
-                __syncwarp();  // the queue entries written in earlier passes are visible
-                const int n_pop = min(qcount, 32);
-                if (lane < n_pop) {
-                    const uint2 item = queue[(qhead + lane) & (kScanQueueCap - 1)];
-                    r = (int)item.x; fl = (uint16_t)item.y;
-                    active = true; search = true;
-                    const uint8_t *s;
-                    read_geom(R, r, s, c.len);
-                    window_from_global<RW>(R, r, s, c.len, seq_order_is_rc(fl), c.win);
-                }
-                qhead = (qhead + n_pop) & (kScanQueueCap - 1);
-                qcount -= n_pop;
-                __syncwarp();  // entries consumed before a later pass overwrites them
+                // UngappedAlignmentBasedPrimerMatcher.find (PM:230-248); a read shorter than k has no candidates (PM:109)
+                search = res.type == IDP_NONE && !(ix.k > 0 && c.len < ix.k);
             }
             if (search) {
                 Best2 best;
@@ -656,10 +514,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
                     };
                     int n_surv = 2;  // "unknown": the general loop below decides
                     bool seeded = false;
-                    if (cand >= 0) {
-                        n_surv = 1; q0 = cand; seeded = true;
-                        c.count((unsigned)kFxBases);
-                    } else if (P.seed_ok) {
+                    if (P.seed_ok) {
                         int s0, s1, s2, s3;
                         if (seed_filter<RW>(P, c, seed_tab, s0, s1, s2, s3)) {
                             seeded = true;
@@ -742,20 +597,18 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
                 write_result(five, r, res);
                 rtype[r] = res.type;  // what metrics_kernel reads: one byte instead of the whole record
             }
-            // fall-through list (IP:444-450), warp-aggregated append
-            const unsigned ballot = __ballot_sync(0xffffffffu, need_gapped);
-            if (ballot) {
-                unsigned base = 0;
-                if (lane == __ffs(ballot) - 1) base = atomicAdd(&ctr->n_fall, __popc(ballot));
-                base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
-                if (need_gapped) fall[base + __popc(ballot & ((1u << lane) - 1u))] = (unsigned)r;
+            // fall-through reads (IP:444-450): one bit each; compact_mask_kernel turns the mask into the list
+            if (S.list == nullptr) {
+                const unsigned ballot = __ballot_sync(0xffffffffu, need_gapped);
+                if (lane == 0) S.fall_mask[wt] = ballot;
+            } else if (need_gapped) {
+                atomicOr(&S.fall_mask[r >> 5], 1u << (r & 31));  // result unused: a fire-and-forget reduction
             }
             if constexpr (ST) compares_total += c.compares;
         }
         __syncwarp();  // all lanes are done with this tile buffer: the next iteration may overwrite it
         cur ^= 1;
     }
-    if (lane == 0 && parked_total) atomicAdd(&ctr->n_parked, parked_total);
     // statistics: base comparisons performed, one atomic per warp
     if constexpr (ST) {
 #pragma unroll

@@ -207,10 +207,14 @@ int idp_match_batch16_device(idp_ctx *ctx, const idp_reads *reads, int32_t n_rea
 void idp_result16_unpack(const idp_result16 *in, int64_t n, idp_result *out);
 
 /* ---- the aligner seam: a batched AsyncAligner.align (AA:37-54) ----
- * queries/targets are ASCII, concatenated, with n+1 offsets; outputs are Alignment.score, targetStart and
- * targetEnd (1-based).  mode is IDP_MODE_*; scoring comes from the context's panel parameters. */
+ * queries/targets are ASCII (upper-case IUPAC or '='), concatenated, with n+1 offsets starting at 0; outputs are
+ * Alignment.score, targetStart and targetEnd (1-based) and, when query_start / query_end are not NULL (both or neither),
+ * queryStart / queryEnd.  mode is IDP_MODE_*; scoring comes from the context's panel parameters.  The letters are packed and
+ * checked on the GPU; queries of up to 64 bases run on the register-resident aligners (Local with query coordinates, Global
+ * and longer queries on the generic one).  Host pointers; the call returns when the results are in place. */
 int idp_align_batch(idp_ctx *ctx, int mode, const char *queries, const int64_t *q_off, const char *targets,
-                    const int64_t *t_off, int32_t n, int32_t *score, int32_t *target_start, int32_t *target_end);
+                    const int64_t *t_off, int32_t n, int32_t *score, int32_t *target_start, int32_t *target_end,
+                    int32_t *query_start, int32_t *query_end);
 
 /* ---- host-side result helpers (pure functions, same IEEE double operations as the JVM) ---- */
 double idp_result_score(const idp_result *r);        /* GappedAlignmentPrimerMatch.score        (PM:315, 321) */
@@ -233,6 +237,16 @@ int    idp_format_info(const idp_panel *panel, const idp_result *r, uint16_t rea
 int    idp_classify_primer_pair(const idp_panel *panel, int32_t f5_primer, int32_t r5_primer, int32_t min_insert_length, int32_t max_insert_length);
 int    idp_classify_templates(const idp_panel *panel, const uint16_t *flags, const idp_result *five, int32_t n_reads,
                               int32_t min_insert_length, int32_t max_insert_length, uint8_t *cls_per_read, int64_t *counts6);
+/* The same classification as a DEVICE epilogue on the 5' records of a batch (no record ever crosses PCIe for it).
+ * idp_classify_batch_device: flags / five / cls_per_read are device pointers on the context's device; five holds n_reads
+ * records, idp_result when compact = 0 and idp_result16 when compact = 1, as the idp_match_batch*_device calls leave them;
+ * cls_per_read (may be NULL) receives one IDP_CLASS_* byte per read, counts6 (host, may be NULL) is ADDED to.
+ * idp_ctx_set_classify makes every later idp_match_batch* call of the context run it right after the 5' matching (before the 3'
+ * pass): cls_per_read (may be NULL) is then a HOST array for idp_match_batch / idp_match_batch16 and a DEVICE array for the
+ * *_device calls, counts6 (host, may be NULL) is ADDED to by every call; min_insert_length < 0 switches the epilogue off. */
+int    idp_classify_batch_device(idp_ctx *ctx, const uint16_t *flags, const void *five, int compact, int32_t n_reads,
+                                 int32_t min_insert_length, int32_t max_insert_length, uint8_t *cls_per_read, int64_t *counts6);
+int    idp_ctx_set_classify(idp_ctx *ctx, int32_t min_insert_length, int32_t max_insert_length, uint8_t *cls_per_read, int64_t *counts6);
 /* Host ingest: uncompressed BAM alignment records (the bytes inside the BGZF blocks: block_size-prefixed records, SAMv1 4.2),
  * queryname-grouped as Bams.templateIterator consumes them (IP:288-289), into the arrays of idp_reads.  The record's own 4-bit
  * `seq` bytes are copied unchanged; unclipped ends come from the CIGAR (PM:180, 186), IDP_F_FR_PAIR from the mate fields (fgbio

@@ -233,17 +233,17 @@ class AsyncCudaAligner {
   public:
     AsyncCudaAligner(int matchScore, int mismatchScore, int gapOpen, int gapExtend, int mode = IDP_MODE_GLOCAL, int device = 0)
         : tool_({Primer("p", "p+", "A", true), Primer("p", "p-", "T", false)}, options(matchScore, mismatchScore, gapOpen, gapExtend), {}, device), mode_(mode) {}
-    struct Alignment { int32_t score, targetStart, targetEnd; };
+    struct Alignment { int32_t score, targetStart, targetEnd, queryStart, queryEnd; };
     std::vector<Alignment> align(const std::vector<std::string> &queries, const std::vector<std::string> &targets) {
         const int32_t n = (int32_t)queries.size();
         std::string q, t;
         std::vector<int64_t> qo(n + 1, 0), to(n + 1, 0);
         for (int32_t i = 0; i < n; ++i) { q += queries[i]; t += targets[i]; qo[i + 1] = (int64_t)q.size(); to[i + 1] = (int64_t)t.size(); }
-        std::vector<int32_t> s(n), ts(n), te(n);
-        check(idp_align_batch(tool_.context(), mode_, q.data(), qo.data(), t.data(), to.data(), n, s.data(), ts.data(), te.data()));
+        std::vector<int32_t> s(n), ts(n), te(n), qs(n), qe(n);
+        check(idp_align_batch(tool_.context(), mode_, q.data(), qo.data(), t.data(), to.data(), n, s.data(), ts.data(), te.data(), qs.data(), qe.data()));
         numAligned += n;
         std::vector<Alignment> out(n);
-        for (int32_t i = 0; i < n; ++i) out[i] = Alignment{s[i], ts[i], te[i]};
+        for (int32_t i = 0; i < n; ++i) out[i] = Alignment{s[i], ts[i], te[i], qs[i], qe[i]};
         return out;
     }
     int64_t numAligned = 0;

@@ -341,11 +341,43 @@ def test_align_batch_matches_oracle_aligner():  # AsyncAlignerTest.scala:33-57, 
         params = O.make_params(**scores)
         for mode in (L.MODE_LOCAL, L.MODE_GLOCAL, L.MODE_GLOBAL):
             al = idp.AsyncCudaAligner(mode=mode, **scores)
-            score, ts, te = al.align(queries, targets)
+            score, ts, te = al.align(queries, targets)                                   # register-resident aligners (Local, Glocal)
+            s2, ts2, te2, qs, qe = al.align(queries, targets, query_coordinates=True)     # Local: the generic one, with query coordinates
+            short = [i for i, q in enumerate(queries) if len(q) <= 32]                   # a batch that fits the 32-row variant
+            s3, ts3, te3 = al.align([queries[i] for i in short], [targets[i] for i in short])
             al.close()
             for i, (q, t) in enumerate(zip(queries, targets)):
                 a = O.align(params, mode, q, t)
                 assert (int(score[i]), int(ts[i]), int(te[i])) == (a["score"], a["target_start"], a["target_end"]), (mode, scores, q, t, a)
+                assert (int(s2[i]), int(ts2[i]), int(te2[i]), int(qs[i]), int(qe[i])) == (a["score"], a["target_start"], a["target_end"], a["query_start"], a["query_end"]), (mode, scores, q, t, a)
+            assert np.array_equal(s3, score[short]) and np.array_equal(ts3, ts[short]) and np.array_equal(te3, te[short])
+
+
+def test_align_batch_long_queries_and_bad_letters():
+    rng = np.random.default_rng(6)
+    queries, targets = [], []
+    for i in range(120):   # queries beyond the 64 register rows: the generic aligner, all modes
+        n, m = int(rng.integers(1, 200)), int(rng.integers(0, 300))
+        q = "".join("ACGTN"[x] for x in rng.integers(0, 5, n))
+        t = "".join("ACGTN"[x] for x in rng.integers(0, 5, m))
+        if i % 2 and m > n:
+            pos = int(rng.integers(0, m - n + 1))
+            t = t[:pos] + q + t[pos + n:]
+        queries.append(q.encode()); targets.append(t.encode())
+    scores = dict(match_score=1, mismatch_score=-4, gap_open=-6, gap_extend=-1)
+    params = O.make_params(**scores)
+    for mode in (L.MODE_LOCAL, L.MODE_GLOCAL, L.MODE_GLOBAL):
+        al = idp.AsyncCudaAligner(mode=mode, **scores)
+        s, ts, te, qs, qe = al.align(queries, targets, query_coordinates=True)
+        for i, (q, t) in enumerate(zip(queries, targets)):
+            a = O.align(params, mode, q, t)
+            assert (int(s[i]), int(ts[i]), int(te[i]), int(qs[i]), int(qe[i])) == (a["score"], a["target_start"], a["target_end"], a["query_start"], a["query_end"]), (mode, q, t, a)
+        with pytest.raises(L.IdpError) as err:   # lower case is not accepted (checked on the GPU while packing)
+            al.align([b"ACGT", b"ACgT"], [b"ACGTACGT", b"ACGTACGT"])
+        assert err.value.code == L.ERR_UNSUPPORTED
+        s4, _, _ = al.align([b"ACGT"], [b"TTACGTTT"])   # the context is still usable
+        assert int(s4[0]) == (4 if mode != L.MODE_GLOBAL else O.align(params, mode, b"ACGT", b"TTACGTTT")["score"])
+        al.close()
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -576,3 +608,70 @@ def test_maximum_sizes_and_empty_batch():
     # beyond the limits the library refuses instead of approximating
     with pytest.raises(idp.IdpError):
         idp.IdentifyPrimers([idp.Primer("x", "x+", seq(257), True), idp.Primer("x", "x-", seq(20), False)], device=None)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# downstream classification as a device epilogue (scripts/post_process_bam.py:56-78): against the host function, which
+# tests/test_host_abi.py pins to the outputs of the reference's own Python function (tests/golden/classify_golden.json)
+# ------------------------------------------------------------------------------------------------------------------
+def _golden_classify_panel():
+    import json
+    g = json.load(open(os.path.join(H.ROOT, "tests", "golden", "classify_golden.json")))
+    return g, [idp.Primer(p["pair_id"], p["primer_id"], p["sequence"], p["positive_strand"], p["ref_name"], p["start"], p["end"]) for p in g["primers"]]
+
+
+@pytest.mark.parametrize("compact", [False, True])
+def test_device_classification_of_crafted_records(compact):
+    """Every (R1 match, R2 match) combination over the golden panel, pairs and fragments, through idp_classify_batch_device."""
+    import torch
+    g, primers = _golden_classify_panel()
+    n_p = len(primers)
+    rng = np.random.default_rng(12)
+    m1, m2 = np.meshgrid(np.arange(-1, n_p), np.arange(-1, n_p), indexing="ij")
+    m1, m2 = m1.reshape(-1), m2.reshape(-1)
+    frag = rng.integers(-1, n_p, 500)
+    prim = np.concatenate([np.stack([m1, m2], axis=1).reshape(-1), frag])
+    flags = np.concatenate([np.tile([H.F_PAIRED | H.F_FIRST | H.F_MATE_NEXT | H.F_UNMAPPED, H.F_PAIRED | H.F_SECOND | H.F_UNMAPPED], len(m1)),
+                            np.where(rng.random(500) < 0.5, H.F_UNMAPPED, H.F_UNMAPPED | H.F_PAIRED | H.F_FIRST)]).astype(np.uint16)
+    five = np.zeros(len(prim), dtype=L.RESULT_DTYPE)
+    five["primer"] = prim
+    five["type"] = np.where(prim >= 0, rng.integers(1, 4, len(prim)), 0)
+    five["next_mm"] = np.where(five["type"] == L.UNGAPPED, L.NEXT_NA, 0)
+    with idp.IdentifyPrimers(primers, ref_names=["chr1", "chr2", "chr3", "chrX"]) as tool:
+        for lo_hi in ((50, 250), (102, 207), (0, 10)):
+            want_cls, want_counts = tool.classify_templates(flags, five, *lo_hi)
+            dev = torch.device("cuda", 0)
+            if compact:
+                rec = np.zeros(len(prim), dtype=L.RESULT16_DTYPE)
+                rec["head"] = (prim + 1).astype(np.uint32) | (five["type"].astype(np.uint32) << 24)
+                rec["b"] = np.where(five["type"] == L.UNGAPPED, L.NEXT16_NA, 0)
+                assert L.unpack16(rec).tobytes() == five.tobytes()
+                d5 = torch.from_numpy(rec.view(np.uint8).reshape(-1, 16)).to(dev)
+            else:
+                d5 = torch.from_numpy(five.view(np.uint8).reshape(-1, 32)).to(dev)
+            dfl = torch.from_numpy(flags.view(np.int16)).to(dev)
+            dcls = torch.full((len(prim),), 255, dtype=torch.uint8, device=dev)
+            counts = tool.classify_batch_device(dfl.data_ptr(), d5.data_ptr(), len(prim), compact, dcls.data_ptr(), *lo_hi)
+            assert counts == want_counts
+            assert np.array_equal(dcls.cpu().numpy(), want_cls)
+            assert len(set(want_cls.tolist())) == 6   # every class occurs
+
+
+@pytest.mark.parametrize("name,compact", [("c5", True), ("c1", False)])
+def test_classification_epilogue_inside_process_batch(name, compact):
+    panel, reads, opts = synth.workload(name, 3000)
+    with idp.IdentifyPrimers(panel.primers, ref_names=panel.ref_names, **opts) as tool:
+        batch = idp.ReadBatch(reads.seq4().reshape(-1), reads.flags, fixed_len=150, ref_idx=reads.ref_idx, unclipped_start=reads.ustart,
+                              unclipped_end=reads.uend)
+        five, _ = tool.process_batch(batch)
+        want_cls, want_counts = tool.classify_templates(reads.flags, five, 60, 240)
+        tool.set_classify(60, 240)
+        os.environ["IDP_CHUNK_READS"] = "1111"   # several chunks: the class bytes come back chunk by chunk
+        try:
+            five2, _ = tool.process_batch(batch, compact=compact)
+        finally:
+            del os.environ["IDP_CHUNK_READS"]
+        assert five2.tobytes() == five.tobytes()
+        assert np.array_equal(tool.last_classes, want_cls)
+        assert dict(zip(tool.CLASS_NAMES, tool.class_counts.tolist())) == want_counts
+        assert want_counts["Canonical"] > 1000
