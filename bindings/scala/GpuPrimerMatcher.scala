@@ -2,6 +2,9 @@
  * Reference-side binding (NOT compiled in this image: no JVM).  Lives in package com.fulcrumgenomics.identifyprimers so that it can
  * see the private[identifyprimers] types, and replaces the body of IdentifyPrimers.processBatch (IdentifyPrimers.scala:381-436):
  * the per-read Future plumbing becomes ONE native call per 5,000-template batch.
+ *
+ * `Native` declares every entry of bindings/jni/idprimer_jni.c, i.e. every export of include/idprimer.h; the class below uses the
+ * ones the matching path needs.
  */
 package com.fulcrumgenomics.identifyprimers
 
@@ -13,17 +16,68 @@ import com.fulcrumgenomics.bam.api.SamRecord
 private[identifyprimers] object GpuPrimerMatcher {
   object Native {
     System.loadLibrary("idprimer_jni")
+    // library
+    @native def abiVersion(): Int
+    @native def lastError(): String
+    @native def deviceCount(): Int
+    @native def alignPolicy(): Int
+    // panel: the three matchers' immutable state (IP:223-234)
     @native def panelCreate(primers: ByteBuffer, n: Int, params: ByteBuffer): Long
     @native def panelDestroy(h: Long): Unit
+    @native def panelSize(h: Long): Int
+    @native def panelPrimerLength(h: Long, i: Int): Int
+    @native def panelPrimerHash(h: Long, i: Int): Int
+    @native def panelKmerPostings(h: Long, which: Int, kmer: String, out: ByteBuffer, cap: Int): Int
     @native def panelWindow(panel: Long): Int  // idp_panel_window: bases the 5' chain can reach, -1 with --three-prime
+    // context: one per worker thread
     @native def ctxCreate(panel: Long, device: Int): Long
     @native def ctxDestroy(h: Long): Unit
+    @native def ctxSetStream(h: Long, cudaStream: Long): Unit
+    @native def ctxTimings(h: Long, out: ByteBuffer): Unit
+    @native def ctxSetClassify(h: Long, minInsert: Int, maxInsert: Int, clsPerRead: ByteBuffer, counts6: ByteBuffer): Unit
+    @native def ctxSetClassifyDevice(h: Long, minInsert: Int, maxInsert: Int, clsPerRead: Long, counts6: ByteBuffer): Unit
+    @native def hostAlloc(bytes: Long): ByteBuffer  // pinned
+    @native def hostFree(buf: ByteBuffer): Unit
+    // processBatch (IP:381-436): 32-byte and 16-byte records, host and device pointers
     @native def matchBatch(ctx: Long, seq4: ByteBuffer, seqOff: ByteBuffer, len: ByteBuffer, refIdx: ByteBuffer, uStart: ByteBuffer,
                            uEnd: ByteBuffer, flags: ByteBuffer, fixedLen: Int, n: Int, five: ByteBuffer, three: ByteBuffer,
                            metrics160: ByteBuffer, nAligned: ByteBuffer): Unit
+    @native def matchBatch16(ctx: Long, seq4: ByteBuffer, seqOff: ByteBuffer, len: ByteBuffer, refIdx: ByteBuffer, uStart: ByteBuffer,
+                             uEnd: ByteBuffer, flags: ByteBuffer, fixedLen: Int, n: Int, five: ByteBuffer, three: ByteBuffer,
+                             metrics160: ByteBuffer, nAligned: ByteBuffer): Unit
+    @native def matchBatchDevice(ctx: Long, seq4: Long, seqOff: Long, len: Long, refIdx: Long, uStart: Long, uEnd: Long, flags: Long,
+                                 fixedLen: Int, n: Int, five: Long, three: Long, metrics160: ByteBuffer, nAligned: ByteBuffer): Unit
+    @native def matchBatch16Device(ctx: Long, seq4: Long, seqOff: Long, len: Long, refIdx: Long, uStart: Long, uEnd: Long, flags: Long,
+                                   fixedLen: Int, n: Int, five: Long, three: Long, metrics160: ByteBuffer, nAligned: ByteBuffer): Unit
+    @native def result16Unpack(in: ByteBuffer, n: Long, out: ByteBuffer): Unit
+    // result helpers, tag strings (PMa:78-88), metrics (IdentifyPrimersMetric.scala:34-89)
+    @native def resultScore(results: ByteBuffer, i: Int): Double
+    @native def resultSecond(results: ByteBuffer, i: Int): Double
+    @native def metricBin(templateType: Int, isFr: Int, r1: Int, r2: Int): Int
+    @native def summaryMetrics(metrics160: ByteBuffer, out17: ByteBuffer): Unit
+    @native def formatInfo(panel: Long, results: ByteBuffer, i: Int, readFlags: Int): String
+    @native def headerComments(): String
+    // downstream classification (scripts/post_process_bam.py:56-78)
+    @native def classifyPrimerPair(panel: Long, f5: Int, r5: Int, minInsert: Int, maxInsert: Int): Int
+    @native def classifyTemplates(panel: Long, flags: ByteBuffer, five: ByteBuffer, n: Int, minInsert: Int, maxInsert: Int,
+                                  clsPerRead: ByteBuffer, counts6: ByteBuffer): Unit
+    @native def classifyBatchDevice(ctx: Long, flags: Long, five: Long, compact: Int, n: Int, minInsert: Int, maxInsert: Int,
+                                    clsPerRead: Long, counts6: ByteBuffer): Unit
+    // BAM records <-> batches
+    @native def bamScan(bam: ByteBuffer, nBytes: Long, out2: ByteBuffer): Unit
+    @native def bamToBatch(bam: ByteBuffer, nBytes: Long, seq4: ByteBuffer, seqOff: ByteBuffer, len: ByteBuffer, refIdx: ByteBuffer,
+                           uStart: ByteBuffer, uEnd: ByteBuffer, flags: ByteBuffer, recIndex: ByteBuffer): Unit
+    @native def bamToBatchWindow(panel: Long, bam: ByteBuffer, nBytes: Long, seq4: ByteBuffer, seqOff: ByteBuffer, len: ByteBuffer,
+                                 refIdx: ByteBuffer, uStart: ByteBuffer, uEnd: ByteBuffer, flags: ByteBuffer, recIndex: ByteBuffer): Unit
+    @native def bamAnnotate(panel: Long, bam: ByteBuffer, nBytes: Long, five: ByteBuffer, three: ByteBuffer, n: Int, out: ByteBuffer, outCap: Long): Long
+    @native def packBases(ascii: ByteBuffer, n: Int, seq4: ByteBuffer): Unit
+    @native def unpackBases(seq4: ByteBuffer, n: Int, ascii: ByteBuffer): Unit
+    // the aligner seam on an existing context (AsyncCudaAligner has its own handle)
+    @native def alignBatch(ctx: Long, mode: Int, queries: ByteBuffer, qOff: ByteBuffer, targets: ByteBuffer, tOff: ByteBuffer, n: Int,
+                           score: ByteBuffer, targetStart: ByteBuffer, targetEnd: ByteBuffer, queryStart: ByteBuffer, queryEnd: ByteBuffer): Unit
   }
-  val ResultBytes = 32 // sizeof(idp_result)
-  private def direct(n: Int) = ByteBuffer.allocateDirect(n).order(ByteOrder.LITTLE_ENDIAN)
+  val ResultBytes = 16 // sizeof(idp_result16): what crosses PCIe
+  private def direct(n: Int) = ByteBuffer.allocateDirect(math.max(n, 8)).order(ByteOrder.LITTLE_ENDIAN)
 }
 
 /** One per worker thread (an idp_ctx is not thread-safe); the panel handle is shared (IdentifyPrimers.scala:223-234). */
@@ -59,25 +113,26 @@ private[identifyprimers] class GpuPrimerMatcher(panel: Long, device: Int, primer
     recs.zipWithIndex.foreach { case (r, j) => seq4.position(seqOff.getLong(8 * j).toInt); seq4.put(htsjdk.samtools.SAMUtils.bytesToCompressedBases(shipped(r))) }
     val five = direct(ResultBytes * n); val three = if (threePrime >= 0) direct(ResultBytes * n) else null
     val metrics = direct(8 * 160); val nAligned = direct(8)
-    Native.matchBatch(ctx, seq4, seqOff, len, refIdx, uS, uE, flags, 0, n, five, three, metrics, nAligned)
+    Native.matchBatch16(ctx, seq4, seqOff, len, refIdx, uS, uE, flags, 0, n, five, three, metrics, nAligned)
     (0 until n).map { j => (decode(five, j), if (three == null) None else decode(three, j)) }
   }
 
-  /** idp_result -> the case classes of PrimerMatch.scala:96-117; a non-zero status is the require() the JVM would have thrown. */
+  /** idp_result16 -> the case classes of PrimerMatch.scala:96-117; a non-zero status is the require() the JVM would have thrown. */
   private def decode(buf: ByteBuffer, j: Int): Option[PrimerMatch] = {
     val b = ResultBytes * j
-    val status = buf.get(b + 5)
+    val head = buf.getInt(b)
+    val primer = (head & 0xFFFFFF) - 1; val kind = (head >>> 24) & 3; val multi = ((head >>> 26) & 1) != 0; val status = (head >>> 27) & 7
     require(status == 0, s"primer matching would have failed a requirement (status $status)")
-    buf.get(b + 4) match {
+    val a = buf.getShort(b + 4).toInt; val bb = buf.getShort(b + 6).toInt
+    kind match {
       case 0 => None
-      case 1 => Some(LocationBasedPrimerMatch(primers(buf.getInt(b)), buf.getInt(b + 8)))
-      case 2 => Some(UngappedAlignmentPrimerMatch(primers(buf.getInt(b)), buf.getInt(b + 8), buf.getInt(b + 12)))
+      case 1 => Some(LocationBasedPrimerMatch(primers(primer), a))
+      case 2 => Some(UngappedAlignmentPrimerMatch(primers(primer), a, if (bb == 32767) Int.MaxValue else bb))  // IDP_NEXT16_NA -> "na"
       case 3 =>
-        val multi = buf.get(b + 6) != 0
-        val raw = buf.getInt(b + 16); val rawNext = buf.getInt(b + 20); val qLen = buf.getShort(b + 24); val qLenNext = buf.getShort(b + 26)
-        val score  = if (multi) raw / qLen.toDouble else raw.toDouble            // PrimerMatcher.scala:321 vs :315
-        val second = if (multi) rawNext / qLenNext.toDouble else 0d               // :322
-        Some(GappedAlignmentPrimerMatch(primers(buf.getInt(b)), score, second, buf.getShort(b + 28), buf.getShort(b + 30)))
+        val qLen = buf.getShort(b + 8) & 0xFFFF; val qLenNext = buf.getShort(b + 10) & 0xFFFF
+        val score  = if (multi) a / qLen.toDouble else a.toDouble                 // PrimerMatcher.scala:321 vs :315
+        val second = if (multi) bb / qLenNext.toDouble else 0d                    // :322
+        Some(GappedAlignmentPrimerMatch(primers(primer), score, second, buf.getShort(b + 12) & 0xFFFF, buf.getShort(b + 14) & 0xFFFF))
     }
   }
   override def close(): Unit = Native.ctxDestroy(ctx)

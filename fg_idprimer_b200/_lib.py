@@ -17,7 +17,7 @@ NEXT_NA = 2147483647
 MODE_LOCAL, MODE_GLOCAL, MODE_GLOBAL = 0, 1, 3
 
 # every symbol include/idprimer.h declares
-EXPORTS = ["idp_abi_version", "idp_last_error", "idp_device_count", "idp_panel_create", "idp_panel_destroy", "idp_panel_size",
+EXPORTS = ["idp_abi_version", "idp_last_error", "idp_device_count", "idp_align_policy", "idp_panel_create", "idp_panel_destroy", "idp_panel_size",
            "idp_panel_primer_length", "idp_panel_primer_hash", "idp_panel_kmer_postings", "idp_ctx_create", "idp_ctx_destroy",
            "idp_ctx_set_stream", "idp_ctx_timings", "idp_host_alloc", "idp_host_free", "idp_match_batch", "idp_match_batch_device",
            "idp_match_batch16", "idp_match_batch16_device", "idp_result16_unpack", "idp_align_batch", "idp_result_score", "idp_result_second", "idp_metric_bin", "idp_summary_metrics", "idp_format_info",

@@ -249,6 +249,9 @@ static int upload_panel(idp_ctx *c) {
     const int wb = p.window_bases;
     c->cfg.rw = wb <= 32 ? 4 : wb <= 40 ? 5 : wb <= 64 ? 8 : wb <= 128 ? 16 : 32;
     c->cfg.nq = p.max_seq_len <= 32 ? 32 : p.max_seq_len <= 64 ? 64 : 0;
+    if (!AlignPolicy::kIsDefault) {  // the register-resident aligners implement the default policy only: everything takes the generic kernels
+        c->cfg.nq = 0; d.packed_trace_ok = 0; d.fits16_glocal = 0; d.fits16_local = 0;
+    }
     const int nq = c->cfg.nq;
     d.qbot = nullptr;
     if (nq > 0) {  // primers bottom-aligned in nq rows for the register-resident aligners
@@ -634,6 +637,8 @@ int idp_match_batch16(idp_ctx *c, const idp_reads *reads, int32_t n_reads, idp_r
                       int64_t *metrics160, int64_t *n_gapped_alignments) {
     return match_batch_host(c, reads, n_reads, five, three, true, metrics160, n_gapped_alignments);
 }
+
+int idp_align_policy(void) { return AlignPolicy::kBits; }
 
 int idp_ctx_set_classify(idp_ctx *c, int32_t min_insert_length, int32_t max_insert_length, uint8_t *cls_per_read, int64_t *counts6) {
     if (!c) { set_error("idp_ctx_set_classify: NULL context"); return IDP_ERR_ARG; }

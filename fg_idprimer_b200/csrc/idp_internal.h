@@ -17,6 +17,31 @@ constexpr int kFxBases = 12;           // read bases hashed by the exact-prefix 
 constexpr int kMaxReadLen = 4095;      // target start/end are carried in 12 bits next to the score
 constexpr int32_t kNegInf = INT32_MIN / 2;  // fgbio Aligner.MinStartScore
 
+// ---- the alignment choices nothing in the reference tree pins (fgbio's Aligner is an un-vendored dependency; the reference's
+// tests only check accept / reject at that boundary: SURVEY 3.5, 8c).  The defaults are the published algorithm as the oracle
+// restates it (oracle/idp_oracle.c, ALIGN_POLICY: the same four switches under the same macro names).  The register-resident
+// aligners implement the DEFAULT policy; with any other setting every alignment is routed through the generic kernels
+// (sw_score_generic / sw_trace), which honour all four, so a correction is a compile-time flag on both sides first
+// (tests/test_align_policy.py keeps that build parity-green) and a re-derivation of the fast kernels second.
+#ifndef IDP_POLICY_LEFT_FROM_UP
+#define IDP_POLICY_LEFT_FROM_UP 0        // 1: a Left gap may also open from the Up matrix
+#endif
+#ifndef IDP_POLICY_UP_FROM_LEFT
+#define IDP_POLICY_UP_FROM_LEFT 0        // 1: an Up gap may also open from the Left matrix
+#endif
+#ifndef IDP_POLICY_EXTEND_OVER_OPEN
+#define IDP_POLICY_EXTEND_OVER_OPEN 0    // 1: equal scores prefer extending a gap over opening one from Diagonal
+#endif
+#ifndef IDP_POLICY_TIE_UP_BEFORE_LEFT
+#define IDP_POLICY_TIE_UP_BEFORE_LEFT 0  // 1: equal scores are tried Diagonal, Up, Left (diagonal move and end cell); default Diagonal, Left, Up
+#endif
+struct AlignPolicy {
+    static constexpr bool kLeftFromUp = IDP_POLICY_LEFT_FROM_UP != 0, kUpFromLeft = IDP_POLICY_UP_FROM_LEFT != 0;
+    static constexpr bool kExtendOverOpen = IDP_POLICY_EXTEND_OVER_OPEN != 0, kTieUpBeforeLeft = IDP_POLICY_TIE_UP_BEFORE_LEFT != 0;
+    static constexpr bool kIsDefault = !kLeftFromUp && !kUpFromLeft && !kExtendOverOpen && !kTieUpBeforeLeft;
+    static constexpr int kBits = IDP_POLICY_LEFT_FROM_UP | IDP_POLICY_UP_FROM_LEFT << 1 | IDP_POLICY_EXTEND_OVER_OPEN << 2 | IDP_POLICY_TIE_UP_BEFORE_LEFT << 3;
+};
+
 void set_error(const char *fmt, ...);
 // slot of a 12-base read prefix in the exact-prefix table: w0 = bases 0..7, w1 = bases 8..15, as STORED in the row (base i of a
 // word in nibble i ^ 1); only the low half of w1 (bases 8..11) takes part

@@ -326,21 +326,24 @@ __device__ __forceinline__ int sw_score(const DevPanel &P, const int32_t *__rest
     return best;
 }
 
-// generic fallback for primers longer than the register-resident variants cover: rows live in local memory
+// generic fallback for primers longer than the register-resident variants cover, and for every alignment when AlignPolicy is
+// not the default: rows live in local memory; all four policy switches are honoured (ties do not change a score, the extra
+// gap-to-gap transitions do)
 template <bool LOCAL, bool SMAT>
 __device__ int sw_score_generic(const DevPanel &P, const int32_t *__restrict__ smat, const uint32_t *__restrict__ qwords, int n,
                                 const Oriented &T, int m, bool &missing) {
     const int oe = P.gap_open + P.gap_extend, e = P.gap_extend;
     if (m == 0) return LOCAL ? 0 : P.gap_open + n * P.gap_extend;
     int D[kMaxPrimerBases], L[kMaxPrimerBases], M[kMaxPrimerBases];
+    int U[AlignPolicy::kLeftFromUp ? kMaxPrimerBases : 1];  // Up of the previous column, only when Left may open from it
     for (int i = 0; i < n; ++i) {
-        if (LOCAL) { D[i] = 0; L[i] = 0; M[i] = 0; }
-        else { D[i] = kNegInf; L[i] = kNegInf; M[i] = P.gap_open + (i + 1) * P.gap_extend; }
+        if (LOCAL) { D[i] = 0; L[i] = 0; M[i] = 0; if (AlignPolicy::kLeftFromUp) U[i] = 0; }
+        else { D[i] = kNegInf; L[i] = kNegInf; M[i] = P.gap_open + (i + 1) * P.gap_extend; if (AlignPolicy::kLeftFromUp) U[i] = M[i]; }  // Up(i,0)
     }
     int best = LOCAL ? 0 : kNegInf;
     for (int j = 0; j < m; ++j) {
         const uint32_t t = T.nib(j);
-        int mdiag = 0, d_up = 0, u_up = 0;
+        int mdiag = 0, d_up = 0, u_up = 0, l_up = 0;  // row 0 is all zero in Glocal and Local
         for (int i = 0; i < n; ++i) {
             const uint32_t qc = (__ldg(&qwords[i >> 3]) >> (4 * (i & 7))) & 15u;
             int s;
@@ -348,12 +351,14 @@ __device__ int sw_score_generic(const DevPanel &P, const int32_t *__restrict__ s
             else s = qc == t ? P.match_score : P.mismatch_score;
             int dn = mdiag + s;
             if (LOCAL) dn = max(dn, 0);
-            const int un = max(d_up + oe, u_up + e);
-            const int ln = max(D[i] + oe, L[i] + e);
+            int un = max(d_up + oe, u_up + e);
+            if (AlignPolicy::kUpFromLeft) un = max(un, l_up + oe);
+            int ln = max(D[i] + oe, L[i] + e);
+            if (AlignPolicy::kLeftFromUp) { ln = max(ln, U[i] + oe); U[i] = un; }
             mdiag = M[i];
             const int mn = max(dn, max(ln, un));
             D[i] = dn; L[i] = ln; M[i] = mn;
-            d_up = dn; u_up = un;
+            d_up = dn; u_up = un; l_up = ln;
             if (LOCAL) best = max(best, dn);
             else if (i == n - 1) best = max(best, mn);
         }
@@ -1104,9 +1109,11 @@ __global__ void __launch_bounds__(128, 4) sw_all_kernel(DevPanel P, DevReads R, 
 // ---------------------------------------------------------------------------------------------------------------
 struct Traced { int score, t_start, t_end, q_start, q_end; bool missing; };
 
-// QS: also carry the query row at which the path started (Local only: in Glocal / Global the whole query is aligned)
+// QS: also carry the query row at which the path started (Local only: in Glocal / Global the whole query is aligned).
+// Every choice of AlignPolicy is honoured here, in the order the oracle applies them (oracle/idp_oracle.c, align_impl).
 template <int TN, bool QS = false>
 __device__ Traced sw_trace(const DevPanel &P, const uint32_t *__restrict__ qwords, int n, const Oriented &T, int m, int mode) {
+    using Pol = AlignPolicy;
     const int oe = P.gap_open + P.gap_extend, e = P.gap_extend;
     Traced out{0, 1, 0, 1, n, false};
     const bool local = mode == IDP_MODE_LOCAL, global = mode == IDP_MODE_GLOBAL;
@@ -1114,20 +1121,26 @@ __device__ Traced sw_trace(const DevPanel &P, const uint32_t *__restrict__ qword
     int D[TN], L[TN], M[TN];
     short sD[TN], sL[TN], sM[TN];
     short qD[QS ? TN : 1], qL[QS ? TN : 1], qM[QS ? TN : 1];  // 1-based row of the boundary / clamped cell the path left
+    int U[Pol::kLeftFromUp ? TN : 1];                          // Up of the previous column (value, target start, query start)
+    short sU[Pol::kLeftFromUp ? TN : 1], qU[Pol::kLeftFromUp && QS ? TN : 1];
     for (int i = 0; i < n; ++i) {
         sD[i] = 0; sL[i] = 0; sM[i] = 0;
         if (QS) { qD[i] = (short)(i + 1); qL[i] = (short)(i + 1); qM[i] = (short)(i + 1); }
         if (local) { D[i] = 0; L[i] = 0; M[i] = 0; }
         else { D[i] = kNegInf; L[i] = kNegInf; M[i] = P.gap_open + (i + 1) * P.gap_extend; }
+        if (Pol::kLeftFromUp) { U[i] = M[i]; sU[i] = 0; if (QS) qU[i] = local ? (short)(i + 1) : (short)0; }  // column 0: Up(i,0) (Local: zero, Done)
     }
     int best = kNegInf, bi = 0, bj = 0, bstart = 0, bq = 0;
     for (int j = 1; j <= m; ++j) {
         const uint32_t t = T.nib(j - 1);
         // row 0: all matrices zero / Done in Glocal and Local; Global has only Left = open + j*extend
-        int mdiag, smdiag, d_up, sd_up, u_up, su_up;
-        int qmdiag = 0, qd_up = 0, qu_up = 0;
-        if (!global) { mdiag = 0; smdiag = j - 1; d_up = 0; sd_up = j; u_up = 0; su_up = j; }
-        else { mdiag = j == 1 ? 0 : P.gap_open + (j - 1) * P.gap_extend; smdiag = 0; d_up = kNegInf; sd_up = 0; u_up = kNegInf; su_up = 0; }
+        int mdiag, smdiag, d_up, sd_up, u_up, su_up, l_up, sl_up;
+        int qmdiag = 0, qd_up = 0, qu_up = 0, ql_up = 0;
+        if (!global) { mdiag = 0; smdiag = j - 1; d_up = 0; sd_up = j; u_up = 0; su_up = j; l_up = 0; sl_up = j; }
+        else {
+            mdiag = j == 1 ? 0 : P.gap_open + (j - 1) * P.gap_extend; smdiag = 0; d_up = kNegInf; sd_up = 0; u_up = kNegInf; su_up = 0;
+            l_up = P.gap_open + j * P.gap_extend; sl_up = 0;  // Left(0, j)
+        }
         for (int i = 0; i < n; ++i) {
             const uint32_t qc = (__ldg(&qwords[i >> 3]) >> (4 * (i & 7))) & 15u;
             int s;
@@ -1136,24 +1149,41 @@ __device__ Traced sw_trace(const DevPanel &P, const uint32_t *__restrict__ qword
             int dn = mdiag + s, sdn = smdiag, qdn = qmdiag;
             if (local && dn < 0) { dn = 0; sdn = j; qdn = i + 1; }
             int un, sun, qun, ln, sln, qln;
-            { const int a = d_up + oe, b = u_up + e; if (a >= b) { un = a; sun = sd_up; qun = qd_up; } else { un = b; sun = su_up; qun = qu_up; } }
-            { const int a = D[i] + oe, b = L[i] + e; if (a >= b) { ln = a; sln = sD[i]; qln = QS ? qD[i] : 0; } else { ln = b; sln = sL[i]; qln = QS ? qL[i] : 0; } }
-            int mn = dn, smn = sdn, qmn = qdn;
-            if (ln > mn) { mn = ln; smn = sln; qmn = qln; }
-            if (un > mn) { mn = un; smn = sun; qmn = qun; }
+            {   // Up: opened from Diagonal, extended, or (policy) opened from Left -- in that order, a later one needs a strictly higher score
+                const int a = d_up + oe, b = u_up + e;
+                if (Pol::kExtendOverOpen ? a > b : a >= b) { un = a; sun = sd_up; qun = qd_up; } else { un = b; sun = su_up; qun = qu_up; }
+                if (Pol::kUpFromLeft) { const int x = l_up + oe; if (x > un) { un = x; sun = sl_up; qun = ql_up; } }
+            }
+            {   // Left: opened from Diagonal, extended, or (policy) opened from Up
+                const int a = D[i] + oe, b = L[i] + e;
+                if (Pol::kExtendOverOpen ? a > b : a >= b) { ln = a; sln = sD[i]; qln = QS ? qD[i] : 0; } else { ln = b; sln = sL[i]; qln = QS ? qL[i] : 0; }
+                if (Pol::kLeftFromUp) { const int x = U[i] + oe; if (x > ln) { ln = x; sln = sU[i]; qln = QS ? qU[i] : 0; } }
+            }
+            int mn = dn, smn = sdn, qmn = qdn;  // the diagonal move of the next column takes the best of the three: Diagonal first on ties
+            if (Pol::kTieUpBeforeLeft) {
+                if (un > mn) { mn = un; smn = sun; qmn = qun; }
+                if (ln > mn) { mn = ln; smn = sln; qmn = qln; }
+            } else {
+                if (ln > mn) { mn = ln; smn = sln; qmn = qln; }
+                if (un > mn) { mn = un; smn = sun; qmn = qun; }
+            }
             mdiag = M[i]; smdiag = sM[i];
             if (QS) qmdiag = qM[i];
             D[i] = dn; sD[i] = (short)sdn; L[i] = ln; sL[i] = (short)sln; M[i] = mn; sM[i] = (short)smn;
             if (QS) { qD[i] = (short)qdn; qL[i] = (short)qln; qM[i] = (short)qmn; }
-            d_up = dn; sd_up = sdn; u_up = un; su_up = sun; qd_up = qdn; qu_up = qun;
-            if (local) {  // best over all cells: lowest row, then lowest column, then Diagonal / Left / Up
+            if (Pol::kLeftFromUp) { U[i] = un; sU[i] = (short)sun; if (QS) qU[i] = (short)qun; }
+            d_up = dn; sd_up = sdn; u_up = un; su_up = sun; qd_up = qdn; qu_up = qun; l_up = ln; sl_up = sln; ql_up = qln;
+            // end cell: strict '>' scanning rows then columns ascending, matrices in the policy's order
+            const int c2 = Pol::kTieUpBeforeLeft ? un : ln, sc2 = Pol::kTieUpBeforeLeft ? sun : sln, qc2 = Pol::kTieUpBeforeLeft ? qun : qln;
+            const int c3 = Pol::kTieUpBeforeLeft ? ln : un, sc3 = Pol::kTieUpBeforeLeft ? sln : sun, qc3 = Pol::kTieUpBeforeLeft ? qln : qun;
+            if (local) {  // best over all cells: lowest row, then lowest column
                 if (dn > best || (dn == best && i + 1 < bi)) { best = dn; bi = i + 1; bj = j; bstart = sdn; bq = qdn; }
-                if (ln > best || (ln == best && i + 1 < bi)) { best = ln; bi = i + 1; bj = j; bstart = sln; bq = qln; }
-                if (un > best || (un == best && i + 1 < bi)) { best = un; bi = i + 1; bj = j; bstart = sun; bq = qun; }
+                if (c2 > best || (c2 == best && i + 1 < bi)) { best = c2; bi = i + 1; bj = j; bstart = sc2; bq = qc2; }
+                if (c3 > best || (c3 == best && i + 1 < bi)) { best = c3; bi = i + 1; bj = j; bstart = sc3; bq = qc3; }
             } else if (i == n - 1 && (!global || j == m)) {
                 if (dn > best) { best = dn; bj = j; bstart = sdn; }
-                if (ln > best) { best = ln; bj = j; bstart = sln; }
-                if (un > best) { best = un; bj = j; bstart = sun; }
+                if (c2 > best) { best = c2; bj = j; bstart = sc2; }
+                if (c3 > best) { best = c3; bj = j; bstart = sc3; }
             }
         }
     }

@@ -1,5 +1,6 @@
 // Launchers of the gapped stage (idp_kernels.cuh): candidate emission, Smith-Waterman, finalize, metrics.
 #include <algorithm>
+#include <cstdlib>
 
 #include "idp_kernels.cuh"
 #include "idp_launch.h"

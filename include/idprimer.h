@@ -161,6 +161,10 @@ typedef struct idp_ctx   idp_ctx;    /* one per calling thread and device: strea
 int         idp_abi_version(void);
 const char *idp_last_error(void);                       /* thread-local message of the last failing call     */
 int         idp_device_count(void);                     /* number of usable CUDA devices (0 if none)         */
+/* The alignment choices this build was compiled with that nothing in the reference pins (fgbio's Aligner is an un-vendored
+ * dependency): bit 0 Left may open from Up, 1 Up may open from Left, 2 ties prefer extending a gap over opening one, 3 ties are
+ * tried Diagonal, Up, Left.  0 = the published algorithm (the default build); see idp_internal.h, AlignPolicy. */
+int         idp_align_policy(void);
 
 /* ---- panel: the three matchers' immutable state (IP:223-234; PM:62-117, 156-175) ---- */
 int  idp_panel_create(const idp_primer *primers, int32_t n, const idp_params *params, idp_panel **out);

@@ -394,9 +394,26 @@ static void ungapped_find(const orc_panel *p, const char *so_bases, int len, int
  * ---------------------------------------------------------------------------------------------- */
 enum { LEFT = 0, UP = 1, DIAG = 2, DONE = 3 };
 #define MIN_START_SCORE (INT_MIN / 2)
+/* The switches below are the UNPINNED choices (nothing in the reference tree decides them: its tests only check accept /
+ * reject at this boundary).  Defaults = the published fgbio algorithm as restated in SURVEY 3.5.  The product carries the very
+ * same switches (fg_idprimer_b200/csrc/idp_internal.h, AlignPolicy); tests/test_align_policy.py builds both with the
+ * non-default values and checks parity again, so that correcting a choice is a one-line change on both sides. */
+#ifndef IDP_POLICY_LEFT_FROM_UP
+#define IDP_POLICY_LEFT_FROM_UP 0      /* 1: a Left gap may also open from the Up matrix */
+#endif
+#ifndef IDP_POLICY_UP_FROM_LEFT
+#define IDP_POLICY_UP_FROM_LEFT 0      /* 1: an Up gap may also open from the Left matrix */
+#endif
+#ifndef IDP_POLICY_EXTEND_OVER_OPEN
+#define IDP_POLICY_EXTEND_OVER_OPEN 0  /* 1: equal scores prefer extending a gap over opening one from Diagonal */
+#endif
+#ifndef IDP_POLICY_TIE_UP_BEFORE_LEFT
+#define IDP_POLICY_TIE_UP_BEFORE_LEFT 0 /* 1: equal scores are tried Diagonal, Up, Left (diagonal move and end cell); default Diagonal, Left, Up */
+#endif
 static const struct {
-    int left_from_up, up_from_left;   /* extra gap->gap transitions: not present in this restatement */
-} ALIGN_POLICY = { 0, 0 };
+    int left_from_up, up_from_left, extend_over_open, tie_up_before_left;
+} ALIGN_POLICY = { IDP_POLICY_LEFT_FROM_UP, IDP_POLICY_UP_FROM_LEFT, IDP_POLICY_EXTEND_OVER_OPEN, IDP_POLICY_TIE_UP_BEFORE_LEFT };
+int orc_align_policy_bits(void) { return IDP_POLICY_LEFT_FROM_UP | IDP_POLICY_UP_FROM_LEFT << 1 | IDP_POLICY_EXTEND_OVER_OPEN << 2 | IDP_POLICY_TIE_UP_BEFORE_LEFT << 3; }
 
 static __thread int *tl_S[3]; static __thread unsigned char *tl_T[3]; static __thread size_t tl_cells;
 
@@ -440,8 +457,9 @@ static int align_impl(const orc_params *pa, int mode, const char *query, int n, 
             { /* Diagonal: from the best of (Diagonal, Left, Up) at (i-1, j-1); ties prefer Diagonal, then Left, then Up */
                 int addend = score_pair(pa, (unsigned char)query[i - 1], (unsigned char)target[j - 1], &missing);
                 int best = S[DIAG][AT(i - 1, j - 1)], dir = DIAG;
-                if (S[LEFT][AT(i - 1, j - 1)] > best) { best = S[LEFT][AT(i - 1, j - 1)]; dir = LEFT; }
-                if (S[UP][AT(i - 1, j - 1)] > best) { best = S[UP][AT(i - 1, j - 1)]; dir = UP; }
+                const int second = ALIGN_POLICY.tie_up_before_left ? UP : LEFT, third = ALIGN_POLICY.tie_up_before_left ? LEFT : UP;
+                if (S[second][AT(i - 1, j - 1)] > best) { best = S[second][AT(i - 1, j - 1)]; dir = second; }
+                if (S[third][AT(i - 1, j - 1)] > best) { best = S[third][AT(i - 1, j - 1)]; dir = third; }
                 int s = best + addend;
                 if (mode == ORC_MODE_LOCAL && s < 0) { s = 0; dir = DONE; }
                 S[DIAG][AT(i, j)] = s; T[DIAG][AT(i, j)] = (unsigned char)dir;
@@ -449,21 +467,21 @@ static int align_impl(const orc_params *pa, int mode, const char *query, int n, 
             { /* Up (consumes a query base): open from Diagonal or extend Up; ties prefer Diagonal */
                 int best = S[DIAG][AT(i - 1, j)] + go + ge, dir = DIAG;
                 int ext = S[UP][AT(i - 1, j)] + ge;
-                if (ext > best) { best = ext; dir = UP; }
+                if (ext > best || (ALIGN_POLICY.extend_over_open && ext == best)) { best = ext; dir = UP; }
                 if (ALIGN_POLICY.up_from_left) { int x = S[LEFT][AT(i - 1, j)] + go + ge; if (x > best) { best = x; dir = LEFT; } }
                 S[UP][AT(i, j)] = best; T[UP][AT(i, j)] = (unsigned char)dir;
             }
             { /* Left (consumes a target base): open from Diagonal or extend Left; ties prefer Diagonal */
                 int best = S[DIAG][AT(i, j - 1)] + go + ge, dir = DIAG;
                 int ext = S[LEFT][AT(i, j - 1)] + ge;
-                if (ext > best) { best = ext; dir = LEFT; }
+                if (ext > best || (ALIGN_POLICY.extend_over_open && ext == best)) { best = ext; dir = LEFT; }
                 if (ALIGN_POLICY.left_from_up) { int x = S[UP][AT(i, j - 1)] + go + ge; if (x > best) { best = x; dir = UP; } }
                 S[LEFT][AT(i, j)] = best; T[LEFT][AT(i, j)] = (unsigned char)dir;
             }
         }
     }
     /* end cell: strict '>' scanning j (and i for Local) ascending, directions in (Diagonal, Left, Up) order */
-    static const int DIR_ORDER[3] = { DIAG, LEFT, UP };
+    const int DIR_ORDER[3] = { DIAG, ALIGN_POLICY.tie_up_before_left ? UP : LEFT, ALIGN_POLICY.tie_up_before_left ? LEFT : UP };
     int ci = n, cj = m, cd = DIAG, max_score = MIN_START_SCORE;
     if (mode == ORC_MODE_GLOBAL) {
         for (int k = 0; k < 3; ++k) { int d = DIR_ORDER[k]; if (S[d][AT(n, m)] > max_score) { max_score = S[d][AT(n, m)]; cd = d; } }

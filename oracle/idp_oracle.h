@@ -133,4 +133,7 @@ void orc_java_format_2f(double v, char *buf, int cap); /* Java f"%.2f" (PMa:115)
 #ifdef __cplusplus
 }
 #endif
+/* the unpinned alignment choices this build was compiled with (bit 0 left_from_up, 1 up_from_left, 2 extend_over_open, 3 tie_up_before_left) */
+int orc_align_policy_bits(void);
+
 #endif

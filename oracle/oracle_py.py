@@ -13,7 +13,9 @@ from typing import Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libidp_oracle.so")
+_LIB_PATH = os.environ.get("IDP_ORACLE_LIB") or os.path.join(_HERE, "libidp_oracle.so")  # override: the alternative-policy build
+ALT_POLICY_FLAGS = ["-DIDP_POLICY_LEFT_FROM_UP=1", "-DIDP_POLICY_UP_FROM_LEFT=1", "-DIDP_POLICY_EXTEND_OVER_OPEN=1", "-DIDP_POLICY_TIE_UP_BEFORE_LEFT=1"]
+ALT_LIB_PATH = os.path.join(_HERE, "libidp_oracle_altpolicy.so")
 
 NEXT_NA = 2147483647
 NONE, LOCATION, UNGAPPED, GAPPED = 0, 1, 2, 3
@@ -59,6 +61,15 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def build_alt_policy(force: bool = False) -> str:
+    """The oracle with every unpinned alignment choice flipped (idp_oracle.c, ALIGN_POLICY): tests/test_align_policy.py."""
+    src = os.path.join(_HERE, "idp_oracle.c")
+    if force or not os.path.exists(ALT_LIB_PATH) or os.path.getmtime(ALT_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "idp_oracle.h"))):
+        subprocess.check_call([os.environ.get("CC", "gcc"), "-O2", "-g", "-fPIC", "-std=gnu11", "-pthread", *ALT_POLICY_FLAGS, "-shared", "-o", ALT_LIB_PATH, src,
+                               "-lm", "-lpthread"])
+    return ALT_LIB_PATH
+
+
 def use_fast_build() -> str:
     """bench.py's reference arm / cpu_baseline only: switch this process to a -O3 -march=native build of the same source
     (BASELINE.md section 2), compiled on the machine that runs it (the file name carries a hash of the CPU's flags, so a
@@ -89,6 +100,7 @@ def lib() -> C.CDLL:
         if os.path.basename(_LIB_PATH) == "libidp_oracle.so":
             build()
         L = C.CDLL(_LIB_PATH)
+        L.orc_align_policy_bits.restype = C.c_int
         L.orc_panel_create.restype = C.c_void_p
         L.orc_panel_create.argtypes = [C.POINTER(OrcPrimer), C.c_int, C.POINTER(OrcParams)]
         L.orc_panel_destroy.argtypes = [C.c_void_p]
