@@ -80,7 +80,7 @@ struct idp_ctx {
     int device = 0;
     LaunchCfg cfg{};
     DevBuf b_fx, b_pm4, b_dfx, b_cinfo, b_cspan, b_qbot, b_bylen, b_pmask, b_pinfo, b_positive, b_loc_key[2], b_loc_primer[2], b_mate_off, b_mate_idx, b_smat;
-    DevBuf b_keys[2], b_offcnt[2], b_postings[2], b_heads[2], b_direct[2], b_dbits[2], b_bsmm, b_bsacc, b_seedtab, b_seedlist, b_diag;
+    DevBuf b_keys[2], b_offcnt[2], b_postings[2], b_heads[2], b_direct[2], b_dbits[2], b_dlohi, b_bloom, b_bsmm, b_bsacc, b_seedtab, b_seedlist, b_diag;
     Slot slots[kSlots];
     cudaStream_t user_stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_finish = nullptr;  // first copy / last harvest of an idp_match_batch call
@@ -123,7 +123,7 @@ static int upload_panel(idp_ctx *c) {
         k.k = h.k > 0 ? h.k : -1;
         k.window = p.max_primer_length;
         k.slot_mask = 0; k.shift = 63; k.keys = nullptr; k.off_cnt = nullptr; k.postings = nullptr;
-        k.heads = nullptr; k.direct = nullptr; k.direct_bits = nullptr; k.n_postings = 0;
+        k.heads = nullptr; k.direct = nullptr; k.direct_lohi = nullptr; k.direct_bits = nullptr; k.iupac_bloom = nullptr; k.n_iupac_kmers = 0; k.n_postings = 0;
         if (h.k > 0) {
             std::vector<OffCnt> oc(h.keys.size());
             for (size_t i = 0; i < oc.size(); ++i) oc[i] = OffCnt{h.off[i], h.cnt[i]};
@@ -139,11 +139,33 @@ static int upload_panel(idp_ctx *c) {
             if (!h.direct.empty()) {
                 if ((rc = upload(h.direct, c->b_direct[w]))) return rc;
                 k.direct = c->b_direct[w].as<uint32_t>();
-                if (h.k <= 10) {  // presence bits of the direct table, for cand5_thread_kernel's shared-memory prefilter
-                    std::vector<uint32_t> bits((h.direct.size() + 31) / 32, 0u);
-                    for (size_t i = 0; i < h.direct.size(); ++i) if (h.direct[i]) bits[i >> 5] |= 1u << (i & 31);
-                    if ((rc = upload(bits, c->b_dbits[w]))) return rc;
-                    k.direct_bits = c->b_dbits[w].as<uint32_t>();
+                if (h.k <= 10 && w == 1) {  // cand5_thread_kernel's copies: the table indexed by bit planes, its presence bits, the IUPAC Bloom filter
+                    const int kk = h.k;
+                    std::vector<uint32_t> lohi(h.direct.size(), 0u), bits((h.direct.size() + 31) / 32, 0u), bloom(2048, 0u);
+                    for (size_t i = 0; i < h.direct.size(); ++i) {
+                        if (!h.direct[i]) continue;
+                        uint32_t lo = 0, hi = 0;  // i holds the 2-bit codes, first base in the highest bits
+                        for (int j = 0; j < kk; ++j) { const uint32_t code = (uint32_t)(i >> (2 * (kk - 1 - j))) & 3u; lo |= (code & 1u) << j; hi |= (code >> 1) << j; }
+                        const uint32_t idx = (hi << kk) | lo;
+                        lohi[idx] = h.direct[i];
+                        bits[idx >> 5] |= 1u << (idx & 31);
+                    }
+                    uint32_t n_iupac = 0;
+                    for (uint64_t key : h.keys) {  // 4-bit codes, first base in the highest nibble; 0 = empty slot
+                        if (!key) continue;
+                        uint32_t lo = 0, hi = 0, bad = 0;
+                        for (int j = 0; j < kk; ++j) {
+                            const uint32_t nib = (uint32_t)(key >> (4 * (kk - 1 - j))) & 15u;
+                            lo |= plane_lo(nib) << j; hi |= plane_hi(nib) << j; bad |= (uint32_t)(__builtin_popcount(nib) != 1) << j;
+                        }
+                        if (!bad) continue;
+                        ++n_iupac;
+                        const uint32_t sig = kmer_plane_signature(lo, hi, bad, kk);
+                        bloom[sig >> 5] |= 1u << (sig & 31);
+                    }
+                    if ((rc = upload(lohi, c->b_dlohi)) || (rc = upload(bits, c->b_dbits[w])) || (rc = upload(bloom, c->b_bloom))) return rc;
+                    k.direct_lohi = c->b_dlohi.as<uint32_t>(); k.direct_bits = c->b_dbits[w].as<uint32_t>();
+                    k.iupac_bloom = c->b_bloom.as<uint32_t>(); k.n_iupac_kmers = n_iupac;
                 }
             }
         }
@@ -604,7 +626,7 @@ void idp_ctx_destroy(idp_ctx *c) {
     if (c->ev_finish) cudaEventDestroy(c->ev_finish);
     for (DevBuf *b : {&c->b_fx, &c->b_pm4, &c->b_dfx, &c->b_cinfo, &c->b_cspan, &c->b_qbot, &c->b_bylen, &c->b_pmask, &c->b_pinfo, &c->b_positive, &c->b_loc_key[0], &c->b_loc_key[1], &c->b_loc_primer[0], &c->b_loc_primer[1],
                       &c->b_mate_off, &c->b_mate_idx, &c->b_smat, &c->b_keys[0], &c->b_keys[1], &c->b_offcnt[0], &c->b_offcnt[1],
-                      &c->b_postings[0], &c->b_postings[1], &c->b_heads[0], &c->b_heads[1], &c->b_direct[0], &c->b_direct[1], &c->b_dbits[0], &c->b_dbits[1], &c->b_bsmm, &c->b_bsacc, &c->b_seedtab, &c->b_seedlist, &c->b_diag,
+                      &c->b_postings[0], &c->b_postings[1], &c->b_heads[0], &c->b_heads[1], &c->b_direct[0], &c->b_direct[1], &c->b_dbits[0], &c->b_dbits[1], &c->b_dlohi, &c->b_bloom, &c->b_bsmm, &c->b_bsacc, &c->b_seedtab, &c->b_seedlist, &c->b_diag,
                       &c->al_q, &c->al_ql, &c->al_t, &c->al_to, &c->al_tl, &c->al_tp, &c->al_out}) b->release();
     delete c;
 }

@@ -49,6 +49,18 @@ void set_error(const char *fmt, ...);
 __host__ __device__
 #endif
 inline uint32_t fx_hash(uint32_t w0, uint32_t w1, uint32_t mul, int shift) { return ((w0 * mul) ^ ((w1 & 0xFFFFu) * 0x85EBCA6Bu)) >> shift; }
+// Bloom slot (0..65535) of a k-mer given its bit planes (computed from ANY codes with the formulas of kmer_planes below) and
+// the k-bit mask of its positions that are not exactly one of A/C/G/T
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t kmer_plane_signature(uint32_t lo, uint32_t hi, uint32_t bad, int k) {
+    return ((((hi << k) | lo) * 0x9E3779B1u) ^ (bad * 0x85EBCA6Bu)) >> 16;
+}
+// one base's contribution to the planes: low bit = code bits 1 or 3 set, high bit = code bits 2 or 3 set (A/C/G/T = 1/2/4/8 -> 0..3)
+inline uint32_t plane_lo(uint32_t nib) { return ((nib >> 1) | (nib >> 3)) & 1u; }
+inline uint32_t plane_hi(uint32_t nib) { return ((nib >> 2) | (nib >> 3)) & 1u; }
+
 // bit of scan_fx_kernel's mismatch-flag word that stands for nibble `nibble` of window word `word` (idp_scanfx.cuh)
 inline int fx_where_bit(int word, int nibble) { return 4 * nibble + ((word & 1) << 1 | (word >> 1)); }
 
@@ -65,7 +77,15 @@ struct DevKmerIndex {
     const uint32_t *postings;  // primer indices in the iteration order of the reference's Set[Primer]
     const uint2 *heads;        // per posting {id | (accept+1) << 24, mask of the first 8 primer bases}
     const uint32_t *direct;    // NULL, or 4^k entries (2 bits per base, all-ACGT k-mers): posting offset | count << 20
-    const uint32_t *direct_bits;  // NULL, or 4^k bits: entry of `direct` is non-zero (k <= 10: the 128 KB map fits shared memory)
+    // cand5_thread_kernel's view of the same table (k <= 10), indexed by the k-mer's two BIT PLANES instead of its 2-bit codes:
+    // index = hi << k | lo, bit j of lo / hi = low / high bit of the code (A 0, C 1, G 2, T 3) of the k-mer's base j.  The planes
+    // of a whole read window are two 32-bit words, so a k-mer's index is two shifts, two ANDs and a shift-add.
+    const uint32_t *direct_lohi;  // NULL, or 4^k entries: posting offset | count << 20
+    const uint32_t *direct_bits;  // NULL, or 4^k presence bits of direct_lohi (128 KB for k = 10: fits shared memory)
+    // k-mers of the hashed table that hold a code other than A/C/G/T (IUPAC letters match literally, PM:113): a 64-Kbit Bloom filter
+    // on kmer_plane_signature(); n_iupac_kmers == 0 means a read k-mer holding such a code can never hit
+    const uint32_t *iupac_bloom;  // 2048 words, or NULL
+    uint32_t n_iupac_kmers;
     uint32_t n_postings;
 };
 

@@ -50,8 +50,10 @@ __global__ void __launch_bounds__(kCand5Threads) cand5_thread_kernel(DevPanel P,
         uint4 *dst = reinterpret_cast<uint4 *>(cand5_bm);
         for (unsigned i = threadIdx.x; i < bm_words / 4; i += blockDim.x) dst[i] = src[i];
         for (unsigned i = (bm_words & ~3u) + threadIdx.x; i < bm_words; i += blockDim.x) cand5_bm[i] = ix.direct_bits[i];
+        for (unsigned i = threadIdx.x; i < 2048u; i += blockDim.x) cand5_bm[bm_words + i] = ix.iupac_bloom[i];
         __syncthreads();
     }
+    const uint32_t *bloom = cand5_bm + bm_words;
     const int lane = threadIdx.x & 31;
     const uint64_t kmask = ix.k >= 16 ? ~0ull : ((1ull << (4 * ix.k)) - 1ull);
     const uint32_t kmask2 = ix.k >= 16 ? ~0u : ((1u << (2 * ix.k)) - 1u);
@@ -79,7 +81,6 @@ __global__ void __launch_bounds__(kCand5Threads) cand5_thread_kernel(DevPanel P,
                 OffCnt oc;
                 if (i < ix.k - 1) return true;
                 if (ix.direct != nullptr && bad == 0) {  // one load, no probing: the lanes of a warp stay together
-                    if (bm_words && !((cand5_bm[key2 >> 5] >> (key2 & 31u)) & 1u)) return true;
                     const uint32_t e = __ldg(&ix.direct[key2]);
                     if (!e) return true;
                     oc.off = e & 0xFFFFFu; oc.cnt = e >> 20;
@@ -97,7 +98,60 @@ __global__ void __launch_bounds__(kCand5Threads) cand5_thread_kernel(DevPanel P,
                 }
                 return true;
             };
-            if (n_bases <= 32) {
+            if (n_bases <= 32 && bm_words) {
+                // Bit planes of the window (DevKmerIndex::direct_lohi): lo / hi = the two bits of every base's A/C/G/T code, badv = the
+                // base is not exactly one of A/C/G/T (incl. the zero codes past the read's end).  A k-mer then costs two shifts, two
+                // ANDs and a shift-add for its table index, one AND for "all A/C/G/T", and one shared-memory bit test that
+                // answers most lookups (the fall-through reads are mostly off-target: their k-mers are not on the panel).
+                uint32_t sr[4];
+                window_from_global<4>(R, r, s, len, rc, sr);
+                uint32_t lo = 0, hi = 0, badv = 0;
+#pragma unroll
+                for (int w4 = 0; w4 < 4; ++w4) {
+                    const uint32_t x = sr[w4];
+                    const uint32_t c2 = (x & 0x55555555u) + ((x >> 1) & 0x55555555u);
+                    const uint32_t d4 = (c2 & 0x33333333u) + ((c2 >> 2) & 0x33333333u);  // bits set per nibble
+                    lo |= gather_nibble_bits(((x >> 1) | (x >> 3)) & 0x11111111u) << (8 * w4);
+                    hi |= gather_nibble_bits(((x >> 2) | (x >> 3)) & 0x11111111u) << (8 * w4);
+                    badv |= gather_nibble_bits(nib_nonzero(d4 ^ 0x11111111u)) << (8 * w4);
+                }
+                const uint32_t km = (1u << ix.k) - 1u;
+                for (int p0 = 0; p0 + ix.k <= n_bases; ++p0) {  // k-mers in read order (PM:110-113)
+                    const uint32_t l = (lo >> p0) & km, h = (hi >> p0) & km, bad = (badv >> p0) & km;
+                    OffCnt oc;
+                    if (bad == 0u) {
+                        const uint32_t idx = (h << ix.k) | l;
+                        if (!((cand5_bm[idx >> 5] >> (idx & 31u)) & 1u)) continue;
+                        const uint32_t e = __ldg(&ix.direct_lohi[idx]);
+                        oc.off = e & 0xFFFFFu; oc.cnt = e >> 20;
+                    } else {
+                        // a k-mer holding another code can only equal a primer k-mer that spells the same code (PM:113)
+                        if (ix.n_iupac_kmers == 0u) continue;
+                        const uint32_t sig = kmer_plane_signature(l, h, bad, ix.k);
+                        if (!((bloom[sig >> 5] >> (sig & 31u)) & 1u)) continue;
+                        uint64_t key = 0;  // rare: spell the k-mer out, first base in the highest nibble
+                        for (int j = 0; j < ix.k; ++j) {
+                            const int b = p0 + j;
+                            const uint32_t word = b < 8 ? sr[0] : b < 16 ? sr[1] : b < 24 ? sr[2] : sr[3];
+                            key = (key << 4) | ((word >> (4 * (b & 7))) & 15u);
+                        }
+                        if (!kmer_lookup(ix, key, oc)) continue;
+                    }
+                    bool full = false;
+                    for (uint32_t j = 0; j < oc.cnt; ++j) {
+                        const int p = (int)__ldg(&ix.postings[oc.off + j]);
+                        bool seen = false;
+#pragma unroll
+                        for (int t = 0; t < kCandLocal; ++t) seen |= (t < nc && cand[t] == p);
+                        if (seen) continue;
+                        if (nc == kCandLocal) { full = true; break; }
+#pragma unroll
+                        for (int t = 0; t < kCandLocal; ++t) if (t == nc) cand[t] = p;
+                        ++nc;
+                    }
+                    if (full) { spilled = true; break; }
+                }
+            } else if (n_bases <= 32) {
                 // a window of at most 32 bases comes in as a 4-word shift register (base i in nibble i: the word loaders of the
                 // scan kernel, forward or reverse complement), so a base costs a handful of register operations instead of a byte fetch
                 uint32_t sr[4];
