@@ -294,7 +294,11 @@ def main():
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     dev = torch.device("cuda", local)
-    stream = torch.cuda.current_stream()
+    # a stream of our own: torch's default current stream is the legacy NULL stream, and NULL means "the context's own stream" to
+    # idp_ctx_set_stream -- the events below must sit on the stream the kernels are enqueued on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -388,16 +392,26 @@ def main():
         loc = b.d_loc
         acc = np.zeros(161, dtype=np.int64)
 
-        def step_resident(compact=True, seq=d_seq, flen=fixed_len, five=d_five, three=d_three):
-            m, na = tool.process_batch_device(n_reads, seq.data_ptr(), b.d_flags.data_ptr(), five.data_ptr(), three.data_ptr() if three is not None else 0,
-                                              fixed_len=flen, ref_idx_ptr=loc[0].data_ptr() if loc else 0, ustart_ptr=loc[1].data_ptr() if loc else 0,
-                                              uend_ptr=loc[2].data_ptr() if loc else 0, compact=compact)
-            acc[:160] += m; acc[160] += na
-            return tool.timings()
+        # device-resident legs run in the library's asynchronous mode: batches are enqueued back to back on torch's current stream
+        # and the counters are collected once after the timed loop (idp_ctx_set_async / idp_ctx_sync)
+        tool.set_async(True)
 
-        ms_res, tm_res = timed(step_resident, True, steps, warmup)
-        acc[:] = 0
-        ms_res, tm_res = timed(step_resident, True, steps, 0)   # counters of exactly `steps` steps
+        def step_resident(compact=True, seq=d_seq, flen=fixed_len, five=d_five, three=d_three):
+            tool.process_batch_device(n_reads, seq.data_ptr(), b.d_flags.data_ptr(), five.data_ptr(), three.data_ptr() if three is not None else 0,
+                                      fixed_len=flen, ref_idx_ptr=loc[0].data_ptr() if loc else 0, ustart_ptr=loc[1].data_ptr() if loc else 0,
+                                      uend_ptr=loc[2].data_ptr() if loc else 0, compact=compact)
+
+        def timed_resident(fn):
+            for _ in range(warmup):
+                fn()
+            tool.sync()
+            ms, _ = timed(fn, True, steps, 0)
+            m, na = tool.sync()   # counters of exactly `steps` steps
+            return ms, m, na, tool.timings()
+
+        ms_res, m_res, na_res, tm_last = timed_resident(step_resident)
+        acc[:160] = m_res; acc[160] = na_res
+        tm_res = [tm_last]
         totals[name] = acc.copy()
         # parity spot check of what was just timed (the checker, not the thing measured): first pairs against the oracle
         torch.cuda.synchronize()
@@ -417,6 +431,7 @@ def main():
             except Exception as e:  # pragma: no cover
                 parity = f"check failed to run: {e}"
 
+        tool.set_async(False)
         # ---- end to end: pinned host buffers through the C-ABI, copies inside the timed region ----
         h_seq, h_flags = pinned(d_seq), pinned(b.d_flags)
         h_loc = [pinned(t) for t in loc] if loc else None
@@ -442,7 +457,7 @@ def main():
 
         scan_ms = statistics.mean(t["ms_scan"] for t in tm_res)
         stages = {k: statistics.mean(t[k] for t in tm_res) for k in ("ms_total", "ms_scan", "ms_gapped", "ms_three_prime", "ms_sw_score")}
-        work = {k: int(tm_res[-1][k]) for k in ("n_fallthrough", "n_alignments_5p", "n_alignments_3p", "sw_cells", "n_scan_parked")}
+        work = {k: int(tm_res[-1][k]) // steps for k in ("n_fallthrough", "n_alignments_5p", "n_alignments_3p", "sw_cells", "n_scan_parked")}  # per step
         shipped = 2 * ((fixed_len + 1) // 2 + 2 + 16 * (2 if do3 else 1) + 1 + (12 if loc else 0))
         out = {
             "workload": workload_desc(name, n_pairs) + " (per GPU)",
@@ -452,6 +467,7 @@ def main():
                     "h2d_bytes_per_step": int(tm_e2e[-1]["h2d_bytes"]), "d2h_bytes_per_step": int(tm_e2e[-1]["d2h_bytes"]),
                     "same_bytes_as_resident_run": same},
             "stages_ms": stages, "work": work, "gpu_launches_per_step": int(tm_res[-1]["kernel_launches"]),
+            "resident_mode": "asynchronous: the steps are enqueued back to back (idp_ctx_set_async), counters collected once by idp_ctx_sync after the timed loop",
             "parity_spot_check_vs_oracle": parity, "generator_seconds": round(b.gen_seconds, 1),
             "roofline": {"bound": "hbm", "kernel": "scan stage = scan_fx_kernel (exact-prefix table + mismatchAlign + k-mer rule) + compact_mask_kernel + scan_kernel over the parked reads (location, bit-sliced filter / seed index / exact walk) + compact_mask_kernel",
                          "achieved": ALGO_BYTES_PER_PAIR * n_pairs / (scan_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
@@ -473,7 +489,10 @@ def main():
         if whole_legs and not do3:
             # the round-1 layout for comparison: 75 B rows in, 32-byte records out
             d5w = torch.empty((n_reads, 32), dtype=torch.uint8, device=dev)
-            ms_w, tm_w = timed(lambda: step_resident(False, b.d_whole, READ_LEN, d5w, None), True, steps, warmup)
+            tool.set_async(True)
+            ms_w, _, _, tw_last = timed_resident(lambda: step_resident(False, b.d_whole, READ_LEN, d5w, None))
+            tool.set_async(False)
+            tm_w = [tw_last]
             ok = bool(np.array_equal(L.unpack16(d_five[:200000].cpu().numpy().view(L.RESULT16_DTYPE).reshape(-1)).view(np.uint8),
                                      d5w[:200000].cpu().numpy().reshape(-1)))
             sw = statistics.mean(t["ms_scan"] for t in tm_w)
@@ -534,7 +553,7 @@ def main():
                    "l2": f"inputs + outputs {head['roofline']['bytes_per_pair_this_layout'] * args.pairs / 1e9:.2f} GB per step exceed the 126 MB L2, no flush needed",
                    "generator": "synth-v1 distributions drawn on the GPU (fg_idprimer_b200/synth_gpu.py)", "generator_seconds": head["generator_seconds"]},
         "e2e": head["e2e"],
-        "gpu_launches": int(sum(t["kernel_launches"] for t in tm_head)),
+        "gpu_launches": int(tm_head[-1]["kernel_launches"]) * args.steps,
         "roofline": dict(head["roofline"], traffic=None),
         "clocks": clocks,
         "stages_ms": head["stages_ms"], "work": head["work"],

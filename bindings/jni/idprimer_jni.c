@@ -74,6 +74,8 @@ JNIEXPORT jlong JNICALL GPM(ctxCreate)(JNIEnv *env, jclass c, jlong panel, jint 
 }
 JNIEXPORT void JNICALL GPM(ctxDestroy)(JNIEnv *env, jclass c, jlong h) { idp_ctx_destroy(PTR(idp_ctx, h)); }
 JNIEXPORT void JNICALL GPM(ctxSetStream)(JNIEnv *env, jclass c, jlong h, jlong cudaStream) { check(env, idp_ctx_set_stream(PTR(idp_ctx, h), PTR(void, cudaStream))); }
+JNIEXPORT void JNICALL GPM(ctxSetAsync)(JNIEnv *env, jclass c, jlong h, jint enable) { check(env, idp_ctx_set_async(PTR(idp_ctx, h), enable)); }
+JNIEXPORT void JNICALL GPM(ctxSync)(JNIEnv *env, jclass c, jlong h, jobject metrics, jobject nAligned) { check(env, idp_ctx_sync(PTR(idp_ctx, h), (int64_t *)ADDR(metrics), (int64_t *)ADDR(nAligned))); }
 JNIEXPORT void JNICALL GPM(ctxTimings)(JNIEnv *env, jclass c, jlong h, jobject out /* idp_timings */) { check(env, idp_ctx_timings(PTR(const idp_ctx, h), (idp_timings *)ADDR(out))); }
 /* clsPerRead: a direct buffer for matchBatch / matchBatch16 (or null); use ctxSetClassifyDevice for the *_device calls */
 JNIEXPORT void JNICALL GPM(ctxSetClassify)(JNIEnv *env, jclass c, jlong h, jint minInsert, jint maxInsert, jobject clsPerRead, jobject counts6) {

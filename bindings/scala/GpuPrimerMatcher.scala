@@ -33,6 +33,8 @@ private[identifyprimers] object GpuPrimerMatcher {
     @native def ctxCreate(panel: Long, device: Int): Long
     @native def ctxDestroy(h: Long): Unit
     @native def ctxSetStream(h: Long, cudaStream: Long): Unit
+    @native def ctxSetAsync(h: Long, enable: Int): Unit
+    @native def ctxSync(h: Long, metrics160: ByteBuffer, nAligned: ByteBuffer): Unit
     @native def ctxTimings(h: Long, out: ByteBuffer): Unit
     @native def ctxSetClassify(h: Long, minInsert: Int, maxInsert: Int, clsPerRead: ByteBuffer, counts6: ByteBuffer): Unit
     @native def ctxSetClassifyDevice(h: Long, minInsert: Int, maxInsert: Int, clsPerRead: Long, counts6: ByteBuffer): Unit

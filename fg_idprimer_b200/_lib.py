@@ -19,7 +19,7 @@ MODE_LOCAL, MODE_GLOCAL, MODE_GLOBAL = 0, 1, 3
 # every symbol include/idprimer.h declares
 EXPORTS = ["idp_abi_version", "idp_last_error", "idp_device_count", "idp_align_policy", "idp_panel_create", "idp_panel_destroy", "idp_panel_size",
            "idp_panel_primer_length", "idp_panel_primer_hash", "idp_panel_kmer_postings", "idp_ctx_create", "idp_ctx_destroy",
-           "idp_ctx_set_stream", "idp_ctx_timings", "idp_host_alloc", "idp_host_free", "idp_match_batch", "idp_match_batch_device",
+           "idp_ctx_set_stream", "idp_ctx_timings", "idp_ctx_set_async", "idp_ctx_sync", "idp_host_alloc", "idp_host_free", "idp_match_batch", "idp_match_batch_device",
            "idp_match_batch16", "idp_match_batch16_device", "idp_result16_unpack", "idp_align_batch", "idp_result_score", "idp_result_second", "idp_metric_bin", "idp_summary_metrics", "idp_format_info",
            "idp_pack_bases", "idp_unpack_bases", "idp_classify_primer_pair", "idp_classify_templates", "idp_classify_batch_device", "idp_ctx_set_classify", "idp_bam_scan", "idp_bam_to_batch", "idp_bam_to_batch_window", "idp_panel_window",
            "idp_bam_annotate", "idp_header_comments"]
@@ -97,6 +97,8 @@ def lib() -> C.CDLL:
     L.idp_ctx_destroy.argtypes = [C.c_void_p]
     L.idp_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.idp_ctx_timings.argtypes = [C.c_void_p, C.POINTER(IdpTimings)]
+    L.idp_ctx_set_async.argtypes = [C.c_void_p, C.c_int]
+    L.idp_ctx_sync.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.idp_host_alloc.argtypes = [C.c_size_t]
     L.idp_host_alloc.restype = C.c_void_p
     L.idp_host_free.argtypes = [C.c_void_p]

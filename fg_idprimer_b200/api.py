@@ -380,6 +380,21 @@ class IdentifyPrimers:
         self.num_alignments += int(n_align[0])
         return metrics, int(n_align[0])
 
+    def set_async(self, enable: bool = True):
+        """Asynchronous device-resident mode (idp_ctx_set_async): process_batch_device only enqueues; sync() collects the counters."""
+        self._require_ctx()
+        L.check(L.lib().idp_ctx_set_async(self._ctx, 1 if enable else 0))
+
+    def sync(self):
+        """idp_ctx_sync: waits for the enqueued batches, adds their counters to metric_counter / num_alignments, returns them."""
+        self._require_ctx()
+        metrics = np.zeros(160, dtype=np.int64)
+        n_align = np.zeros(1, dtype=np.int64)
+        L.check(L.lib().idp_ctx_sync(self._ctx, metrics.ctypes.data, n_align.ctypes.data))
+        self.metric_counter += metrics
+        self.num_alignments += int(n_align[0])
+        return metrics, int(n_align[0])
+
     def set_stream(self, cuda_stream_ptr: int):
         L.check(L.lib().idp_ctx_set_stream(self._ctx, cuda_stream_ptr or None))
 

@@ -35,10 +35,13 @@ bool parse(const uint8_t *bam, size_t n_bytes, size_t &off, BamRec &r) {
     r.l_read_name = p[8];
     r.n_cigar = rd16(p + 12); r.flag = rd16(p + 14);
     r.l_seq = rd32(p + 16); r.next_ref_id = rd32(p + 20); r.next_pos = rd32(p + 24); r.tlen = rd32(p + 28);
+    if (r.l_seq < 0) return false;
+    // name, CIGAR, packed bases AND the l_seq quality bytes must all lie inside the record (idp_bam_annotate copies up to the aux fields)
+    const size_t fixed = 32 + (size_t)r.l_read_name + 4 * (size_t)r.n_cigar;
+    if (fixed > (size_t)r.block_size || fixed + (size_t)((r.l_seq + 1) / 2) + (size_t)r.l_seq > (size_t)r.block_size) return false;
     r.name = reinterpret_cast<const char *>(p + 32);
     r.cigar = p + 32 + r.l_read_name;
     r.seq = r.cigar + 4 * (size_t)r.n_cigar;
-    if ((size_t)(r.seq - p) + (size_t)((r.l_seq + 1) / 2) > (size_t)r.block_size || r.l_seq < 0) return false;
     off += 4 + (size_t)r.block_size;
     return true;
 }

@@ -86,6 +86,9 @@ struct idp_ctx {
     cudaEvent_t ev_begin = nullptr, ev_finish = nullptr;  // first copy / last harvest of an idp_match_batch call
     idp_timings last{};
     bool compact_ok = false;  // every value of this panel's results fits idp_result16
+    // asynchronous device-resident mode (idp_ctx_set_async): batches are enqueued back to back, counters accumulate on the device
+    bool async_on = false;
+    int async_pending = 0;
     // classification epilogue (idp_ctx_set_classify)
     bool cls_on = false;
     int32_t cls_min = 0, cls_max = 0;
@@ -310,7 +313,9 @@ static int upload_panel(idp_ctx *c) {
 
 // Enqueue the whole matcher chain for reads already on the device.  Nothing here waits on the host.
 // five / three: where the per-read records go, in either format (ResultOut).
-static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R, ResultOut five, ResultOut three, uint8_t *cls_dev) {
+// keep_totals: only the per-batch scratch counters are cleared, the metric / alignment / class totals keep accumulating
+static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R, ResultOut five, ResultOut three, uint8_t *cls_dev,
+                         bool keep_totals = false) {
     const idp_panel &p = *c->panel;
     const LaunchCfg &cfg = c->cfg;
     const size_t n = (size_t)R.n;
@@ -330,7 +335,8 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
     unsigned *fall = s.fall.as<unsigned>();
     uint8_t *rtype = s.rtype.as<uint8_t>();
     s.launches = 0;
-    CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(Counters), st));
+    CUDA_TRY(cudaMemsetAsync(ctr, 0, keep_totals ? offsetof(Counters, overflow) : sizeof(Counters), st));  // n_fall, n_parked, n_pairs, n_all (overflow is sticky)
+    if (keep_totals) CUDA_TRY(cudaMemsetAsync(&ctr->n_spill, 0, sizeof(unsigned), st));
     CUDA_TRY(cudaEventRecord(s.ev[EV_START], st));
     if (n > 0) {
         if ((rc = launch_scan(cfg, st, R, five, rtype, fall, s.parked.as<unsigned>(), s.masks.as<uint32_t>(), ctr, &s.launches))) return rc;
@@ -432,6 +438,13 @@ static int match_batch_device(idp_ctx *c, const idp_reads *reads, int32_t n_read
     cudaStream_t st = c->user_stream ? c->user_stream : s.stream;
     DevReads R{reads->seq4, reads->seq_off, reads->len, reads->ref_idx, reads->unclipped_start, reads->unclipped_end, reads->flags, reads->fixed_len, n_reads};
     c->last = idp_timings{};
+    if (c->async_on) {  // enqueue and return: idp_ctx_sync() collects the counters of everything enqueued since the last one
+        if (c->async_pending == 0) CUDA_TRY(cudaMemsetAsync(s.d_ctr, 0, sizeof(Counters), st));
+        if ((rc = enqueue_chain(c, s, st, R, ResultOut{five, compact}, ResultOut{three, compact}, c->cls_user, true))) { cudaStreamSynchronize(st); cudaGetLastError(); c->async_pending = 0; return rc; }
+        ++c->async_pending;
+        c->last.n_reads = n_reads;
+        return IDP_OK;
+    }
     for (int attempt = 0;; ++attempt) {
         if ((rc = enqueue_chain(c, s, st, R, ResultOut{five, compact}, ResultOut{three, compact}, c->cls_user))) { cudaStreamSynchronize(st); cudaGetLastError(); return rc; }
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -661,6 +674,37 @@ int idp_match_batch16(idp_ctx *c, const idp_reads *reads, int32_t n_reads, idp_r
 }
 
 int idp_align_policy(void) { return AlignPolicy::kBits; }
+
+int idp_ctx_set_async(idp_ctx *c, int enable) {
+    if (!c) { set_error("idp_ctx_set_async: NULL context"); return IDP_ERR_ARG; }
+    if (c->async_pending) { set_error("idp_ctx_set_async: batches are pending; call idp_ctx_sync first"); return IDP_ERR_ARG; }
+    c->async_on = enable != 0;
+    return IDP_OK;
+}
+
+int idp_ctx_sync(idp_ctx *c, int64_t *metrics160, int64_t *n_gapped_alignments) {
+    if (!c) { set_error("idp_ctx_sync: NULL context"); return IDP_ERR_ARG; }
+    if (c->async_pending == 0) return IDP_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    Slot &s = c->slots[0];
+    cudaStream_t st = c->user_stream ? c->user_stream : s.stream;
+    c->async_pending = 0;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    if (s.h_ctr->overflow) {
+        s.pair_cap *= 4;  // the next batches get more room
+        set_error("a batch listed more -K candidates than the pair buffer holds (asynchronous mode cannot redo it): rerun the batches since the last idp_ctx_sync");
+        return IDP_ERR_NOMEM;
+    }
+    c->last = idp_timings{};
+    add_timings(c, s, true);  // stage times of the last batch; the work counters cover every batch since the last sync
+    float ms = 0; cudaEventElapsedTime(&ms, s.ev[EV_START], s.ev[EV_END]);
+    c->last.ms_total = ms;
+    if (metrics160) for (int i = 0; i < 160; ++i) metrics160[i] += (int64_t)s.h_ctr->metrics[i];
+    if (n_gapped_alignments) *n_gapped_alignments += (int64_t)s.h_ctr->n_align5;
+    if (c->cls_on && c->cls_counts) for (int i = 0; i < 6; ++i) c->cls_counts[i] += (int64_t)s.h_ctr->classes[i];
+    return IDP_OK;
+}
 
 int idp_ctx_set_classify(idp_ctx *c, int32_t min_insert_length, int32_t max_insert_length, uint8_t *cls_per_read, int64_t *counts6) {
     if (!c) { set_error("idp_ctx_set_classify: NULL context"); return IDP_ERR_ARG; }

@@ -1301,6 +1301,7 @@ __global__ void __launch_bounds__(128) finalize_pairs_kernel(DevPanel P, DevRead
     for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
         const int cnt = seg_cnt[w];
         if (cnt < 0) continue;  // -1: did not fit (reported through Counters::overflow); -2: handled by the all-primers path
+        if (cnt == 0 && !three_prime) continue;  // no candidate: the scan already wrote this read's "no match" record (most fall-through reads are off-target)
         const int r = work_read ? (int)work_read[w] : (int)w;
         Fin f;
         f.count = cnt; f.primer = -1; f.raw = 0; f.raw_next = 0; f.qlen = 0; f.qlen_next = 0;

@@ -199,6 +199,16 @@ int idp_match_batch(idp_ctx *ctx, const idp_reads *reads, int32_t n_reads, idp_r
 int idp_match_batch_device(idp_ctx *ctx, const idp_reads *reads, int32_t n_reads, idp_result *five, idp_result *three,
                            int64_t *metrics160, int64_t *n_gapped_alignments);
 
+/* Asynchronous device-resident mode.  After idp_ctx_set_async(ctx, 1) the two *_device calls only ENQUEUE the batch on the
+ * context's stream (idp_ctx_set_stream) and return; their metrics160 / n_gapped_alignments arguments are ignored.  Batches run
+ * back to back without a host round trip in between and their counters accumulate on the device; idp_ctx_sync() waits for
+ * everything enqueued since the last sync and ADDS the accumulated counters to its arguments (either may be NULL).  Input and
+ * output arrays of a batch must stay valid until then.  If a batch lists more -K candidates than the pair buffer holds (the
+ * synchronous calls redo such a batch themselves), idp_ctx_sync returns IDP_ERR_NOMEM and enlarges the buffer: rerun the batches
+ * enqueued since the last sync.  idp_ctx_timings then reports the stage times of the last batch and the work counters of all. */
+int idp_ctx_set_async(idp_ctx *ctx, int enable);
+int idp_ctx_sync(idp_ctx *ctx, int64_t *metrics160, int64_t *n_gapped_alignments);
+
 /* The same two calls writing 16-byte records (idp_result16).  This is what a caller that ships windowed batches
  * (idp_bam_to_batch_window) should use: 18 B of bases + 2 B of flags in and 16 B out per 150 bp read instead of 77 B in and
  * 32 B out.  IDP_ERR_UNSUPPORTED when the panel's scores or size do not fit the record (|alignment score| >= 32767 possible,

@@ -106,6 +106,19 @@ def test_bam_packer_rejects_malformed_input():
     good = bam_record("q", 0x4, -1, 0, [], "ACGT")
     with pytest.raises(idp.IdpError):
         idp.ReadBatch.from_bam(good[:-3])
+    import struct
+    body = bytearray(good[4:])
+    # a record whose l_seq says more bases + qualities than block_size holds (the packed bases alone would still fit), and one
+    # whose name + CIGAR already overrun it: both are rejected before anything is read past the record
+    long_seq = bytearray(body); struct.pack_into("<i", long_seq, 16, 10)
+    with pytest.raises(idp.IdpError):
+        idp.ReadBatch.from_bam(struct.pack("<i", len(long_seq)) + bytes(long_seq))
+    many_ops = bytearray(body); struct.pack_into("<H", many_ops, 12, 4000)
+    with pytest.raises(idp.IdpError):
+        idp.ReadBatch.from_bam(struct.pack("<i", len(many_ops)) + bytes(many_ops))
+    neg = bytearray(body); struct.pack_into("<i", neg, 16, -5)
+    with pytest.raises(idp.IdpError):
+        idp.ReadBatch.from_bam(struct.pack("<i", len(neg)) + bytes(neg))
     two_r1 = bam_record("q", 0x1 | 0x40 | 0x4, -1, 0, [], "ACGT") * 2
     with pytest.raises(idp.IdpError):
         idp.ReadBatch.from_bam(two_r1)

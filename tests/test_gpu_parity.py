@@ -675,3 +675,34 @@ def test_classification_epilogue_inside_process_batch(name, compact):
         assert np.array_equal(tool.last_classes, want_cls)
         assert dict(zip(tool.CLASS_NAMES, tool.class_counts.tolist())) == want_counts
         assert want_counts["Canonical"] > 1000
+
+
+def test_asynchronous_device_mode_accumulates_counters():
+    """idp_ctx_set_async / idp_ctx_sync: batches enqueued back to back give the same records, and the counters of all of them at the sync."""
+    import torch
+    panel, reads, opts = synth.workload("c5", 2000)
+    arr = reads.oracle_arrays()
+    want5, want3, want_metrics, want_align = O.Panel(_synth_primers(panel), _opts_to_oracle(opts)).process_batch(arr, n_threads=4)
+    dev = torch.device("cuda", 0)
+    s4 = torch.from_numpy(reads.seq4()).to(dev)
+    fl = torch.from_numpy(reads.flags.view(np.int16)).to(dev)
+    loc = [torch.from_numpy(a).to(dev) for a in (reads.ref_idx, reads.ustart, reads.uend)]
+    outs = [(torch.zeros((reads.n, 16), dtype=torch.uint8, device=dev), torch.zeros((reads.n, 16), dtype=torch.uint8, device=dev)) for _ in range(3)]
+    with idp.IdentifyPrimers(panel.primers, ref_names=panel.ref_names, **opts) as tool:
+        tool.set_stream(torch.cuda.current_stream().cuda_stream)
+        tool.set_async(True)
+        for f5, f3 in outs:
+            m, na = tool.process_batch_device(reads.n, s4.data_ptr(), fl.data_ptr(), f5.data_ptr(), f3.data_ptr(), fixed_len=150, ref_idx_ptr=loc[0].data_ptr(),
+                                              ustart_ptr=loc[1].data_ptr(), uend_ptr=loc[2].data_ptr(), compact=True)
+            assert not m.any() and na == 0   # nothing is reported before the sync
+        metrics, n_align = tool.sync()
+        assert np.array_equal(metrics, 3 * want_metrics) and n_align == 3 * want_align
+        assert np.array_equal(tool.metric_counter, 3 * want_metrics)
+        for f5, f3 in outs:
+            assert_same(L.unpack16(f5.cpu().numpy().view(L.RESULT16_DTYPE).reshape(-1)), want5, "async 5'")
+            assert_same(L.unpack16(f3.cpu().numpy().view(L.RESULT16_DTYPE).reshape(-1)), want3, "async 3'")
+        assert not tool.sync()[0].any()   # nothing pending: a no-op
+        tool.set_async(False)
+        m, na = tool.process_batch_device(reads.n, s4.data_ptr(), fl.data_ptr(), outs[0][0].data_ptr(), outs[0][1].data_ptr(), fixed_len=150,
+                                          ref_idx_ptr=loc[0].data_ptr(), ustart_ptr=loc[1].data_ptr(), uend_ptr=loc[2].data_ptr(), compact=True)
+        assert np.array_equal(m, want_metrics) and na == want_align
