@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libidprimer_b200.so")
 SOURCES = ["idp_panel.cpp", "idp_bam.cpp", "idp_ctx.cu", "idp_scan.cu", "idp_sw.cu"]
-HEADERS = ["idp_internal.h", "idp_device.cuh", "idp_launch.h", "idp_kernels.cuh", "idp_scan.cuh", os.path.join("..", "..", "include", "idprimer.h")]
+HEADERS = ["idp_internal.h", "idp_device.cuh", "idp_launch.h", "idp_kernels.cuh", "idp_scan.cuh", "idp_scanfx.cuh", os.path.join("..", "..", "include", "idprimer.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -145,6 +145,7 @@ static int upload_panel(idp_ctx *c) {
                 if (h.k <= 10 && w == 1) {  // cand5_thread_kernel's copies: the table indexed by bit planes, its presence bits, the IUPAC Bloom filter
                     const int kk = h.k;
                     std::vector<uint32_t> lohi(h.direct.size(), 0u), bits((h.direct.size() + 31) / 32, 0u), bloom(2048, 0u);
+                    bool inline_ok = true;  // no ordinary entry has bit 31 set (counts below 2048)
                     for (size_t i = 0; i < h.direct.size(); ++i) {
                         if (!h.direct[i]) continue;
                         uint32_t lo = 0, hi = 0;  // i holds the 2-bit codes, first base in the highest bits
@@ -152,7 +153,11 @@ static int upload_panel(idp_ctx *c) {
                         const uint32_t idx = (hi << kk) | lo;
                         lohi[idx] = h.direct[i];
                         bits[idx >> 5] |= 1u << (idx & 31);
+                        inline_ok = inline_ok && !(h.direct[i] & 0x80000000u);
                     }
+                    if (inline_ok)  // a k-mer with one primer carries it in the entry: one dependent load less per hit
+                        for (uint32_t &e : lohi)
+                            if ((e >> 20) == 1u) { const uint32_t pr = h.postings[e & 0xFFFFFu]; if (!(pr & 0x80000000u)) e = 0x80000000u | pr; }
                     uint32_t n_iupac = 0;
                     for (uint64_t key : h.keys) {  // 4-bit codes, first base in the highest nibble; 0 = empty slot
                         if (!key) continue;

@@ -80,7 +80,7 @@ struct DevKmerIndex {
     // cand5_thread_kernel's view of the same table (k <= 10), indexed by the k-mer's two BIT PLANES instead of its 2-bit codes:
     // index = hi << k | lo, bit j of lo / hi = low / high bit of the code (A 0, C 1, G 2, T 3) of the k-mer's base j.  The planes
     // of a whole read window are two 32-bit words, so a k-mer's index is two shifts, two ANDs and a shift-add.
-    const uint32_t *direct_lohi;  // NULL, or 4^k entries: posting offset | count << 20
+    const uint32_t *direct_lohi;  // NULL, or 4^k entries: posting offset | count << 20, or 0x80000000 | primer when the k-mer has one primer
     const uint32_t *direct_bits;  // NULL, or 4^k presence bits of direct_lohi (128 KB for k = 10: fits shared memory)
     // k-mers of the hashed table that hold a code other than A/C/G/T (IUPAC letters match literally, PM:113): a 64-Kbit Bloom filter
     // on kmer_plane_signature(); n_iupac_kmers == 0 means a read k-mer holding such a code can never hit

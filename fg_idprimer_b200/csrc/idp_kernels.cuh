@@ -116,33 +116,57 @@ __global__ void __launch_bounds__(kCand5Threads) cand5_thread_kernel(DevPanel P,
                     badv |= gather_nibble_bits(nib_nonzero(d4 ^ 0x11111111u)) << (8 * w4);
                 }
                 const uint32_t km = (1u << ix.k) - 1u;
-                for (int p0 = 0; p0 + ix.k <= n_bases; ++p0) {  // k-mers in read order (PM:110-113)
+                // pass 1, registers and shared memory only: which k-mer positions can hit at all
+                uint32_t hits = 0u;
+                for (int p0 = 0; p0 + ix.k <= n_bases; ++p0) {
                     const uint32_t l = (lo >> p0) & km, h = (hi >> p0) & km, bad = (badv >> p0) & km;
-                    OffCnt oc;
+                    bool hit;
                     if (bad == 0u) {
                         const uint32_t idx = (h << ix.k) | l;
-                        if (!((cand5_bm[idx >> 5] >> (idx & 31u)) & 1u)) continue;
-                        const uint32_t e = __ldg(&ix.direct_lohi[idx]);
-                        oc.off = e & 0xFFFFFu; oc.cnt = e >> 20;
+                        hit = ((cand5_bm[idx >> 5] >> (idx & 31u)) & 1u) != 0u;
+                    } else if (ix.n_iupac_kmers == 0u) {
+                        hit = false;  // a k-mer holding another code can only equal a primer k-mer that spells the same code (PM:113)
                     } else {
-                        // a k-mer holding another code can only equal a primer k-mer that spells the same code (PM:113)
-                        if (ix.n_iupac_kmers == 0u) continue;
                         const uint32_t sig = kmer_plane_signature(l, h, bad, ix.k);
-                        if (!((bloom[sig >> 5] >> (sig & 31u)) & 1u)) continue;
+                        hit = ((bloom[sig >> 5] >> (sig & 31u)) & 1u) != 0u;
+                    }
+                    hits |= (uint32_t)hit << p0;
+                }
+                // pass 2: the hits in read order (PM:110-113); the table entry of the next hit is requested while this one is walked
+                auto entry_of = [&](int p0) -> uint32_t {  // all-A/C/G/T k-mers only; 0 for the others (they take the hashed table)
+                    const uint32_t l = (lo >> p0) & km, h = (hi >> p0) & km, bad = (badv >> p0) & km;
+                    return bad == 0u ? __ldg(&ix.direct_lohi[(h << ix.k) | l]) : 0u;
+                };
+                int last_p = -1;
+                uint32_t e_next = hits ? entry_of(__ffs((int)hits) - 1) : 0u;
+                while (hits) {
+                    const int p0 = __ffs((int)hits) - 1;
+                    hits &= hits - 1u;
+                    const uint32_t e = e_next;
+                    if (hits) e_next = entry_of(__ffs((int)hits) - 1);
+                    OffCnt oc;
+                    int single = -1;  // the entry's one primer, stored in the entry itself (DevKmerIndex::direct_lohi)
+                    if (((badv >> p0) & km) == 0u) {
+                        if (e & 0x80000000u) single = (int)(e & 0x7FFFFFFFu);
+                        else { oc.off = e & 0xFFFFFu; oc.cnt = e >> 20; }
+                    } else {
                         uint64_t key = 0;  // rare: spell the k-mer out, first base in the highest nibble
                         for (int j = 0; j < ix.k; ++j) {
                             const int b = p0 + j;
                             const uint32_t word = b < 8 ? sr[0] : b < 16 ? sr[1] : b < 24 ? sr[2] : sr[3];
                             key = (key << 4) | ((word >> (4 * (b & 7))) & 15u);
                         }
-                        if (!kmer_lookup(ix, key, oc)) continue;
+                        if (!kmer_lookup(ix, key, oc)) continue;  // the Bloom filter said "maybe"
                     }
                     bool full = false;
-                    for (uint32_t j = 0; j < oc.cnt; ++j) {
-                        const int p = (int)__ldg(&ix.postings[oc.off + j]);
+                    const uint32_t cnt = single >= 0 ? 1u : oc.cnt;
+                    for (uint32_t j = 0; j < cnt; ++j) {
+                        const int p = single >= 0 ? single : (int)__ldg(&ix.postings[oc.off + j]);
+                        if (p == last_p) continue;  // consecutive k-mers of an on-target read list the same primer again and again
                         bool seen = false;
 #pragma unroll
                         for (int t = 0; t < kCandLocal; ++t) seen |= (t < nc && cand[t] == p);
+                        last_p = p;
                         if (seen) continue;
                         if (nc == kCandLocal) { full = true; break; }
 #pragma unroll
@@ -1349,10 +1373,17 @@ __global__ void __launch_bounds__(256) metrics_kernel(DevReads R, const uint8_t 
     // either side (the read before decides whether the first one is an R2, the one after is the last one's mate)
     const bool vec = (reinterpret_cast<uintptr_t>(R.flags) & 15) == 0 && (reinterpret_cast<uintptr_t>(rtype) & 7) == 0;
     const long long n8 = ((long long)R.n + 7) / 8;
+    // A batch puts nearly all of its templates into a handful of bins.  Each warp picks up to four of them from the first
+    // templates it sees and counts those in registers for the whole launch (same-address shared-memory atomics serialise:
+    // they were this kernel's whole cost); only the templates of other bins go to the shared histogram one by one.
+    int B[4] = {-1, -1, -1, -1};
+    unsigned c[4] = {0u, 0u, 0u, 0u};
+    bool chosen = false;
     for (long long base = (long long)blockIdx.x * blockDim.x; base < n8; base += (long long)gridDim.x * blockDim.x) {
         const long long g = base + threadIdx.x;
-        int cur = -1;
-        unsigned cnt = 0;
+        int bin[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) bin[u] = -1;
         if (g < n8) {
             const int r0 = (int)(g * 8);
             uint16_t f[10];  // f[0] = flags[r0 - 1], f[1..8] = flags[r0 .. r0 + 7], f[9] = flags[r0 + 8]; zero outside the batch
@@ -1380,23 +1411,38 @@ __global__ void __launch_bounds__(256) metrics_kernel(DevReads R, const uint8_t 
                 const bool has_r2 = (fl & IDP_F_MATE_NEXT) && r + 1 < R.n;
                 const bool m1 = !(fl & IDP_F_UNMAPPED), m2 = !(f[u + 2] & IDP_F_UNMAPPED);
                 const int tt = !has_r2 ? (m1 ? 3 : 4) : ((m1 && m2) ? 0 : (m1 != m2 ? 1 : 2));
-                const int bin = ((tt * 2 + ((fl & IDP_F_FR_PAIR) ? 1 : 0)) * 4 + t[u]) * 4 + (has_r2 ? (int)t[u + 1] : (int)IDP_NONE);
-                if (bin != cur) {  // runs of one bin are counted in a register
-                    if (cnt) atomicAdd(&hist[cur], cnt);
-                    cur = bin; cnt = 0;
-                }
-                ++cnt;
+                bin[u] = ((tt * 2 + ((fl & IDP_F_FR_PAIR) ? 1 : 0)) * 4 + t[u]) * 4 + (has_r2 ? (int)t[u + 1] : (int)IDP_NONE);
             }
         }
-        // most templates of a batch land in one bin: the warp adds that bin once, the other lanes add their own
-        const unsigned have = __ballot_sync(0xffffffffu, cnt != 0u);
-        if (have) {
-            const int lead = __ffs(have) - 1;
-            const int b0 = __shfl_sync(0xffffffffu, cur, lead);
-            const unsigned sum = __reduce_add_sync(0xffffffffu, (cnt != 0u && cur == b0) ? cnt : 0u);
-            if ((int)(threadIdx.x & 31) == lead) atomicAdd(&hist[b0], sum);
-            else if (cnt != 0u && cur != b0) atomicAdd(&hist[cur], cnt);
+        if (!chosen) {  // warp-uniform: the loop bound is the same for the whole block
+            chosen = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int want = -1;  // this lane's first bin that is not picked yet
+#pragma unroll
+                for (int u = 7; u >= 0; --u) {
+                    bool taken = bin[u] < 0;
+#pragma unroll
+                    for (int j = 0; j < k; ++j) taken |= bin[u] == B[j];
+                    if (!taken) want = bin[u];
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, want >= 0);
+                if (m) B[k] = __shfl_sync(0xffffffffu, want, __ffs(m) - 1);
+            }
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (bin[u] < 0) continue;
+            bool counted = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const bool h = bin[u] == B[k]; c[k] += h ? 1u : 0u; counted |= h; }
+            if (!counted) atomicAdd(&hist[bin[u]], 1u);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned sum = __reduce_add_sync(0xffffffffu, c[k]);
+        if ((threadIdx.x & 31) == 0 && sum) atomicAdd(&hist[B[k]], sum);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 160; i += blockDim.x) if (hist[i]) atomicAdd(&ctr->metrics[i], (unsigned long long)hist[i]);

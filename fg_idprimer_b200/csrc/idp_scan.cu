@@ -11,7 +11,7 @@ namespace idp {
 
 template <int RW, bool FAST>
 static int launch_scan_t(const LaunchCfg &c, cudaStream_t st, const DevReads &R, ResultOut five, uint8_t *rtype, uint32_t *fall_mask, Counters *ctr,
-                         const unsigned *list) {
+                         const unsigned *list, uint32_t *defer_mask) {
     // shared-memory plan: the per-warp read tiles first (two buffers each), then as much of the panel side as fits in half
     // an SM (two CTAs per SM: the kernel holds 64 registers per thread)
     ScanLaunch S{};
@@ -20,6 +20,7 @@ static int launch_scan_t(const LaunchCfg &c, cudaStream_t st, const DevReads &R,
     size_t used = 0;
     S.list = list;
     S.fall_mask = fall_mask;
+    S.defer_mask = FAST && list != nullptr && !c.scan_stats ? defer_mask : nullptr;
     S.stride = R.fixed_len > 0 ? (uint32_t)((R.fixed_len + 1) >> 1) : 0;
     // a warp tile is 32 reads: 32 * stride bytes, always a multiple of 16 as the TMA bulk copy requires
     S.stage_tile = list == nullptr && R.fixed_len > 0 && (reinterpret_cast<uintptr_t>(R.seq4) & 15) == 0;
@@ -67,18 +68,18 @@ static int launch_scan_t(const LaunchCfg &c, cudaStream_t st, const DevReads &R,
 }
 template <int RW>
 static int launch_scan_rw(const LaunchCfg &c, cudaStream_t st, const DevReads &R, ResultOut five, uint8_t *rtype, uint32_t *fall_mask, Counters *ctr,
-                          const unsigned *list) {
-    if (RW <= 8 && c.dp.bs_ok && !getenv("IDP_SCAN_EXACT_WALK")) return launch_scan_t<(RW <= 8 ? RW : 8), true>(c, st, R, five, rtype, fall_mask, ctr, list);
-    return launch_scan_t<RW, false>(c, st, R, five, rtype, fall_mask, ctr, list);
+                          const unsigned *list, uint32_t *defer_mask) {
+    if (RW <= 8 && c.dp.bs_ok && !getenv("IDP_SCAN_EXACT_WALK")) return launch_scan_t<(RW <= 8 ? RW : 8), true>(c, st, R, five, rtype, fall_mask, ctr, list, defer_mask);
+    return launch_scan_t<RW, false>(c, st, R, five, rtype, fall_mask, ctr, list, defer_mask);
 }
 static int launch_scan_general(const LaunchCfg &c, cudaStream_t st, const DevReads &R, ResultOut five, uint8_t *rtype, uint32_t *fall_mask, Counters *ctr,
-                               const unsigned *list) {
+                               const unsigned *list, uint32_t *defer_mask) {
     switch (c.rw) {
-        case 4: return launch_scan_rw<4>(c, st, R, five, rtype, fall_mask, ctr, list);
-        case 5: return launch_scan_rw<5>(c, st, R, five, rtype, fall_mask, ctr, list);
-        case 8: return launch_scan_rw<8>(c, st, R, five, rtype, fall_mask, ctr, list);
-        case 16: return launch_scan_rw<16>(c, st, R, five, rtype, fall_mask, ctr, list);
-        default: return launch_scan_rw<32>(c, st, R, five, rtype, fall_mask, ctr, list);
+        case 4: return launch_scan_rw<4>(c, st, R, five, rtype, fall_mask, ctr, list, defer_mask);
+        case 5: return launch_scan_rw<5>(c, st, R, five, rtype, fall_mask, ctr, list, defer_mask);
+        case 8: return launch_scan_rw<8>(c, st, R, five, rtype, fall_mask, ctr, list, defer_mask);
+        case 16: return launch_scan_rw<16>(c, st, R, five, rtype, fall_mask, ctr, list, defer_mask);
+        default: return launch_scan_rw<32>(c, st, R, five, rtype, fall_mask, ctr, list, defer_mask);
     }
 }
 
@@ -127,9 +128,16 @@ static int launch_scan_fx(const LaunchCfg &c, cudaStream_t st, const DevReads &R
     return IDP_OK;
 }
 
-static void launch_compact(const LaunchCfg &c, cudaStream_t st, const uint32_t *mask, int n_tiles, unsigned *list, unsigned *counter) {
+static void launch_compact(const LaunchCfg &c, cudaStream_t st, const uint32_t *mask, int n_tiles, unsigned *list, unsigned *counter,
+                           const unsigned *n_items_dev = nullptr) {
     const int grid = std::max(1, std::min((n_tiles + 255) / 256, c.sm_count * 8));
-    compact_mask_kernel<<<grid, 256, 0, st>>>(mask, n_tiles, list, counter);
+    compact_mask_kernel<<<grid, 256, 0, st>>>(mask, n_tiles, list, counter, n_items_dev);
+}
+
+template <int RW>
+static void launch_member_check_t(const LaunchCfg &c, cudaStream_t st, const DevReads &R, const unsigned *parked, const unsigned *items, Counters *ctr,
+                                  ResultOut five, uint8_t *rtype, uint32_t *fall_mask) {
+    member_check_kernel<RW><<<c.sm_count * 4, 128, 0, st>>>(c.dp, R, parked, items, ctr, five, rtype, fall_mask);
 }
 
 // masks: 2 * ceil(R.n / 32) words of scratch (fall-through bits, then parked bits)
@@ -142,9 +150,16 @@ int launch_scan(const LaunchCfg &c, cudaStream_t st, const DevReads &R, ResultOu
         if ((rc = launch_scan_fx(c, st, R, five, rtype, fall_mask, park_mask))) return rc;
         launch_compact(c, st, park_mask, n_tiles, parked, &ctr->n_parked);
         *launches += 2;
-        rc = launch_scan_general(c, st, R, five, rtype, fall_mask, ctr, parked);
+        // the parked bits are spent: their words now take the deferred bits, one per LIST item
+        const bool defer = c.dp.kidx[0].k > 0 && !getenv("IDP_SCAN_NO_DEFER");
+        if ((rc = launch_scan_general(c, st, R, five, rtype, fall_mask, ctr, parked, defer ? park_mask : nullptr))) return rc;
+        if (defer) {  // `fall` holds the deferred items until the last compaction below overwrites it
+            launch_compact(c, st, park_mask, n_tiles, fall, &ctr->n_defer, &ctr->n_parked);
+            launch_member_check_t<4>(c, st, R, parked, fall, ctr, five, rtype, fall_mask);  // fx_applies: four window words
+            *launches += 2;
+        }
     } else {
-        rc = launch_scan_general(c, st, R, five, rtype, fall_mask, ctr, nullptr);
+        rc = launch_scan_general(c, st, R, five, rtype, fall_mask, ctr, nullptr, nullptr);
     }
     if (rc) return rc;
     launch_compact(c, st, fall_mask, n_tiles, fall, &ctr->n_fall);

@@ -40,6 +40,10 @@ struct ScanLaunch {
     // reads 0 .. R.n; nothing is staged then, every lane fetches its own read
     const unsigned int *list;
     uint32_t *fall_mask;       // [ceil(R.n / 32)] bit i of word t: read 32 t + i fell through to the gapped stage (IP:444-450)
+    // list mode only, may be NULL: bit i of word t = list item 32 t + i has ONE accepted primer whose k-mer rule neither the table
+    // nor the diagonal proves.  The kernel then records that primer provisionally and member_check_kernel does the exact walk
+    // with one read per lane (inside this kernel the walk ran on a lane or two of a warp while the others waited)
+    uint32_t *defer_mask;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -433,6 +437,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
             int r = item;
             uint16_t fl = 0;
             bool search = false;   // this lane still needs the ungapped matcher
+            bool defer = false;    // the record written below is provisional (ScanLaunch::defer_mask)
             idp_result res = none_result();
             c.compares = 0;
             if (active) {
@@ -571,6 +576,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
                             } else {
                                 proved = diagonal_kmer<RW>(P, c, a_p, a_seq, ix.k, n_bases);
                             }
+                            if (!proved && S.defer_mask != nullptr) { defer = true; proved = true; }
                             if (proved || member_exact(a_p))
                                 best.offer(a_p, a_mm, 0.0);  // the only accepted candidate: its sort key is never compared
                         } else if (n_acc >= 2) {
@@ -601,8 +607,12 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
             if (S.list == nullptr) {
                 const unsigned ballot = __ballot_sync(0xffffffffu, need_gapped);
                 if (lane == 0) S.fall_mask[wt] = ballot;
-            } else if (need_gapped) {
-                atomicOr(&S.fall_mask[r >> 5], 1u << (r & 31));  // result unused: a fire-and-forget reduction
+            } else {
+                if (need_gapped) atomicOr(&S.fall_mask[r >> 5], 1u << (r & 31));  // result unused: a fire-and-forget reduction
+                if (S.defer_mask != nullptr) {
+                    const unsigned ballot = __ballot_sync(0xffffffffu, defer);
+                    if (lane == 0) S.defer_mask[wt] = ballot;
+                }
             }
             if constexpr (ST) compares_total += c.compares;
         }
@@ -614,6 +624,31 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) compares_total += __shfl_xor_sync(0xffffffffu, compares_total, d);
         if (lane == 0 && compares_total) atomicAdd(&ctr->base_compares, compares_total);
+    }
+}
+
+// The reads scan_kernel deferred (ScanLaunch::defer_mask): is the provisionally recorded primer among the read's k-mer
+// candidates (PM:108-116)?  One read per thread, every lane busy with the same walk.  No: the record goes back to "no match"
+// and the read joins the fall-through reads.
+template <int RW>
+__global__ void __launch_bounds__(128) member_check_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ parked,
+                                                           const unsigned int *__restrict__ items, const Counters *__restrict__ ctr, ResultOut five,
+                                                           uint8_t *__restrict__ rtype, uint32_t *__restrict__ fall_mask) {
+    const unsigned n = ctr->n_defer;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int r = (int)parked[items[i]];
+        ScanCtx<RW, false> c;
+        c.compares = 0; c.pmask = nullptr; c.pinfo = nullptr;
+        const uint8_t *s;
+        read_geom(R, r, s, c.len);
+        window_from_global<RW>(R, r, s, c.len, seq_order_is_rc(R.flags[r]), c.win);
+        int type, primer;
+        read_type_primer(five, r, type, primer);
+        if (!kmer_member_exact<RW>(P, c, primer)) {
+            write_result(five, r, none_result());
+            rtype[r] = (uint8_t)IDP_NONE;
+            atomicOr(&fall_mask[r >> 5], 1u << (r & 31));
+        }
     }
 }
 

@@ -198,8 +198,11 @@ __global__ void __launch_bounds__(kFxThreads, 3) scan_fx_kernel(const __grid_con
 
 // Bit masks (one bit per read, one word per 32-read tile) -> index list.  One thread per tile, a block-wide prefix sum and ONE
 // atomic per 256 tiles reserve the room; inside a block the list keeps read order.
+// n_items_dev != NULL: the mask covers *n_items_dev bits (a count an earlier kernel of the stream left on the device), n_tiles is
+// then only the upper bound the grid was sized for.
 __global__ void __launch_bounds__(256) compact_mask_kernel(const uint32_t *__restrict__ mask, int n_tiles, unsigned int *__restrict__ list,
-                                                           unsigned int *__restrict__ counter) {
+                                                           unsigned int *__restrict__ counter, const unsigned int *__restrict__ n_items_dev) {
+    if (n_items_dev != nullptr) n_tiles = (int)((*n_items_dev + 31u) / 32u);
     __shared__ unsigned warp_sum[8];
     __shared__ unsigned block_base;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
