@@ -273,6 +273,11 @@ static int upload_panel(idp_ctx *c) {
         const bool no16 = getenv("IDP_SW_NO_16X2") != nullptr;
         d.fits16_glocal = !no16 && d.smat == nullptr && 2 * m16 * span < 16000;
         d.fits16_local = !no16 && d.smat == nullptr && m16 * (64 + 2) < 16000;
+        // sw_trace2_local16: six signed score bits per half-word (the rows * match <= 31 part is checked per pair)
+        // sw_trace2_glocal16: eight signed score bits in shifted coordinates (the upper end is checked per pair: rows, columns)
+        d.glocal16_ok = d.packed_trace_ok && !getenv("IDP_SW_NO_GLOCAL16") && ma >= 0 && mi <= 0 && go <= 0 && ge <= 0 &&
+                        std::min(go, 0L) + std::min(mi - 2 * ge, 0L) + go + ge * (32 + 63) >= -127 && (ma - 2 * ge) <= 127 && -ge * 64 <= 127;
+        d.local16_ok = d.packed_trace_ok && !getenv("IDP_SW_NO_LOCAL16") && ma >= 1 && ma <= 31 && mi <= 0 && mi >= -32 && go <= 0 && ge <= 0 && go + 2 * ge >= -32;
     }
     d.slop = p.params.slop; d.three_prime = p.params.three_prime;
     d.max_mismatch_rate = p.params.max_mismatch_rate; d.min_alignment_score_rate = p.params.min_alignment_score_rate;
@@ -280,7 +285,7 @@ static int upload_panel(idp_ctx *c) {
     c->cfg.rw = wb <= 32 ? 4 : wb <= 40 ? 5 : wb <= 64 ? 8 : wb <= 128 ? 16 : 32;
     c->cfg.nq = p.max_seq_len <= 32 ? 32 : p.max_seq_len <= 64 ? 64 : 0;
     if (!AlignPolicy::kIsDefault) {  // the register-resident aligners implement the default policy only: everything takes the generic kernels
-        c->cfg.nq = 0; d.packed_trace_ok = 0; d.fits16_glocal = 0; d.fits16_local = 0;
+        c->cfg.nq = 0; d.packed_trace_ok = 0; d.fits16_glocal = 0; d.fits16_local = 0; d.local16_ok = 0; d.glocal16_ok = 0;
     }
     const int nq = c->cfg.nq;
     d.qbot = nullptr;

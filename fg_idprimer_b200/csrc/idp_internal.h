@@ -147,6 +147,8 @@ struct DevPanel {
     // (a product formed in the kernel is folded back into every use as a multiply-add):
     // tr_*: value << 14 for the register traceback (glocal ones in shifted coordinates: match/mismatch - 2*extend)
     int32_t tr_open, tr_open_ext, tr_ext, tr_match, tr_mismatch, tr_match_shifted, tr_mismatch_shifted;
+    int32_t glocal16_ok;  // 5' Glocal with traceback fits (score << 8 | rank << 6 | start) half-words: sw_trace2_glocal16
+    int32_t local16_ok;  // 3' Local with traceback fits (score << 10 | rank << 8 | start) half-words: sw_trace2_local16
     int32_t fits16_glocal, fits16_local;  // every value of a 5' (Glocal) / 3' (Local) score matrix fits 16 bits: two alignments per register
     int32_t slop, three_prime;
     double max_mismatch_rate, min_alignment_score_rate;

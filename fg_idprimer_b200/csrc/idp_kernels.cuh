@@ -583,6 +583,22 @@ __device__ __forceinline__ int sw_score_fast(const DevPanel &P, const uint32_t *
 // value range (DevPanel::fits16_glocal / fits16_local).  Glocal runs in the shifted coordinates of
 // sw_score_glocal_shifted, Local in plain coordinates with the zero clamp folded into the .RELU form.
 __device__ __forceinline__ uint32_t pack16(int x) { return ((uint32_t)x & 0xFFFFu) * 0x00010001u; }
+// PRMT with the selector's sign bits honoured (__byte_perm drops them): a selector nibble 8 | b replicates the TOP BIT of byte b
+template <uint32_t SEL>
+__device__ __forceinline__ uint32_t prmt_sign(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "n"(SEL));
+    return d;
+}
+// the top bit of every nibble that is non-zero (the other bits are left as they fall)
+__device__ __forceinline__ uint32_t nib_nonzero_top(uint32_t x) {
+    x |= x << 1;
+    x |= x << 2;
+    return x;
+}
+// selector of the PRMT that turns the flags of row r into two half-word masks: byte (r % 8) / 2 of the first word for the low half,
+// of the second word for the high half, each as its replicated top bit
+#define IDP_SEL16(r) ((8u | (((r) & 7) >> 1)) * 0x0011u | (8u | (4u + (((r) & 7) >> 1))) * 0x1100u)
 
 template <int NQ, bool LOCAL>
 __device__ __forceinline__ void sw_score2_fast(const DevPanel &P, const uint32_t *__restrict__ qbot_a, const uint32_t *__restrict__ qbot_b, int na,
@@ -619,15 +635,13 @@ __device__ __forceinline__ void sw_score2_fast(const DevPanel &P, const uint32_t
         uint32_t tA = ts.nib(j - 1), tB = j < m ? ts.nib(j) : 0u;
         asm volatile("" : "+r"(tA), "+r"(tB));
         const uint32_t trepA = tA * 0x11111111u, trepB = tB * 0x11111111u;
-        uint32_t pkA[NQ / 4], pkB[NQ / 4];  // rows 4w..4w+3: mismatch flags of a at bits 0,4,8,12 and of b at bits 16,20,24,28
+        // mismatch flags in the TOP BIT of a byte, where the sign-replicating PRMT of a row picks them up: rows 8w+2h+1 in byte h
+        // of ?o, rows 8w+2h in byte h of ?e (a, b = the two queries; A, B = the two columns)
+        uint32_t aoA[NQ / 8], aeA[NQ / 8], boA[NQ / 8], beA[NQ / 8], aoB[NQ / 8], aeB[NQ / 8], boB[NQ / 8], beB[NQ / 8];
 #pragma unroll
         for (int w = 0; w < NQ / 8; ++w) {
-            const uint32_t fa = nib_nonzero(qa[w] ^ trepA), fb = nib_nonzero(qb[w] ^ trepA);
-            pkA[2 * w] = __byte_perm(fa, fb, 0x5410);
-            pkA[2 * w + 1] = __byte_perm(fa, fb, 0x7632);
-            const uint32_t ga = nib_nonzero(qa[w] ^ trepB), gb = nib_nonzero(qb[w] ^ trepB);
-            pkB[2 * w] = __byte_perm(ga, gb, 0x5410);
-            pkB[2 * w + 1] = __byte_perm(ga, gb, 0x7632);
+            aoA[w] = nib_nonzero_top(qa[w] ^ trepA); aeA[w] = aoA[w] << 4; boA[w] = nib_nonzero_top(qb[w] ^ trepA); beA[w] = boA[w] << 4;
+            aoB[w] = nib_nonzero_top(qa[w] ^ trepB); aeB[w] = aoB[w] << 4; boB[w] = nib_nonzero_top(qb[w] ^ trepB); beB[w] = boB[w] << 4;
         }
         uint32_t mdiagA, d_upA, u_upA, mdiagB, d_upB, u_upB;
         if (LOCAL) { mdiagA = d_upA = u_upA = 0u; mdiagB = d_upB = u_upB = 0u; }
@@ -636,7 +650,8 @@ __device__ __forceinline__ void sw_score2_fast(const DevPanel &P, const uint32_t
             mdiagB = edge; edge = __vadd2(edge, ne2); d_upB = edge; u_upB = edge;
         }
 #define IDP_CELL2(r, S)                                                                                    \
-            const uint32_t mask##S = ((pk##S[(r) >> 2] >> (4 * ((r) & 3))) & 0x00010001u) * 0xFFFFu;         \
+            const uint32_t mask##S = ((r) & 1) ? prmt_sign<IDP_SEL16(r)>(ao##S[(r) >> 3], bo##S[(r) >> 3])   \
+                                               : prmt_sign<IDP_SEL16(r)>(ae##S[(r) >> 3], be##S[(r) >> 3]);  \
             const uint32_t s2##S = ma2 ^ (mask##S & selx);                                                 \
             const uint32_t dn##S = LOCAL ? __viaddmax_s16x2_relu(mdiag##S, s2##S, 0u) : __vadd2(mdiag##S, s2##S); \
             const uint32_t un##S = LOCAL ? __viaddmax_s16x2(d_up##S, o2, __vadd2(u_up##S, e2)) : __viaddmax_s16x2(d_up##S, o2, u_up##S); \
@@ -873,6 +888,188 @@ __device__ __forceinline__ TracedReg sw_trace_reg_local(const DevPanel &P, const
     return out;
 }
 
+// The same, TWO alignments per thread (different queries AND different targets), one in each 16-bit half of every register:
+//      value = (score << 10) | (rank << 8) | (255 - start)
+// A Local Diagonal value is never negative, so Left / Up never fall below open + extend and six signed score bits are
+// enough when  rows * match <= 31,  mismatch >= -32  and  open + 2 * extend >= -32  (DevPanel::local16_ok and the caller's check
+// of the rows); start columns need targets of at most 254 bases.  Per step of two cells: one PRMT turns the two mismatch flags
+// into the two half-word masks (sign-replicating byte select on the pre-shifted flag words), then the packed DPX forms.
+// The zero clamp rides in the third operand of the diagonal VIADDMNMX: "score 0, rank 0, path starts after this column" loses
+// against any positive value and, rank 0 being below every stamped rank, against the cell's own value at exactly zero.
+template <int NQ>
+__device__ __forceinline__ void sw_trace2_local16(const DevPanel &P, const uint32_t *__restrict__ qbot_a, const uint32_t *__restrict__ qbot_b, int na, int nb,
+                                                  int lo, int hi, const Oriented &Ta, int m_a, const Oriented &Tb, int m_b, TracedReg &out_a, TracedReg &out_b) {
+    static_assert(NQ == 32, "six score bits hold at most 31 rows of match score 1");
+    constexpr uint32_t LOW = 0x03FF03FFu, RANK = 0x03000300u, RD = 0x03000300u, RL = 0x02000200u, RU = 0x01000100u, INV2 = 0x00FF00FFu, MIN2 = 0x80008000u;
+    constexpr int SH = 10, INV = 0xFF;
+    out_a = TracedReg{0, 1, 0}; out_b = TracedReg{0, 1, 0};
+    const int m = max(m_a, m_b);
+    if (m == 0) return;
+    uint32_t ma2 = pack16(P.match_score << SH), selx = ma2 ^ pack16(P.mismatch_score << SH);
+    uint32_t oe2 = pack16((P.gap_open + P.gap_extend) << SH), e2 = pack16(P.gap_extend << SH);
+    asm volatile("" : "+r"(ma2), "+r"(selx), "+r"(oe2), "+r"(e2));
+    const unsigned am = __activemask();
+    const int self = (int)(threadIdx.x & 31u);
+    const uint32_t keep = __shfl_sync(am, ~RANK, self), keeplow = __shfl_sync(am, ~LOW, self);  // in registers: "& keep | stamp" is then ONE LOP3
+    const int offa = NQ - na, offb = NQ - nb;
+    uint32_t qa[NQ / 8], qb[NQ / 8];
+#pragma unroll
+    for (int w = 0; w < NQ / 8; ++w) { qa[w] = __ldg(&qbot_a[w]); qb[w] = __ldg(&qbot_b[w]); }
+    uint32_t LN[NQ], M[NQ];  // LN[r] = Left(r, next column), stamped
+#pragma unroll
+    for (int r = 0; r < NQ; ++r) { LN[r] = (__viaddmax_s16x2(RD | INV2, oe2, __vadd2(RL | INV2, e2)) & ~RANK) | RL; M[r] = RD | INV2; }  // column 0: all zero, start 0
+    uint32_t bestkey = MIN2;
+    int best_a = (int)((RD | INV2) & 0xFFFFu), best_b = best_a, bj_a = 0, bj_b = 0;
+    TargetStream tsa(Ta), tsb(Tb);
+    for (int j = 1; j <= m; ++j) {
+        uint32_t ta = j <= m_a ? tsa.nib(j - 1) : 0u, tb = j <= m_b ? tsb.nib(j - 1) : 0u;
+        asm volatile("" : "+r"(ta), "+r"(tb));
+        const uint32_t trepa = ta * 0x11111111u, trepb = tb * 0x11111111u;
+        // mismatch flags of rows 8w..8w+7, moved to the top bit of a byte: even rows 8w+2h in byte h of ?e, odd rows 8w+2h+1 in byte h of ?o
+        uint32_t ae[NQ / 8], ao[NQ / 8], be[NQ / 8], bo[NQ / 8];
+#pragma unroll
+        for (int w = 0; w < NQ / 8; ++w) {
+            ao[w] = nib_nonzero_top(qa[w] ^ trepa); ae[w] = ao[w] << 4; bo[w] = nib_nonzero_top(qb[w] ^ trepb); be[w] = bo[w] << 4;
+        }
+        const uint32_t fresh0 = pack16(INV - j);  // score 0, rank 0, the path starts after this column
+        uint32_t mdiag = pack16(INV + 1 - j), d_up = RD | fresh0, u_up = RU | fresh0;  // row 0: score 0, path starts at this column
+        uint32_t colmax = MIN2;
+#define IDP_CELL(r)                                                                                                   \
+            const uint32_t mask = ((r) & 1) ? prmt_sign<IDP_SEL16(r)>(ao[(r) >> 3], bo[(r) >> 3])                     \
+                                            : prmt_sign<IDP_SEL16(r)>(ae[(r) >> 3], be[(r) >> 3]);                    \
+            const uint32_t s2 = ma2 ^ (mask & selx);                                                                  \
+            const uint32_t dn = (__viaddmax_s16x2(mdiag, s2, fresh0) & keep) | RD;                                    \
+            const uint32_t un = (__viaddmax_s16x2(d_up, oe2, __vadd2(u_up, e2)) & keep) | RU;                         \
+            const uint32_t ln = LN[(r)];                                                                              \
+            const uint32_t mold = M[(r)];                                                                             \
+            M[(r)] = __vimax3_s16x2(dn, ln, un);                                                                      \
+            LN[(r)] = (__viaddmax_s16x2(dn, oe2, __vadd2(ln, e2)) & keep) | RL;
+#define IDP_ROW(r)                                                                                                    \
+    case (r): {                                                                                                       \
+        if ((r) >= hi) break;                                                                                         \
+        const uint32_t act = (((r) >= offa) ? 0x0000FFFFu : 0u) | (((r) >= offb) ? 0xFFFF0000u : 0u);                 \
+        IDP_CELL(r)                                                                                                   \
+        mdiag = (mold & act) | (mdiag & ~act); d_up = (dn & act) | (d_up & ~act); u_up = (un & act) | (u_up & ~act);  \
+        colmax = __vmaxs2(colmax, ((((dn & keeplow) | (uint32_t)(NQ - 1 - (r)) * 0x00010001u) & act) | (MIN2 & ~act)));  \
+    }
+        IDP_SWITCH_ROWS(NQ, lo)
+#undef IDP_ROW
+#define IDP_ROW(r)                                                                                                    \
+    case (r): {                                                                                                       \
+        IDP_CELL(r)                                                                                                   \
+        mdiag = mold; d_up = dn; u_up = un;                                                                           \
+        colmax = __vmaxs2(colmax, (dn & keeplow) | (uint32_t)(NQ - 1 - (r)) * 0x00010001u);                           \
+    }
+        IDP_SWITCH_ROWS(NQ, hi)
+#undef IDP_ROW
+#undef IDP_CELL
+        const uint32_t valid = (j <= m_a ? 0x0000FFFFu : 0u) | (j <= m_b ? 0xFFFF0000u : 0u);
+        const uint32_t gt = __vcmpgts2(colmax, bestkey) & valid;
+        if (gt) {  // a new best cell in this column (rare after the first few columns): fetch its start bits
+            bestkey = (colmax & gt) | (bestkey & ~gt);
+            if (gt & 0xFFFFu) {
+                bj_a = j;
+                const int row = NQ - 1 - (int)(colmax & 31u);
+#pragma unroll
+                for (int r = 0; r < NQ; ++r) best_a = r == row ? (int)(M[r] & 0xFFFFu) : best_a;
+            }
+            if (gt >> 16) {
+                bj_b = j;
+                const int row = NQ - 1 - (int)((colmax >> 16) & 31u);
+#pragma unroll
+                for (int r = 0; r < NQ; ++r) best_b = r == row ? (int)(M[r] >> 16) : best_b;
+            }
+        }
+    }
+    if (m_a > 0) { out_a.score = (int)(int16_t)best_a >> SH; out_a.t_start = (INV - (best_a & INV)) + 1; out_a.t_end = bj_a; }
+    if (m_b > 0) { out_b.score = (int)(int16_t)best_b >> SH; out_b.t_start = (INV - (best_b & INV)) + 1; out_b.t_end = bj_b; }
+}
+
+// Glocal (5' matching) the same way: two alignments per thread in 16-bit half-words, shifted coordinates as in
+// sw_trace_reg_glocal_shifted:      value = (score << 8) | (rank << 6) | start
+// In shifted coordinates every value of row >= 1 lies between  min(open, 0) + min(mismatch - 2 extend, 0) + open  and
+// rows * match - extend * (rows + columns): eight signed score bits hold that for the default scores up to 32 rows and 63
+// columns (DevPanel::glocal16_ok and the caller's per-pair check); six start bits need targets of at most 63 bases.
+template <int NQ>
+__device__ __forceinline__ void sw_trace2_glocal16(const DevPanel &P, const uint32_t *__restrict__ qbot_a, const uint32_t *__restrict__ qbot_b, int na, int nb,
+                                                   int lo, int hi, const Oriented &Ta, int m_a, const Oriented &Tb, int m_b, TracedReg &out_a, TracedReg &out_b) {
+    static_assert(NQ == 32, "eight score bits: at most 32 rows");
+    constexpr uint32_t LOW = 0x00FF00FFu, RANK = 0x00C000C0u, RD = 0x00C000C0u, RL = 0x00800080u, RU = 0x00400040u, NEG2 = 0x80008000u;
+    constexpr int SH = 8;
+    out_a = TracedReg{P.gap_open + na * P.gap_extend, 1, 0}; out_b = TracedReg{P.gap_open + nb * P.gap_extend, 1, 0};  // an empty target
+    const int m = max(m_a, m_b);
+    if (m == 0) return;
+    const int e = P.gap_extend;
+    uint32_t ma2 = pack16((P.match_score - 2 * e) << SH), selx = ma2 ^ pack16((P.mismatch_score - 2 * e) << SH);
+    uint32_t o2 = pack16(P.gap_open << SH), ext2 = pack16(e << SH), ne2 = pack16((-e) << SH);
+    asm volatile("" : "+r"(ma2), "+r"(selx), "+r"(o2), "+r"(ext2), "+r"(ne2));
+    const unsigned am = __activemask();
+    const int self = (int)(threadIdx.x & 31u);
+    const uint32_t keep = __shfl_sync(am, ~RANK, self);  // in a register: "& keep | stamp" is then ONE LOP3
+    const int offa = NQ - na, offb = NQ - nb;
+    uint32_t qa[NQ / 8], qb[NQ / 8];
+#pragma unroll
+    for (int w = 0; w < NQ / 8; ++w) { qa[w] = __ldg(&qbot_a[w]); qb[w] = __ldg(&qbot_b[w]); }
+    uint32_t LN[NQ], M[NQ];
+#pragma unroll
+    for (int r = 0; r < NQ; ++r) { LN[r] = NEG2 | RL; M[r] = o2 | RU; }  // column 0: Up'(i, 0) = open, start 0
+    uint32_t best = NEG2, bj = 0u;
+    uint32_t edge = 0u;                                                              // -extend * j in both halves
+    uint32_t back = (pack16((e * na) << SH) & 0x0000FFFFu) | (pack16((e * nb) << SH) & 0xFFFF0000u);  // extend * (rows + j), per half
+    TargetStream tsa(Ta), tsb(Tb);
+    for (int j = 1; j <= m; ++j) {
+        uint32_t ta = j <= m_a ? tsa.nib(j - 1) : 0u, tb = j <= m_b ? tsb.nib(j - 1) : 0u;
+        asm volatile("" : "+r"(ta), "+r"(tb));
+        const uint32_t trepa = ta * 0x11111111u, trepb = tb * 0x11111111u;
+        uint32_t ae[NQ / 8], ao[NQ / 8], be[NQ / 8], bo[NQ / 8];  // mismatch flags in the top bit of a byte, see sw_trace2_local16
+#pragma unroll
+        for (int w = 0; w < NQ / 8; ++w) {
+            ao[w] = nib_nonzero_top(qa[w] ^ trepa); ae[w] = ao[w] << 4; bo[w] = nib_nonzero_top(qb[w] ^ trepb); be[w] = bo[w] << 4;
+        }
+        const uint32_t jj = pack16(j);
+        uint32_t mdiag = edge + (jj - 0x00010001u);  // row 0: score 0 (shifted: -extend * (j - 1)), rank 0, the path starts at this column
+        edge = __vadd2(edge, ne2);
+        uint32_t d_up = edge | RD | jj, u_up = edge | RU | jj;
+#define IDP_CELL(r)                                                                                                   \
+            const uint32_t mask = ((r) & 1) ? prmt_sign<IDP_SEL16(r)>(ao[(r) >> 3], bo[(r) >> 3])                     \
+                                            : prmt_sign<IDP_SEL16(r)>(ae[(r) >> 3], be[(r) >> 3]);                    \
+            const uint32_t s2 = ma2 ^ (mask & selx);                                                                  \
+            const uint32_t dn = (__vadd2(mdiag, s2) & keep) | RD;                                                     \
+            const uint32_t un = (__viaddmax_s16x2(d_up, o2, u_up) & keep) | RU; /* equal scores: opened from Diagonal */  \
+            const uint32_t ln = LN[(r)];                                                                              \
+            const uint32_t mold = M[(r)];                                                                             \
+            M[(r)] = __vimax3_s16x2(dn, ln, un); /* equal scores: Diagonal, then Left, then Up */                     \
+            LN[(r)] = (__viaddmax_s16x2(dn, o2, ln) & keep) | RL;
+#define IDP_ROW(r)                                                                                                    \
+    case (r): {                                                                                                       \
+        if ((r) >= hi) break;                                                                                         \
+        const uint32_t act = (((r) >= offa) ? 0x0000FFFFu : 0u) | (((r) >= offb) ? 0xFFFF0000u : 0u);                 \
+        IDP_CELL(r)                                                                                                   \
+        mdiag = (mold & act) | (mdiag & ~act); d_up = (dn & act) | (d_up & ~act); u_up = (un & act) | (u_up & ~act);  \
+    }
+        IDP_SWITCH_ROWS(NQ, lo)
+#undef IDP_ROW
+#define IDP_ROW(r)                                                                                                    \
+    case (r): {                                                                                                       \
+        IDP_CELL(r)                                                                                                   \
+        mdiag = mold; d_up = dn; u_up = un;                                                                           \
+    }
+        IDP_SWITCH_ROWS(NQ, hi)
+#undef IDP_ROW
+#undef IDP_CELL
+        // last row, columns ascending, Diagonal then Up, strict '>' on the score, back in true coordinates
+        back = __vadd2(back, ext2);
+        const uint32_t valid = (j <= m_a ? 0x0000FFFFu : 0u) | (j <= m_b ? 0xFFFF0000u : 0u);
+        const uint32_t dt = __vadd2(d_up, back), ut = __vadd2(u_up, back);
+        const uint32_t g1 = __vcmpgts2(dt, best | LOW) & valid;
+        best = (dt & g1) | (best & ~g1); bj = (jj & g1) | (bj & ~g1);
+        const uint32_t g2 = __vcmpgts2(ut, best | LOW) & valid;
+        best = (ut & g2) | (best & ~g2); bj = (jj & g2) | (bj & ~g2);
+    }
+    if (m_a > 0) { const int b = (int)(int16_t)(best & 0xFFFFu); out_a.score = b >> SH; out_a.t_start = (b & 0x3F) + 1; out_a.t_end = (int)(bj & 0xFFFFu); }
+    if (m_b > 0) { const int b = (int)(int16_t)(best >> 16); out_b.score = b >> SH; out_b.t_start = (b & 0x3F) + 1; out_b.t_end = (int)(bj >> 16); }
+}
+
 template <int NQ, bool LOCAL>
 __device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint32_t *__restrict__ qbot, int n, int lo, int hi, const Oriented &T, int m) {
     static_assert(NQ == 32 || NQ == 64, "row count");
@@ -968,7 +1165,7 @@ __device__ __forceinline__ Oriented make_target(const DevPanel &P, const DevRead
 
 constexpr int32_t kScoreMissing = INT32_MIN;  // pair touched a base pair the scoring matrix has no entry for
 
-template <int NQ, bool LOCAL, bool SMAT, bool TRACE>
+template <int NQ, bool LOCAL, bool SMAT, bool TRACE, bool PACK2 = false>
 __global__ void __launch_bounds__(128, 4) sw_pairs_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ work_read,
                                                        Counters *ctr, const unsigned int *__restrict__ pair_work,
                                                        const unsigned int *__restrict__ pair_primer, int *__restrict__ pair_score,
@@ -989,7 +1186,7 @@ __global__ void __launch_bounds__(128, 4) sw_pairs_kernel(DevPanel P, DevReads R
     const unsigned per_round = gridDim.x * blockDim.x;
     // a span is tile x 128 pairs; half of the grid is resident (4 blocks per SM), so spans stay single (every pair gets its own
     // thread at once) until the batch exceeds one round of the whole grid
-    const int tile = n_pairs > 2u * per_round ? 4 : n_pairs > per_round ? 2 : 1;
+    const int tile = n_pairs > 2u * per_round ? 4 : (n_pairs > per_round || PACK2) ? 2 : 1;  // PACK2: a thread takes two pairs at a time
     const unsigned span = (unsigned)tile * blockDim.x;
     for (unsigned base = blockIdx.x * span; base < n_pairs; base += gridDim.x * span) {
         for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist_s[i] = 0;
@@ -1025,6 +1222,61 @@ __global__ void __launch_bounds__(128, 4) sw_pairs_kernel(DevPanel P, DevReads R
         for (int k = 0; k < kTileMax; ++k)
             if (k < tile) order_s[hist_s[bin[k]] + rank[k]] = (unsigned short)(k * blockDim.x + threadIdx.x);
         __syncthreads();
+        if constexpr (PACK2) {
+            // traceback-equivalent alignments, two pairs per thread (sw_trace2_local16 / sw_trace2_glocal16): NEIGHBOURS of the sorted span share a thread, so
+            // the two queries have (nearly) the same number of rows
+            static_assert(!PACK2 || (NQ == 32 && TRACE && !SMAT), "packed traced form: 32 rows, byte-equality scorer");
+            for (int k2 = 0; k2 < tile / 2; ++k2) {
+                const unsigned slot = (k2 & 1) ? (blockDim.x - 32u - (threadIdx.x & ~31u)) + (threadIdx.x & 31u) : threadIdx.x;
+                const unsigned idx = 2u * ((unsigned)k2 * blockDim.x + slot);
+                const unsigned t2[2] = {base + order_s[idx], base + order_s[idx + 1]};
+                bool act2[2];
+                int n2[2] = {0, 0}, m2[2] = {0, 0}, p2[2] = {0, 0};
+                Oriented T2[2] = {Oriented{nullptr, 0, false}, Oriented{nullptr, 0, false}};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    act2[h] = t2[h] < n_pairs;
+                    if (act2[h]) {
+                        const unsigned w = pair_work[t2[h]];
+                        p2[h] = (int)pair_primer[t2[h]];
+                        act2[h] = w < n_work && (unsigned)p2[h] < (unsigned)P.n_primers;
+                        if (act2[h]) {
+                            const int r = work_read ? (int)work_read[w] : (int)w;
+                            n2[h] = __ldg(&P.pinfo[p2[h]]).w;
+                            T2[h] = make_target(P, R, r, n2[h], LOCAL, m2[h]);
+                        }
+                    }
+                }
+                if (!act2[1]) { n2[1] = n2[0]; m2[1] = m2[0]; p2[1] = p2[0]; T2[1] = T2[0]; }  // the sort puts non-pairs last: a lone pair is half 0
+                const bool active = act2[0];
+                const int n_warp_max = __reduce_max_sync(0xffffffffu, max(n2[0], n2[1]));
+                const int n_warp_min = __reduce_min_sync(0xffffffffu, active ? min(n2[0], n2[1]) : n_warp_max);
+                if (active) {
+                    TracedReg ra, rb;
+                    const int nmax = max(n2[0], n2[1]), mmax = max(m2[0], m2[1]);
+                    const bool fits = LOCAL ? (nmax * P.match_score <= 31 && mmax <= 254)
+                                            : (nmax * P.match_score - P.gap_extend * (nmax + mmax) <= 127 && mmax <= 63);
+                    if (fits) {
+                        if constexpr (LOCAL) sw_trace2_local16<32>(P, P.qbot + (size_t)p2[0] * 4, P.qbot + (size_t)p2[1] * 4, n2[0], n2[1], 32 - n_warp_max, 32 - n_warp_min,
+                                                                   T2[0], m2[0], T2[1], m2[1], ra, rb);
+                        else sw_trace2_glocal16<32>(P, P.qbot + (size_t)p2[0] * 4, P.qbot + (size_t)p2[1] * 4, n2[0], n2[1], 32 - n_warp_max, 32 - n_warp_min,
+                                                    T2[0], m2[0], T2[1], m2[1], ra, rb);
+                    } else {  // a long primer or a long target: one at a time, 32-bit values
+                        ra = sw_trace_reg<32, LOCAL>(P, P.qbot + (size_t)p2[0] * 4, n2[0], 32 - n_warp_max, 32 - n_warp_min, T2[0], m2[0]);
+                        rb = ra;
+                        if (act2[1]) rb = sw_trace_reg<32, LOCAL>(P, P.qbot + (size_t)p2[1] * 4, n2[1], 32 - n_warp_max, 32 - n_warp_min, T2[1], m2[1]);
+                    }
+                    pair_score[t2[0]] = ra.score;
+                    pair_se[t2[0]] = ((unsigned)ra.t_start & 0xFFFFu) | ((unsigned)ra.t_end << 16);
+                    cells += (unsigned long long)n2[0] * (unsigned long long)m2[0];
+                    if (act2[1]) {
+                        pair_score[t2[1]] = rb.score;
+                        pair_se[t2[1]] = ((unsigned)rb.t_start & 0xFFFFu) | ((unsigned)rb.t_end << 16);
+                        cells += (unsigned long long)n2[1] * (unsigned long long)m2[1];
+                    }
+                }
+            }
+        } else
         for (int k = 0; k < tile; ++k) {
             // the sorted span is dealt to the warps in snake order (0 1 2 3 / 3 2 1 0 / ...), so every warp gets the same mix
             // of short and long primers and the warps reach the barrier below together

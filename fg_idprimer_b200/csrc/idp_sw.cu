@@ -34,6 +34,8 @@ static void launch_sw_pairs_t(const LaunchCfg &c, cudaStream_t st, const DevRead
                               const unsigned *pw, const unsigned *pp, int *ps, unsigned *pse, unsigned cap) {
     const int grid = c.sm_count * 8;
     if (!SMAT && pairs_trace(c)) {
+        // two pairs per thread in 16-bit halves when the scores allow it
+        if (c.nq == 32 && (LOCAL ? c.dp.local16_ok : c.dp.glocal16_ok)) { sw_pairs_kernel<32, LOCAL, false, true, true><<<grid, 128, 0, st>>>(c.dp, R, work_read, ctr, pw, pp, ps, pse, cap); return; }
         if (c.nq == 32) sw_pairs_kernel<32, LOCAL, false, true><<<grid, 128, 0, st>>>(c.dp, R, work_read, ctr, pw, pp, ps, pse, cap);
         else sw_pairs_kernel<64, LOCAL, false, true><<<grid, 128, 0, st>>>(c.dp, R, work_read, ctr, pw, pp, ps, pse, cap);
         return;

@@ -219,6 +219,35 @@ def test_score_ranges_all_primers_and_three_prime(scores):
                  match_score=match, mismatch_score=mismatch, gap_open=gap_open, gap_extend=gap_extend, min_alignment_score_rate=0.05)
 
 
+@pytest.mark.parametrize("scores", [(1, -4, -6, -1), (1, -32, -30, -1), (1, -1, 0, 0), (1, 0, 0, -1), (1, -2, -1, 0), (2, -3, -4, -2), (1, -33, -6, -1)])
+@pytest.mark.parametrize("read_len", [150, 254, 300])
+def test_three_prime_two_pairs_per_thread(scores, read_len):
+    """3' Local alignments with traceback, two (read, primer) pairs per thread in 16-bit half-words (sw_trace2_local16): at the
+    edges of its value range, and past them -- rows * match above 31, a mismatch below -32, reads above 254 bases -- where the
+    pairs take the 32-bit aligner one at a time.  Mapped and unmapped reads, both strands, primers of mixed lengths."""
+    match, mismatch, gap_open, gap_extend = scores
+    w = synth.WORKLOADS["c5"]
+    panel = synth.make_panel(w["pairs"], w["panel_seed"], degenerate=False, mapped=True, read_len=read_len)
+    reads = synth.make_reads(panel, 1501, w["read_seed"], indel_frac=0.1, mapped_frac=0.6, read_len=read_len)
+    opts = dict(w["options"])
+    opts.update(match_score=match, mismatch_score=mismatch, gap_open=gap_open, gap_extend=gap_extend, min_alignment_score_rate=0.2)
+    got5, got3, _, _ = run_both(_synth_primers(panel), reads.oracle_arrays(), ref_names=panel.ref_names, **opts)
+    assert (got3["type"] == L.GAPPED).any()
+
+
+@pytest.mark.parametrize("scores,slop", [((1, -4, -6, -1), 5), ((1, -4, -6, -1), 40), ((1, -4, -6, -1), 0), ((2, -3, -4, 0), 5), ((1, -12, -10, -1), 7),
+                                         ((3, -2, -1, -1), 5), ((1, -20, -10, -1), 5), ((0, -1, -1, -1), 3), ((1, 0, 0, 0), 9)])
+def test_five_prime_two_pairs_per_thread(scores, slop):
+    """5' Glocal alignments with traceback, two (read, primer) pairs per thread in 16-bit half-words (sw_trace2_glocal16): at the
+    edges of its value range and past them -- targets above 63 bases (slop 40), scores whose shifted values leave eight bits --
+    where single pairs (or the whole panel) take the 32-bit aligner.  Indel reads of c3 behind the -K candidate filter."""
+    match, mismatch, gap_open, gap_extend = scores
+    panel, reads, opts = synth.workload("c3", 2501)
+    opts.update(match_score=match, mismatch_score=mismatch, gap_open=gap_open, gap_extend=gap_extend, slop=slop, min_alignment_score_rate=0.1)
+    got5, _, _, t = run_both(_synth_primers(panel)[:400], reads.oracle_arrays(), ref_names=panel.ref_names, **opts)
+    assert t["n_alignments_5p"] > 0
+
+
 def test_ties_near_duplicate_primers():
     """Candidate order decides ties (PM:241, PM:309): near-duplicate primers, with and without the k-mer filters."""
     rng = np.random.default_rng(11)
