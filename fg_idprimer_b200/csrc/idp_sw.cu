@@ -56,9 +56,12 @@ void launch_sw_pairs(const LaunchCfg &c, cudaStream_t st, bool local, const DevR
 template <bool LOCAL, bool SMAT>
 static void launch_sw_all_t(const LaunchCfg &c, cudaStream_t st, const DevReads &R, const unsigned *work_read, const unsigned *n_work,
                             Fin *fin, Counters *ctr, int as5) {
-    const int threads = c.dp.n_primers <= 32 ? 32 : c.dp.n_primers <= 64 ? 64 : 128;
-    const int grid = c.sm_count * (threads == 128 ? 8 : threads == 64 ? 16 : 32);
     const bool packed = !SMAT && (LOCAL ? c.dp.fits16_local : c.dp.fits16_glocal);  // two alignments per register
+    // one block per read, one round of the panel if it fits: as many warps as the panel needs (two primers per thread when packed),
+    // so that no warp of a resident block sits idle -- 192 primers: 96 threads, five blocks per SM instead of four with a warp idle
+    const int per_thread = packed && c.nq > 0 ? 2 : 1;
+    const int threads = std::min(128, std::max(32, ((c.dp.n_primers + per_thread - 1) / per_thread + 31) / 32 * 32));
+    const int grid = c.sm_count * (1024 / threads);
     switch (c.nq) {
         case 32:
             if (packed) sw_all_kernel<32, LOCAL, SMAT, !SMAT><<<grid, threads, 0, st>>>(c.dp, R, work_read, n_work, fin, ctr, as5);

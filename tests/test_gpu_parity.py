@@ -248,6 +248,21 @@ def test_five_prime_two_pairs_per_thread(scores, slop):
     assert t["n_alignments_5p"] > 0
 
 
+@pytest.mark.parametrize("scores", [(1, -4, -6, -1), (1, -1, -1, 0), (2, -3, -4, -2), (1, -8, -1, -1), (3, -1, -9, 0)])
+@pytest.mark.parametrize("n_panel_pairs", [96, 7, 300])
+def test_three_prime_all_primers(scores, n_panel_pairs):
+    """3' matching of templates without a 5' match aligns every primer (IP:497): half of the templates are off-target here, panels
+    of 14, 192 and 600 primers (one, two and several rounds of the all-primers kernel, odd thread counts)."""
+    match, mismatch, gap_open, gap_extend = scores
+    w = synth.WORKLOADS["c5"]
+    panel = synth.make_panel(n_panel_pairs, w["panel_seed"] + n_panel_pairs, degenerate=n_panel_pairs == 7, mapped=True)
+    reads = synth.make_reads(panel, 400, w["read_seed"], indel_frac=0.05, mapped_frac=0.3, offtarget=0.5)
+    opts = dict(w["options"])
+    opts.update(match_score=match, mismatch_score=mismatch, gap_open=gap_open, gap_extend=gap_extend, min_alignment_score_rate=0.0)
+    got5, got3, _, t = run_both(_synth_primers(panel), reads.oracle_arrays(), ref_names=panel.ref_names, **opts)
+    assert (got5["type"] == 0).sum() > 300 and (got3["type"] == L.GAPPED).sum() > 300
+
+
 def test_ties_near_duplicate_primers():
     """Candidate order decides ties (PM:241, PM:309): near-duplicate primers, with and without the k-mer filters."""
     rng = np.random.default_rng(11)

@@ -20,6 +20,11 @@ ncu --set full --clock-control none -k regex:sw_all -c 1 -f -o /tmp/swa python t
 python tools/ncu_summary.py /tmp/swa.ncu-rep > $out/${tag}_ncu_sw_all_c3b_100kpairs.txt 2>&1
 ncu --set full --clock-control none -k regex:sw_pairs -c 1 -f -o /tmp/swp3 python tools/run_workload.py --workload c3 --pairs 4000000 --iters 1 > /dev/null 2>&1
 python tools/ncu_summary.py /tmp/swp3.ncu-rep > $out/${tag}_ncu_sw_pairs_c3_4Mpairs.txt 2>&1
+ncu --set full --import-source on --clock-control none -k regex:sw_pairs -c 1 -f -o /tmp/swp4 python tools/run_workload.py --workload c4 --pairs 4000000 --iters 1 > /dev/null 2>&1
+python tools/ncu_summary.py /tmp/swp4.ncu-rep > $out/${tag}_ncu_sw_pairs_packed_c4_4Mpairs.txt 2>&1
+python tools/ncu_lines.py /tmp/swp4.ncu-rep sw_pairs 1 0.01 > $out/${tag}_ncu_sw_pairs_packed_c4_lines.txt 2>&1
+ncu --set full --clock-control none -k regex:sw_all -c 1 -f -o /tmp/swa5 python tools/run_workload.py --workload c5 --pairs 200000 --iters 1 > /dev/null 2>&1
+python tools/ncu_summary.py /tmp/swa5.ncu-rep > $out/${tag}_ncu_sw_all_c5_200kpairs.txt 2>&1
 ncu --set full --import-source on --clock-control none -k regex:cand5_thread -c 1 -f -o /tmp/c5t python tools/run_workload.py --workload c4 --pairs 4000000 --iters 1 > /dev/null 2>&1
 python tools/ncu_summary.py /tmp/c5t.ncu-rep > $out/${tag}_ncu_cand5_thread_c4_4Mpairs.txt 2>&1
 python tools/ncu_lines.py /tmp/c5t.ncu-rep cand5_thread 1 0.02 > $out/${tag}_ncu_cand5_thread_lines.txt 2>&1
