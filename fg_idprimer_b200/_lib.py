@@ -45,7 +45,7 @@ class IdpTimings(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_scan", C.c_float), ("ms_gapped", C.c_float), ("ms_three_prime", C.c_float),
                 ("ms_sw_score", C.c_float), ("n_reads", C.c_int64), ("n_fallthrough", C.c_int64), ("n_alignments_5p", C.c_int64),
                 ("n_alignments_3p", C.c_int64), ("sw_cells", C.c_int64), ("scan_base_compares", C.c_int64),
-                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("n_scan_parked", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("n_scan_parked", C.c_int64), ("n_scan_deferred", C.c_int64)]
 
 
 RESULT_DTYPE = np.dtype([("primer", "<i4"), ("type", "u1"), ("status", "u1"), ("multi", "u1"), ("reserved", "u1"),

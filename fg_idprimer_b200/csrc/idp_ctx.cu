@@ -79,7 +79,7 @@ struct idp_ctx {
     const idp_panel *panel = nullptr;
     int device = 0;
     LaunchCfg cfg{};
-    DevBuf b_fx, b_pm4, b_dfx, b_cinfo, b_cspan, b_qbot, b_bylen, b_pmask, b_pinfo, b_positive, b_loc_key[2], b_loc_primer[2], b_mate_off, b_mate_idx, b_smat;
+    DevBuf b_fx, b_pm4, b_dfx, b_cinfo, b_cspan, b_qbot, b_mbits, b_bylen, b_pmask, b_pinfo, b_positive, b_loc_key[2], b_loc_primer[2], b_mate_off, b_mate_idx, b_smat;
     DevBuf b_keys[2], b_offcnt[2], b_postings[2], b_heads[2], b_direct[2], b_dbits[2], b_dlohi, b_bloom, b_bsmm, b_bsacc, b_seedtab, b_seedlist, b_diag;
     Slot slots[kSlots];
     cudaStream_t user_stream = nullptr;
@@ -126,7 +126,7 @@ static int upload_panel(idp_ctx *c) {
         k.k = h.k > 0 ? h.k : -1;
         k.window = p.max_primer_length;
         k.slot_mask = 0; k.shift = 63; k.keys = nullptr; k.off_cnt = nullptr; k.postings = nullptr;
-        k.heads = nullptr; k.direct = nullptr; k.direct_lohi = nullptr; k.direct_bits = nullptr; k.iupac_bloom = nullptr; k.n_iupac_kmers = 0; k.n_postings = 0;
+        k.heads = nullptr; k.direct = nullptr; k.direct_lohi = nullptr; k.direct_bits = nullptr; k.direct_bits_words = 0; k.iupac_bloom = nullptr; k.n_iupac_kmers = 0; k.n_postings = 0;
         if (h.k > 0) {
             std::vector<OffCnt> oc(h.keys.size());
             for (size_t i = 0; i < oc.size(); ++i) oc[i] = OffCnt{h.off[i], h.cnt[i]};
@@ -171,6 +171,20 @@ static int upload_panel(idp_ctx *c) {
                         const uint32_t sig = kmer_plane_signature(lo, hi, bad, kk);
                         bloom[sig >> 5] |= 1u << (sig & 31);
                     }
+                    // a sparse map is folded (OR of its halves, up to three times) while at most 3 % of its bits stay set: a small panel
+                    // then takes 16 KB instead of 128 KB of shared memory and two blocks of the candidate kernel fit an SM.  A bit set
+                    // by another k-mer only sends the lookup on to the table, which says "no primer".
+                    {
+                        size_t set = 0;
+                        for (uint32_t v : bits) set += (size_t)__builtin_popcount(v);
+                        const size_t full_words = bits.size();
+                        while (bits.size() > full_words / 8 && bits.size() >= 2048 && set * 100 <= 3 * (bits.size() * 32 / 2)) {
+                            const size_t half = bits.size() / 2;
+                            for (size_t i = 0; i < half; ++i) bits[i] |= bits[i + half];
+                            bits.resize(half);
+                        }
+                    }
+                    k.direct_bits_words = (uint32_t)bits.size();
                     if ((rc = upload(lohi, c->b_dlohi)) || (rc = upload(bits, c->b_dbits[w])) || (rc = upload(bloom, c->b_bloom))) return rc;
                     k.direct_lohi = c->b_dlohi.as<uint32_t>(); k.direct_bits = c->b_dbits[w].as<uint32_t>();
                     k.iupac_bloom = c->b_bloom.as<uint32_t>(); k.n_iupac_kmers = n_iupac;
@@ -182,6 +196,21 @@ static int upload_panel(idp_ctx *c) {
     d.bs_mm = c->b_bsmm.as<uint32_t>(); d.bs_acc = c->b_bsacc.as<uint2>(); d.bs_groups = (int)(p.bs_acc.size() / 2);
     d.bs_ok = p.acc_max <= 1 && p.window_bases <= 64;
     d.diag = nullptr;
+    d.member_bits = nullptr;
+    if (p.kidx[0].k > 0 && p.kidx[0].k <= 16) {  // hash bits of every primer's k-mers (member_check_kernel)
+        const int k = p.kidx[0].k;
+        const uint64_t kmask4 = k >= 16 ? ~0ull : ((1ull << (4 * k)) - 1ull);
+        std::vector<uint32_t> mb((size_t)p.n * 32, 0u);
+        for (int i = 0; i < p.n; ++i) {
+            uint64_t key = 0;
+            for (int b = 0; b < p.seq_len[i]; ++b) {
+                key = ((key << 4) | ((p.pmask[(size_t)i * p.ww + b / 8] >> (4 * (b % 8))) & 15u)) & kmask4;
+                if (b >= k - 1) { const uint32_t h = member_bits_hash(key); mb[(size_t)i * 32 + (h >> 5)] |= 1u << (h & 31); }
+            }
+        }
+        if ((rc = upload(mb, c->b_mbits))) return rc;
+        d.member_bits = c->b_mbits.as<uint32_t>();
+    }
     if (d.bs_ok && p.kidx[0].k > 0 && p.ww <= 4) {
         // a position holding one of A/C/G/T that the read matches carries the same letter in the read (PM:143 on one-bit
         // masks), so the literally equal positions are the non-degenerate ones minus the mismatch position
@@ -414,6 +443,7 @@ static void add_timings(idp_ctx *c, Slot &s, bool first) {
     t.scan_base_compares += (int64_t)s.h_ctr->base_compares;
     t.kernel_launches += s.launches;
     t.n_scan_parked += (int64_t)s.h_ctr->n_parked;
+    t.n_scan_deferred += (int64_t)s.h_ctr->n_defer;
 }
 
 // a failed call must not leave copies in flight into the caller's arrays, nor slots that a later call would harvest
@@ -647,7 +677,7 @@ void idp_ctx_destroy(idp_ctx *c) {
     }
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_finish) cudaEventDestroy(c->ev_finish);
-    for (DevBuf *b : {&c->b_fx, &c->b_pm4, &c->b_dfx, &c->b_cinfo, &c->b_cspan, &c->b_qbot, &c->b_bylen, &c->b_pmask, &c->b_pinfo, &c->b_positive, &c->b_loc_key[0], &c->b_loc_key[1], &c->b_loc_primer[0], &c->b_loc_primer[1],
+    for (DevBuf *b : {&c->b_fx, &c->b_pm4, &c->b_dfx, &c->b_cinfo, &c->b_cspan, &c->b_qbot, &c->b_mbits, &c->b_bylen, &c->b_pmask, &c->b_pinfo, &c->b_positive, &c->b_loc_key[0], &c->b_loc_key[1], &c->b_loc_primer[0], &c->b_loc_primer[1],
                       &c->b_mate_off, &c->b_mate_idx, &c->b_smat, &c->b_keys[0], &c->b_keys[1], &c->b_offcnt[0], &c->b_offcnt[1],
                       &c->b_postings[0], &c->b_postings[1], &c->b_heads[0], &c->b_heads[1], &c->b_direct[0], &c->b_direct[1], &c->b_dbits[0], &c->b_dbits[1], &c->b_dlohi, &c->b_bloom, &c->b_bsmm, &c->b_bsacc, &c->b_seedtab, &c->b_seedlist, &c->b_diag,
                       &c->al_q, &c->al_ql, &c->al_t, &c->al_to, &c->al_tl, &c->al_tp, &c->al_out}) b->release();

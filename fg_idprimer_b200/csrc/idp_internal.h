@@ -12,6 +12,10 @@
 namespace idp {
 
 constexpr int kMaxPrimerBases = 256;   // longest primer sequence the kernels cover
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t member_bits_hash(uint64_t key4) { return (uint32_t)((key4 * 0x9E3779B97F4A7C15ull) >> 54); }  // 10 bits
 constexpr int kMaxK = 16;              // k-mer key = 4 bits/base in a 64-bit word
 constexpr int kFxBases = 12;           // read bases hashed by the exact-prefix table
 constexpr int kMaxReadLen = 4095;      // target start/end are carried in 12 bits next to the score
@@ -81,7 +85,9 @@ struct DevKmerIndex {
     // index = hi << k | lo, bit j of lo / hi = low / high bit of the code (A 0, C 1, G 2, T 3) of the k-mer's base j.  The planes
     // of a whole read window are two 32-bit words, so a k-mer's index is two shifts, two ANDs and a shift-add.
     const uint32_t *direct_lohi;  // NULL, or 4^k entries: posting offset | count << 20, or 0x80000000 | primer when the k-mer has one primer
-    const uint32_t *direct_bits;  // NULL, or 4^k presence bits of direct_lohi (128 KB for k = 10: fits shared memory)
+    const uint32_t *direct_bits;  // NULL, or the presence bits of direct_lohi: 4^k bits (128 KB for k = 10: fits shared memory), or for a sparse
+                                  // table the OR of its 2 / 4 / 8 equal parts -- bit (index mod size), direct_bits_words 32-bit words (a power of two)
+    uint32_t direct_bits_words;
     // k-mers of the hashed table that hold a code other than A/C/G/T (IUPAC letters match literally, PM:113): a 64-Kbit Bloom filter
     // on kmer_plane_signature(); n_iupac_kmers == 0 means a read k-mer holding such a code can never hit
     const uint32_t *iupac_bloom;  // 2048 words, or NULL
@@ -98,6 +104,9 @@ struct DevPanel {
     const uint32_t *pmask;     // [n][ww] IUPAC masks, base i in nibble i, padded with 0xF
     const uint32_t *qbot;      // [n][nq/8] the same letters bottom-aligned in nq (32 or 64) rows, zero above; NULL if nq == 0
     const uint32_t *by_len;    // [n] primer indices sorted by sequence length (stable)
+    // [n][32] per primer, 1,024 hash bits of its -k k-mers (member_bits_hash of the 4-bit-per-base key), NULL without -k:
+    // "is primer p among the primers that share a k-mer with this read" starts with one bit test per read k-mer
+    const uint32_t *member_bits;
     // [n] {Primer.length (PR:206), early-exit cap of numMismatches and largest accepted mismatch count when the read
     //      is at least Primer.length long (PM:130-134), primer.sequence.length}
     const int4 *pinfo;

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kCand5Threads) cand5_thread_kernel(DevPanel P,
                     bool hit;
                     if (bad == 0u) {
                         const uint32_t idx = (h << ix.k) | l;
-                        hit = ((cand5_bm[idx >> 5] >> (idx & 31u)) & 1u) != 0u;
+                        hit = ((cand5_bm[(idx >> 5) & (bm_words - 1u)] >> (idx & 31u)) & 1u) != 0u;  // bm_words: a power of two (folded map)
                     } else if (ix.n_iupac_kmers == 0u) {
                         hit = false;  // a k-mer holding another code can only equal a primer k-mer that spells the same code (PM:113)
                     } else {
@@ -1640,17 +1640,34 @@ __global__ void __launch_bounds__(256) metrics_kernel(DevReads R, const uint8_t 
             const int r0 = (int)(g * 8);
             uint16_t f[10];  // f[0] = flags[r0 - 1], f[1..8] = flags[r0 .. r0 + 7], f[9] = flags[r0 + 8]; zero outside the batch
             uint8_t t[9];    // t[0..7] = rtype[r0 .. r0 + 7], t[8] = rtype[r0 + 8]
+            bool done = false;
             if (vec && r0 + 8 <= R.n) {
                 const uint4 fv = *reinterpret_cast<const uint4 *>(R.flags + r0);
                 const uint2 tv = *reinterpret_cast<const uint2 *>(rtype + r0);
                 const uint32_t fw[4] = {fv.x, fv.y, fv.z, fv.w};
                 const uint32_t tw[2] = {tv.x, tv.y};
+                // the usual batch: R1 at the even positions, each followed by its R2 -- four templates, a word of flags each
+                static_assert(IDP_F_UNMAPPED == (1 << 2) && IDP_F_FR_PAIR == (1 << 12), "bit positions used below");
+                const uint32_t all_and = fw[0] & fw[1] & fw[2] & fw[3], all_or = fw[0] | fw[1] | fw[2] | fw[3];
+                const uint16_t before = r0 > 0 ? R.flags[r0 - 1] : (uint16_t)0;
+                if ((all_and & IDP_F_MATE_NEXT) && !(all_or & ((uint32_t)IDP_F_MATE_NEXT << 16)) && !(before & IDP_F_MATE_NEXT)) {
+                    done = true;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t w = fw[k];
+                        // TemplateType of a pair: both mapped 0, one mapped 1, none 2 = the number of unmapped reads
+                        const uint32_t tt = ((w >> 2) & 1u) + ((w >> 18) & 1u), fr = (w >> 12) & 1u;
+                        const uint32_t ty = tw[k >> 1] >> (16 * (k & 1));  // type of R1 in the low byte, of R2 in the next
+                        bin[2 * k] = (int)(tt * 32u + fr * 16u + (ty & 0xFFu) * 4u + ((ty >> 8) & 0xFFu));
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) { f[u + 1] = (uint16_t)(fw[u >> 1] >> (16 * (u & 1))); t[u] = (uint8_t)(tw[u >> 2] >> (8 * (u & 3))); }
             } else {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) { const bool in = r0 + u < R.n; f[u + 1] = in ? R.flags[r0 + u] : (uint16_t)0; t[u] = in ? rtype[r0 + u] : (uint8_t)IDP_NONE; }
             }
+            if (!done) {
             f[0] = r0 > 0 ? R.flags[r0 - 1] : (uint16_t)0;
             const bool after = r0 + 8 < R.n;
             f[9] = after ? R.flags[r0 + 8] : (uint16_t)0;
@@ -1664,6 +1681,7 @@ __global__ void __launch_bounds__(256) metrics_kernel(DevReads R, const uint8_t 
                 const bool m1 = !(fl & IDP_F_UNMAPPED), m2 = !(f[u + 2] & IDP_F_UNMAPPED);
                 const int tt = !has_r2 ? (m1 ? 3 : 4) : ((m1 && m2) ? 0 : (m1 != m2 ? 1 : 2));
                 bin[u] = ((tt * 2 + ((fl & IDP_F_FR_PAIR) ? 1 : 0)) * 4 + t[u]) * 4 + (has_r2 ? (int)t[u + 1] : (int)IDP_NONE);
+            }
             }
         }
         if (!chosen) {  // warp-uniform: the loop bound is the same for the whole block

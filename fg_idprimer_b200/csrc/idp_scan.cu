@@ -137,7 +137,7 @@ static void launch_compact(const LaunchCfg &c, cudaStream_t st, const uint32_t *
 template <int RW>
 static void launch_member_check_t(const LaunchCfg &c, cudaStream_t st, const DevReads &R, const unsigned *parked, const unsigned *items, Counters *ctr,
                                   ResultOut five, uint8_t *rtype, uint32_t *fall_mask) {
-    member_check_kernel<RW><<<c.sm_count * 4, 128, 0, st>>>(c.dp, R, parked, items, ctr, five, rtype, fall_mask);
+    member_check_kernel<RW><<<c.sm_count * 16, 128, 0, st>>>(c.dp, R, parked, items, ctr, five, rtype, fall_mask);
 }
 
 // masks: 2 * ceil(R.n / 32) words of scratch (fall-through bits, then parked bits)

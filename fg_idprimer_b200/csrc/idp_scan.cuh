@@ -627,6 +627,35 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
     }
 }
 
+// The same question without the index: primer p is a candidate iff one of the read's k-mers (search window, PM:110) equals one of
+// the primer's, letter by letter (PM:113).  Every read k-mer is first tested against the primer's 1,024 hash bits
+// (DevPanel::member_bits: about 2 % of them set, independent loads from a 128-byte row that stays in L1); only a hit is compared
+// with the primer's k-mers themselves.  The index walk is a chain of ~3 dependent table loads per read k-mer.
+template <int RW>
+__device__ __noinline__ bool kmer_member_bits(const DevPanel &P, const uint32_t (&win)[RW], int len, int p) {
+    const DevKmerIndex &ix = P.kidx[0];
+    const int k = ix.k, n_bases = min(min(ix.window, len), 8 * RW), seq_len = __ldg(&P.pinfo[p]).w;
+    if (k <= 0 || n_bases < k || seq_len < k) return false;
+    const uint64_t kmask4 = k >= 16 ? ~0ull : ((1ull << (4 * k)) - 1ull);
+    const uint32_t *bits = P.member_bits + (size_t)p * 32;
+    uint64_t key = 0;
+    for (int i = 0; i < n_bases; ++i) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int w = 0; w < RW; ++w) if ((i >> 3) == w) word = win[w];
+        key = ((key << 4) | ((word >> (4 * (i & 7))) & 15u)) & kmask4;
+        if (i < k - 1) continue;
+        const uint32_t h = member_bits_hash(key);
+        if (!((__ldg(&bits[h >> 5]) >> (h & 31u)) & 1u)) continue;
+        uint64_t pk = 0;  // a hit: the primer's k-mers themselves
+        for (int b = 0; b < seq_len; ++b) {
+            pk = ((pk << 4) | ((__ldg(&P.pmask[(size_t)p * P.ww + (b >> 3)]) >> (4 * (b & 7))) & 15u)) & kmask4;
+            if (b >= k - 1 && pk == key) return true;
+        }
+    }
+    return false;
+}
+
 // The reads scan_kernel deferred (ScanLaunch::defer_mask): is the provisionally recorded primer among the read's k-mer
 // candidates (PM:108-116)?  One read per thread, every lane busy with the same walk.  No: the record goes back to "no match"
 // and the read joins the fall-through reads.
@@ -644,7 +673,10 @@ __global__ void __launch_bounds__(128) member_check_kernel(DevPanel P, DevReads 
         window_from_global<RW>(R, r, s, c.len, seq_order_is_rc(R.flags[r]), c.win);
         int type, primer;
         read_type_primer(five, r, type, primer);
-        if (!kmer_member_exact<RW>(P, c, primer)) {
+        bool member;
+        if (P.member_bits != nullptr) member = kmer_member_bits<RW>(P, c.win, c.len, primer);
+        else member = kmer_member_exact<RW>(P, c, primer);
+        if (!member) {
             write_result(five, r, none_result());
             rtype[r] = (uint8_t)IDP_NONE;
             atomicOr(&fall_mask[r >> 5], 1u << (r & 31));

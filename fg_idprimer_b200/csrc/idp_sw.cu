@@ -12,7 +12,7 @@ void launch_cand5(const LaunchCfg &c, cudaStream_t st, const DevReads &R, const 
     const int words = (c.dp.n_primers + 31) / 32;
     const size_t smem = (size_t)8 * words * 4;
     const DevKmerIndex &ix = c.dp.kidx[1];
-    const unsigned bm_words = ix.direct_bits != nullptr ? std::max(1u, (1u << (2 * ix.k)) / 32u) : 0u;  // + the 8 KB Bloom filter of the IUPAC k-mers
+    const unsigned bm_words = ix.direct_bits != nullptr ? ix.direct_bits_words : 0u;  // + the 8 KB Bloom filter of the IUPAC k-mers
     const size_t bm_bytes = bm_words ? (size_t)bm_words * 4 + 2048 * 4 : 0;
     cudaFuncSetAttribute(cand5_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bm_bytes, 1024));
     // one block of 1024 threads per SM when the map takes 128 KB, two otherwise

@@ -152,6 +152,7 @@ typedef struct {
     int64_t  kernel_launches;     /* kernels of this library launched by the call                              */
     int64_t  h2d_bytes, d2h_bytes;
     int64_t  n_scan_parked;       /* reads the exact-prefix table of the scan kernel did not decide (they took the filter pass) */
+    int64_t  n_scan_deferred;     /* of those, reads whose one accepted primer needed the exact k-mer membership test    */
 } idp_timings;
 
 typedef struct idp_panel idp_panel;  /* immutable after create; shareable across threads and devices           */
