@@ -137,7 +137,7 @@ static void launch_compact(const LaunchCfg &c, cudaStream_t st, const uint32_t *
 template <int RW>
 static void launch_member_check_t(const LaunchCfg &c, cudaStream_t st, const DevReads &R, const unsigned *parked, const unsigned *items, Counters *ctr,
                                   ResultOut five, uint8_t *rtype, uint32_t *fall_mask) {
-    member_check_kernel<RW><<<c.sm_count * 16, 128, 0, st>>>(c.dp, R, parked, items, ctr, five, rtype, fall_mask);
+    member_check_kernel<RW><<<c.sm_count * 2, 128, 0, st>>>(c.dp, R, parked, items, ctr, five, rtype, fall_mask);
 }
 
 // masks: 2 * ceil(R.n / 32) words of scratch (fall-through bits, then parked bits)
@@ -151,7 +151,7 @@ int launch_scan(const LaunchCfg &c, cudaStream_t st, const DevReads &R, ResultOu
         launch_compact(c, st, park_mask, n_tiles, parked, &ctr->n_parked);
         *launches += 2;
         // the parked bits are spent: their words now take the deferred bits, one per LIST item
-        const bool defer = c.dp.kidx[0].k > 0 && !getenv("IDP_SCAN_NO_DEFER");
+        const bool defer = c.dp.kidx[0].k > 0 && c.dp.member_bits != nullptr && !getenv("IDP_SCAN_NO_DEFER");
         if ((rc = launch_scan_general(c, st, R, five, rtype, fall_mask, ctr, parked, defer ? park_mask : nullptr))) return rc;
         if (defer) {  // `fall` holds the deferred items until the last compaction below overwrites it
             launch_compact(c, st, park_mask, n_tiles, fall, &ctr->n_defer, &ctr->n_parked);

@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks) scan_kernel(cons
 // (DevPanel::member_bits: about 2 % of them set, independent loads from a 128-byte row that stays in L1); only a hit is compared
 // with the primer's k-mers themselves.  The index walk is a chain of ~3 dependent table loads per read k-mer.
 template <int RW>
-__device__ __noinline__ bool kmer_member_bits(const DevPanel &P, const uint32_t (&win)[RW], int len, int p) {
+__device__ __forceinline__ bool kmer_member_bits(const DevPanel &P, const uint32_t (&win)[RW], int len, int p) {
     const DevKmerIndex &ix = P.kidx[0];
     const int k = ix.k, n_bases = min(min(ix.window, len), 8 * RW), seq_len = __ldg(&P.pinfo[p]).w;
     if (k <= 0 || n_bases < k || seq_len < k) return false;
@@ -673,10 +673,9 @@ __global__ void __launch_bounds__(128) member_check_kernel(DevPanel P, DevReads 
         window_from_global<RW>(R, r, s, c.len, seq_order_is_rc(R.flags[r]), c.win);
         int type, primer;
         read_type_primer(five, r, type, primer);
-        bool member;
-        if (P.member_bits != nullptr) member = kmer_member_bits<RW>(P, c.win, c.len, primer);
-        else member = kmer_member_exact<RW>(P, c, primer);
-        if (!member) {
+        // (inlined: an out-of-line call would take the address of the kernel's parameter block, which then costs every thread of
+        // the launch a local-memory copy of it; the launcher defers only when DevPanel::member_bits exists)
+        if (!kmer_member_bits<RW>(P, c.win, c.len, primer)) {
             write_result(five, r, none_result());
             rtype[r] = (uint8_t)IDP_NONE;
             atomicOr(&fall_mask[r >> 5], 1u << (r & 31));
