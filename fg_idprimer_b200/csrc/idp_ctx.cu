@@ -200,12 +200,12 @@ static int upload_panel(idp_ctx *c) {
     if (p.kidx[0].k > 0 && p.kidx[0].k <= 16) {  // hash bits of every primer's k-mers (member_check_kernel)
         const int k = p.kidx[0].k;
         const uint64_t kmask4 = k >= 16 ? ~0ull : ((1ull << (4 * k)) - 1ull);
-        std::vector<uint32_t> mb((size_t)p.n * 32, 0u);
+        std::vector<uint32_t> mb((size_t)p.n * kMemberWords, 0u);
         for (int i = 0; i < p.n; ++i) {
             uint64_t key = 0;
             for (int b = 0; b < p.seq_len[i]; ++b) {
                 key = ((key << 4) | ((p.pmask[(size_t)i * p.ww + b / 8] >> (4 * (b % 8))) & 15u)) & kmask4;
-                if (b >= k - 1) { const uint32_t h = member_bits_hash(key); mb[(size_t)i * 32 + (h >> 5)] |= 1u << (h & 31); }
+                if (b >= k - 1) { const uint32_t h = member_bits_hash(key); mb[(size_t)i * kMemberWords + (h >> 5)] |= 1u << (h & 31); }
             }
         }
         if ((rc = upload(mb, c->b_mbits))) return rc;

@@ -36,6 +36,7 @@ constexpr int kCandLocal = 8;
 // answer most lookups -- the fall-through reads are mostly off-target templates whose k-mers are not on the panel, and the
 // 4^k-entry table itself lives in L2, where one 4-byte probe costs a whole sector (the kernel was bound by exactly that).
 constexpr int kCand5Threads = 1024;
+__device__ __forceinline__ uint32_t smem_ld32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 __global__ void __launch_bounds__(kCand5Threads) cand5_thread_kernel(DevPanel P, DevReads R, const unsigned int *__restrict__ fall,
                                                            Counters *__restrict__ ctr, unsigned int *__restrict__ pair_work,
                                                            unsigned int *__restrict__ pair_primer, unsigned int pair_cap,
@@ -116,21 +117,29 @@ __global__ void __launch_bounds__(kCand5Threads) cand5_thread_kernel(DevPanel P,
                     badv |= gather_nibble_bits(nib_nonzero(d4 ^ 0x11111111u)) << (8 * w4);
                 }
                 const uint32_t km = (1u << ix.k) - 1u;
-                // pass 1, registers and shared memory only: which k-mer positions can hit at all
+                // pass 1, registers and shared memory only: which k-mer positions can hit at all.  The k-mers holding a code other than
+                // A/C/G/T are found for all positions at once (bk) and handled after the loop; the loop itself is branch-free: two
+                // shifts and two ANDs for the planes, a shift-or for the table index, one shared-memory load, one bit test
+                const int kk = ix.k, n_pos = max(n_bases - kk + 1, 0);
+                uint32_t bk = badv;
+                for (int t = 1; t < kk; ++t) bk |= badv >> t;
+                const uint32_t bm_addr = (uint32_t)__cvta_generic_to_shared(cand5_bm), wmask = bm_words - 1u;
                 uint32_t hits = 0u;
-                for (int p0 = 0; p0 + ix.k <= n_bases; ++p0) {
-                    const uint32_t l = (lo >> p0) & km, h = (hi >> p0) & km, bad = (badv >> p0) & km;
-                    bool hit;
-                    if (bad == 0u) {
-                        const uint32_t idx = (h << ix.k) | l;
-                        hit = ((cand5_bm[(idx >> 5) & (bm_words - 1u)] >> (idx & 31u)) & 1u) != 0u;  // bm_words: a power of two (folded map)
-                    } else if (ix.n_iupac_kmers == 0u) {
-                        hit = false;  // a k-mer holding another code can only equal a primer k-mer that spells the same code (PM:113)
-                    } else {
-                        const uint32_t sig = kmer_plane_signature(l, h, bad, ix.k);
-                        hit = ((bloom[sig >> 5] >> (sig & 31u)) & 1u) != 0u;
+                for (int p0 = 0; p0 < n_pos; ++p0) {
+                    const uint32_t idx = ((((hi >> p0) & km) << kk) | ((lo >> p0) & km));
+                    const uint32_t word = smem_ld32(bm_addr + (((idx >> 5) & wmask) << 2));  // bm_words is a power of two (folded map)
+                    hits |= ((word >> (idx & 31u)) & 1u) << p0;
+                }
+                const uint32_t pos_mask = n_pos >= 32 ? ~0u : ((1u << n_pos) - 1u);
+                hits &= ~bk & pos_mask;
+                if (ix.n_iupac_kmers != 0u) {  // a k-mer holding another code can only equal a primer k-mer that spells the same code (PM:113)
+                    uint32_t todo = bk & pos_mask;
+                    while (todo) {
+                        const int p0 = __ffs((int)todo) - 1;
+                        todo &= todo - 1u;
+                        const uint32_t sig = kmer_plane_signature((lo >> p0) & km, (hi >> p0) & km, (badv >> p0) & km, kk);
+                        hits |= ((bloom[sig >> 5] >> (sig & 31u)) & 1u) << p0;
                     }
-                    hits |= (uint32_t)hit << p0;
                 }
                 // pass 2: the hits in read order (PM:110-113); the table entry of the next hit is requested while this one is walked
                 auto entry_of = [&](int p0) -> uint32_t {  // all-A/C/G/T k-mers only; 0 for the others (they take the hashed table)
