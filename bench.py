@@ -457,7 +457,9 @@ def main():
 
         scan_ms = statistics.mean(t["ms_scan"] for t in tm_res)
         stages = {k: statistics.mean(t[k] for t in tm_res) for k in ("ms_total", "ms_scan", "ms_gapped", "ms_three_prime", "ms_sw_score")}
-        work = {k: int(tm_res[-1][k]) // steps for k in ("n_fallthrough", "n_alignments_5p", "n_alignments_3p", "sw_cells", "n_scan_parked", "n_scan_deferred")}  # per step
+        # per step: the alignment / cell totals accumulate on the device over the asynchronous steps, the list lengths are the last batch's
+        work = {k: int(tm_res[-1][k]) // steps for k in ("n_alignments_5p", "n_alignments_3p", "sw_cells")}
+        work.update({k: int(tm_res[-1][k]) for k in ("n_fallthrough", "n_scan_parked", "n_scan_deferred")})
         shipped = 2 * ((fixed_len + 1) // 2 + 2 + 16 * (2 if do3 else 1) + 1 + (12 if loc else 0))
         out = {
             "workload": workload_desc(name, n_pairs) + " (per GPU)",
