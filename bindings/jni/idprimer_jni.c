@@ -76,7 +76,15 @@ JNIEXPORT void JNICALL GPM(ctxDestroy)(JNIEnv *env, jclass c, jlong h) { idp_ctx
 JNIEXPORT void JNICALL GPM(ctxSetStream)(JNIEnv *env, jclass c, jlong h, jlong cudaStream) { check(env, idp_ctx_set_stream(PTR(idp_ctx, h), PTR(void, cudaStream))); }
 JNIEXPORT void JNICALL GPM(ctxSetAsync)(JNIEnv *env, jclass c, jlong h, jint enable) { check(env, idp_ctx_set_async(PTR(idp_ctx, h), enable)); }
 JNIEXPORT void JNICALL GPM(ctxSync)(JNIEnv *env, jclass c, jlong h, jobject metrics, jobject nAligned) { check(env, idp_ctx_sync(PTR(idp_ctx, h), (int64_t *)ADDR(metrics), (int64_t *)ADDR(nAligned))); }
-JNIEXPORT void JNICALL GPM(ctxTimings)(JNIEnv *env, jclass c, jlong h, jobject out /* idp_timings */) { check(env, idp_ctx_timings(PTR(const idp_ctx, h), (idp_timings *)ADDR(out))); }
+JNIEXPORT void JNICALL GPM(ctxTimings)(JNIEnv *env, jclass c, jlong h, jobject out /* idp_timings */) {
+    /* the struct grows at its end from one ABI revision to the next: refuse a buffer cut for an older one instead of writing past it */
+    if (out && (*env)->GetDirectBufferCapacity(env, out) < (jlong)sizeof(idp_timings)) {
+        jclass cls = (*env)->FindClass(env, "java/lang/IllegalArgumentException");
+        if (cls) (*env)->ThrowNew(env, cls, "ctxTimings: the buffer is smaller than idp_timings");
+        return;
+    }
+    check(env, idp_ctx_timings(PTR(const idp_ctx, h), (idp_timings *)ADDR(out)));
+}
 /* clsPerRead: a direct buffer for matchBatch / matchBatch16 (or null); use ctxSetClassifyDevice for the *_device calls */
 JNIEXPORT void JNICALL GPM(ctxSetClassify)(JNIEnv *env, jclass c, jlong h, jint minInsert, jint maxInsert, jobject clsPerRead, jobject counts6) {
     check(env, idp_ctx_set_classify(PTR(idp_ctx, h), minInsert, maxInsert, (uint8_t *)ADDR(clsPerRead), (int64_t *)ADDR(counts6)));

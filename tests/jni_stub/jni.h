@@ -16,6 +16,7 @@ struct JNINativeInterface_ {
     jclass (*FindClass)(JNIEnv *, const char *);
     jint (*ThrowNew)(JNIEnv *, jclass, const char *);
     void *(*GetDirectBufferAddress)(JNIEnv *, jobject);
+    jlong (*GetDirectBufferCapacity)(JNIEnv *, jobject);
     jobject (*NewDirectByteBuffer)(JNIEnv *, void *, jlong);
     jstring (*NewStringUTF)(JNIEnv *, const char *);
     const char *(*GetStringUTFChars)(JNIEnv *, jstring, jboolean *);

@@ -34,3 +34,9 @@ def test_windowed_batch_on_gpu(opts):
             assert np.array_equal(got5[f], want5[f]), f
         # process_batch accumulates like the tool's counter does: the second batch doubles both
         assert np.array_equal(tool.metric_counter, 2 * want_metrics) and tool.num_alignments == 2 * want_align
+        # the same two batches through the 16-byte records (idp_match_batch16, what the plugin ships by default): after
+        # idp_result16_unpack the rows are the very bytes of the 32-byte records
+        for batch in (whole, cut):
+            c5, _ = tool.process_batch(batch, compact=True)
+            assert c5.tobytes() == want5.tobytes()
+        assert np.array_equal(tool.metric_counter, 4 * want_metrics) and tool.num_alignments == 4 * want_align
