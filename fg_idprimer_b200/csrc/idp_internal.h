@@ -15,8 +15,8 @@ constexpr int kMaxPrimerBases = 256;   // longest primer sequence the kernels co
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-inline uint32_t member_bits_hash(uint64_t key4) { return (uint32_t)((key4 * 0x9E3779B97F4A7C15ull) >> 56); }  // 8 bits
-constexpr int kMemberWords = 8;  // 256 hash bits per primer: two 16-byte loads put them into registers
+inline uint32_t member_bits_hash(uint64_t key4) { return (uint32_t)((key4 * 0x9E3779B97F4A7C15ull) >> 54); }  // 10 bits
+constexpr int kMemberWords = 32;  // 1,024 hash bits per primer: a 128-byte row that stays in L1 while a read is tested
 constexpr int kMaxK = 16;              // k-mer key = 4 bits/base in a 64-bit word
 constexpr int kFxBases = 12;           // read bases hashed by the exact-prefix table
 constexpr int kMaxReadLen = 4095;      // target start/end are carried in 12 bits next to the score
@@ -105,7 +105,7 @@ struct DevPanel {
     const uint32_t *pmask;     // [n][ww] IUPAC masks, base i in nibble i, padded with 0xF
     const uint32_t *qbot;      // [n][nq/8] the same letters bottom-aligned in nq (32 or 64) rows, zero above; NULL if nq == 0
     const uint32_t *by_len;    // [n] primer indices sorted by sequence length (stable)
-    // [n][kMemberWords] per primer, 256 hash bits of its -k k-mers (member_bits_hash of the 4-bit-per-base key), NULL without -k:
+    // [n][kMemberWords] per primer, 1,024 hash bits of its -k k-mers (member_bits_hash of the 4-bit-per-base key), NULL without -k:
     // "is primer p among the primers that share a k-mer with this read" starts with one bit test per read k-mer
     const uint32_t *member_bits;
     // [n] {Primer.length (PR:206), early-exit cap of numMismatches and largest accepted mismatch count when the read

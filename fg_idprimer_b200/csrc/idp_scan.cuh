@@ -637,10 +637,7 @@ __device__ __forceinline__ bool kmer_member_bits(const DevPanel &P, const uint32
     const int k = ix.k, n_bases = min(min(ix.window, len), 8 * RW), seq_len = __ldg(&P.pinfo[p]).w;
     if (k <= 0 || n_bases < k || seq_len < k) return false;
     const uint64_t kmask4 = k >= 16 ? ~0ull : ((1ull << (4 * k)) - 1ull);
-    static_assert(kMemberWords == 8, "two uint4 loads");
-    const uint4 *bp = reinterpret_cast<const uint4 *>(P.member_bits + (size_t)p * kMemberWords);
-    const uint4 b0 = __ldg(&bp[0]), b1 = __ldg(&bp[1]);
-    const uint32_t bits[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const uint32_t *bits = P.member_bits + (size_t)p * kMemberWords;
     uint64_t key = 0;
     for (int i = 0; i < n_bases; ++i) {
         uint32_t word = 0;
@@ -649,10 +646,7 @@ __device__ __forceinline__ bool kmer_member_bits(const DevPanel &P, const uint32
         key = ((key << 4) | ((word >> (4 * (i & 7))) & 15u)) & kmask4;
         if (i < k - 1) continue;
         const uint32_t h = member_bits_hash(key);
-        uint32_t bw = 0u;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) bw = (h >> 5) == (uint32_t)w ? bits[w] : bw;
-        if (!((bw >> (h & 31u)) & 1u)) continue;
+        if (!((__ldg(&bits[h >> 5]) >> (h & 31u)) & 1u)) continue;
         uint64_t pk = 0;  // a hit: the primer's k-mers themselves
         for (int b = 0; b < seq_len; ++b) {
             pk = ((pk << 4) | ((__ldg(&P.pmask[(size_t)p * P.ww + (b >> 3)]) >> (4 * (b & 7))) & 15u)) & kmask4;
