@@ -380,10 +380,11 @@ class IdentifyPrimers:
         self.num_alignments += int(n_align[0])
         return metrics, int(n_align[0])
 
-    def set_async(self, enable: bool = True):
-        """Asynchronous device-resident mode (idp_ctx_set_async): process_batch_device only enqueues; sync() collects the counters."""
+    def set_async(self, enable=True, stage_timing: bool = True):
+        """Asynchronous device-resident mode (idp_ctx_set_async): process_batch_device only enqueues; sync() collects the counters.
+        stage_timing=False drops the per-stage events and the per-batch counter copy (mode 2)."""
         self._require_ctx()
-        L.check(L.lib().idp_ctx_set_async(self._ctx, 1 if enable else 0))
+        L.check(L.lib().idp_ctx_set_async(self._ctx, (1 if stage_timing else 2) if enable else 0))
 
     def sync(self):
         """idp_ctx_sync: waits for the enqueued batches, adds their counters to metric_counter / num_alignments, returns them."""

@@ -88,6 +88,8 @@ struct idp_ctx {
     bool compact_ok = false;  // every value of this panel's results fits idp_result16
     // asynchronous device-resident mode (idp_ctx_set_async): batches are enqueued back to back, counters accumulate on the device
     bool async_on = false;
+    bool async_lean = false;   // asynchronous mode without the per-stage events and the per-batch counter copy (idp_ctx_set_async(ctx, 2))
+    bool stage_events_recorded = false;
     int async_pending = 0;
     // classification epilogue (idp_ctx_set_classify)
     bool cls_on = false;
@@ -360,6 +362,10 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
     const size_t n = (size_t)R.n;
     int rc;
     const bool k_gapped = p.kidx[1].k > 0, do3 = p.params.three_prime >= 0;
+    // the stage events each cost the stream a small bubble, the counter copy another: the lean asynchronous mode drops both
+    // (idp_ctx_sync then reports ms_total of the last batch only and copies the counters itself)
+    const bool stage = !(keep_totals && c->async_lean);
+    c->stage_events_recorded = stage;
     if ((rc = s.fall.ensure(n * 4)) || (rc = s.parked.ensure(n * 4)) || (rc = s.masks.ensure(((n + 31) / 32) * 8 + 8))) return rc;
     if (k_gapped && (rc = s.spill.ensure(n * 4))) return rc;
     if (k_gapped || do3) {
@@ -380,48 +386,48 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
     if (n > 0) {
         if ((rc = launch_scan(cfg, st, R, five, rtype, fall, s.parked.as<unsigned>(), s.masks.as<uint32_t>(), ctr, &s.launches))) return rc;
     }
-    CUDA_TRY(cudaEventRecord(s.ev[EV_SCAN], st));
+    if (stage) CUDA_TRY(cudaEventRecord(s.ev[EV_SCAN], st));
     // ---- 5' gapped stage over the fall-through list ----
     if (n > 0) {
         if (k_gapped) {
             launch_cand5(cfg, st, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), (unsigned)s.pair_cap,
                          s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(), s.spill.as<unsigned>());
-            CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st));
+            if (stage) CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st));
             launch_sw_pairs(cfg, st, false, R, fall, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), (unsigned)s.pair_cap);
-            CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st));
+            if (stage) CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st));
             launch_finalize_pairs(cfg, st, R, fall, &ctr->n_fall, 0u, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(),
                                   s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), five, rtype, ctr, 0);
             s.launches += 4;
         } else {
-            CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st));
+            if (stage) CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st));
             launch_sw_all(cfg, st, false, R, fall, &ctr->n_fall, s.fin.as<Fin>(), ctr, 1);
-            CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st));
+            if (stage) CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st));
             launch_finalize_all(cfg, st, R, fall, &ctr->n_fall, s.fin.as<Fin>(), five, rtype, 0);
             s.launches += 2;
         }
-    } else { CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st)); CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st)); }
+    } else { if (stage) CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_A], st)); if (stage) CUDA_TRY(cudaEventRecord(s.ev[EV_SW5_B], st)); }
     if (c->cls_on && n > 0) {  // classification epilogue on the finished 5' records
         launch_classify(cfg, st, R.flags, five, R.n, c->cls_min, c->cls_max, cls_dev, ctr);
         ++s.launches;
     }
-    CUDA_TRY(cudaEventRecord(s.ev[EV_GAPPED], st));
+    if (stage) CUDA_TRY(cudaEventRecord(s.ev[EV_GAPPED], st));
     // ---- 3' stage (IP:483-516) ----
     if (do3 && n > 0 && three.p) {
         CUDA_TRY(cudaMemsetAsync(&ctr->n_pairs, 0, sizeof(unsigned), st));
         launch_cand3(cfg, st, R, five, ctr, s.all_list.as<unsigned>(), s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(),
                      (unsigned)s.pair_cap, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>());
-        CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_A], st));
+        if (stage) CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_A], st));
         launch_sw_pairs(cfg, st, true, R, nullptr, ctr, s.pair_work.as<unsigned>(), s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), (unsigned)s.pair_cap);
         launch_sw_all(cfg, st, true, R, s.all_list.as<unsigned>(), &ctr->n_all, s.fin.as<Fin>(), ctr, 0);
-        CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_B], st));
+        if (stage) CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_B], st));
         launch_finalize_pairs(cfg, st, R, nullptr, nullptr, (unsigned)R.n, s.seg_off.as<unsigned>(), s.seg_cnt.as<int>(),
                               s.pair_primer.as<unsigned>(), s.pair_score.as<int>(), s.pair_se.as<unsigned>(), three, nullptr, ctr, 1);
         launch_finalize_all(cfg, st, R, s.all_list.as<unsigned>(), &ctr->n_all, s.fin.as<Fin>(), three, nullptr, 1);
         s.launches += 5;
-    } else { CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_A], st)); CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_B], st)); }
-    CUDA_TRY(cudaEventRecord(s.ev[EV_THREE], st));
+    } else { if (stage) CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_A], st)); if (stage) CUDA_TRY(cudaEventRecord(s.ev[EV_SW3_B], st)); }
+    if (stage) CUDA_TRY(cudaEventRecord(s.ev[EV_THREE], st));
     if (n > 0) { launch_metrics(cfg, st, R, rtype, ctr); ++s.launches; }
-    CUDA_TRY(cudaMemcpyAsync(s.h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    if (stage) CUDA_TRY(cudaMemcpyAsync(s.h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(s.ev[EV_END], st));
     CUDA_TRY(cudaGetLastError());
     return IDP_OK;
@@ -432,10 +438,12 @@ static void add_timings(idp_ctx *c, Slot &s, bool first) {
     float ms = 0;
     auto el = [&](int a, int b) { ms = 0; cudaEventElapsedTime(&ms, s.ev[a], s.ev[b]); return ms; };
     if (first) t.ms_total = 0;
-    t.ms_scan += el(EV_START, EV_SCAN);
-    t.ms_gapped += el(EV_SCAN, EV_GAPPED);
-    t.ms_three_prime += el(EV_GAPPED, EV_THREE);
-    t.ms_sw_score += el(EV_SW5_A, EV_SW5_B) + el(EV_SW3_A, EV_SW3_B);
+    if (c->stage_events_recorded) {
+        t.ms_scan += el(EV_START, EV_SCAN);
+        t.ms_gapped += el(EV_SCAN, EV_GAPPED);
+        t.ms_three_prime += el(EV_GAPPED, EV_THREE);
+        t.ms_sw_score += el(EV_SW5_A, EV_SW5_B) + el(EV_SW3_A, EV_SW3_B);
+    }
     t.n_fallthrough += s.h_ctr->n_fall;
     t.n_alignments_5p += (int64_t)s.h_ctr->n_align5;
     t.n_alignments_3p += (int64_t)s.h_ctr->n_align3;
@@ -719,6 +727,7 @@ int idp_ctx_set_async(idp_ctx *c, int enable) {
     if (!c) { set_error("idp_ctx_set_async: NULL context"); return IDP_ERR_ARG; }
     if (c->async_pending) { set_error("idp_ctx_set_async: batches are pending; call idp_ctx_sync first"); return IDP_ERR_ARG; }
     c->async_on = enable != 0;
+    c->async_lean = enable == 2;
     return IDP_OK;
 }
 
@@ -729,6 +738,7 @@ int idp_ctx_sync(idp_ctx *c, int64_t *metrics160, int64_t *n_gapped_alignments) 
     Slot &s = c->slots[0];
     cudaStream_t st = c->user_stream ? c->user_stream : s.stream;
     c->async_pending = 0;
+    if (c->async_lean) CUDA_TRY(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     if (s.h_ctr->overflow) {

@@ -206,7 +206,9 @@ int idp_match_batch_device(idp_ctx *ctx, const idp_reads *reads, int32_t n_reads
  * everything enqueued since the last sync and ADDS the accumulated counters to its arguments (either may be NULL).  Input and
  * output arrays of a batch must stay valid until then.  If a batch lists more -K candidates than the pair buffer holds (the
  * synchronous calls redo such a batch themselves), idp_ctx_sync returns IDP_ERR_NOMEM and enlarges the buffer: rerun the batches
- * enqueued since the last sync.  idp_ctx_timings then reports the stage times of the last batch and the work counters of all. */
+ * enqueued since the last sync.  idp_ctx_timings then reports the stage times of the last batch and the work counters of all.
+ * enable == 2: the same without the per-stage CUDA events and the per-batch copy of the counters (each is a small bubble on the
+ * stream between two kernels): idp_ctx_timings then reports ms_total of the last batch and zero stage times. */
 int idp_ctx_set_async(idp_ctx *ctx, int enable);
 int idp_ctx_sync(idp_ctx *ctx, int64_t *metrics160, int64_t *n_gapped_alignments);
 

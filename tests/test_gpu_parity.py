@@ -721,8 +721,10 @@ def test_classification_epilogue_inside_process_batch(name, compact):
         assert want_counts["Canonical"] > 1000
 
 
-def test_asynchronous_device_mode_accumulates_counters():
-    """idp_ctx_set_async / idp_ctx_sync: batches enqueued back to back give the same records, and the counters of all of them at the sync."""
+@pytest.mark.parametrize("stage_timing", [True, False])
+def test_asynchronous_device_mode_accumulates_counters(stage_timing):
+    """idp_ctx_set_async / idp_ctx_sync: batches enqueued back to back give the same records, and the counters of all of them at the
+    sync -- with the per-stage events (mode 1) and without them and the per-batch counter copy (mode 2)."""
     import torch
     panel, reads, opts = synth.workload("c5", 2000)
     arr = reads.oracle_arrays()
@@ -734,7 +736,7 @@ def test_asynchronous_device_mode_accumulates_counters():
     outs = [(torch.zeros((reads.n, 16), dtype=torch.uint8, device=dev), torch.zeros((reads.n, 16), dtype=torch.uint8, device=dev)) for _ in range(3)]
     with idp.IdentifyPrimers(panel.primers, ref_names=panel.ref_names, **opts) as tool:
         tool.set_stream(torch.cuda.current_stream().cuda_stream)
-        tool.set_async(True)
+        tool.set_async(True, stage_timing=stage_timing)
         for f5, f3 in outs:
             m, na = tool.process_batch_device(reads.n, s4.data_ptr(), fl.data_ptr(), f5.data_ptr(), f3.data_ptr(), fixed_len=150, ref_idx_ptr=loc[0].data_ptr(),
                                               ustart_ptr=loc[1].data_ptr(), uend_ptr=loc[2].data_ptr(), compact=True)
@@ -742,6 +744,8 @@ def test_asynchronous_device_mode_accumulates_counters():
         metrics, n_align = tool.sync()
         assert np.array_equal(metrics, 3 * want_metrics) and n_align == 3 * want_align
         assert np.array_equal(tool.metric_counter, 3 * want_metrics)
+        t = tool.timings()
+        assert t["ms_total"] > 0 and (t["ms_scan"] > 0) == stage_timing and t["n_alignments_5p"] == 3 * want_align
         for f5, f3 in outs:
             assert_same(L.unpack16(f5.cpu().numpy().view(L.RESULT16_DTYPE).reshape(-1)), want5, "async 5'")
             assert_same(L.unpack16(f3.cpu().numpy().view(L.RESULT16_DTYPE).reshape(-1)), want3, "async 3'")
