@@ -380,8 +380,7 @@ static int enqueue_chain(idp_ctx *c, Slot &s, cudaStream_t st, const DevReads &R
     unsigned *fall = s.fall.as<unsigned>();
     uint8_t *rtype = s.rtype.as<uint8_t>();
     s.launches = 0;
-    CUDA_TRY(cudaMemsetAsync(ctr, 0, keep_totals ? offsetof(Counters, overflow) : sizeof(Counters), st));  // n_fall, n_parked, n_pairs, n_all (overflow is sticky)
-    if (keep_totals) CUDA_TRY(cudaMemsetAsync(&ctr->n_spill, 0, sizeof(unsigned), st));
+    CUDA_TRY(cudaMemsetAsync(ctr, 0, keep_totals ? offsetof(Counters, overflow) : sizeof(Counters), st));  // the per-batch list lengths (overflow and what follows are totals)
     CUDA_TRY(cudaEventRecord(s.ev[EV_START], st));
     if (n > 0) {
         if ((rc = launch_scan(cfg, st, R, five, rtype, fall, s.parked.as<unsigned>(), s.masks.as<uint32_t>(), ctr, &s.launches))) return rc;

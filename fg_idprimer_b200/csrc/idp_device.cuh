@@ -27,8 +27,8 @@ struct Counters {
     unsigned int n_pairs;         // (read, primer) pairs emitted for sw_pairs_kernel
     unsigned int n_all;           // 3' reads that take every primer
     unsigned int n_defer;         // parked reads whose one accepted primer still needs the exact k-mer walk (member_check_kernel)
-    unsigned int overflow;        // pair buffer too small: number of work items not emitted
     unsigned int n_spill;         // fall-through reads with more -K candidates than the per-thread list holds
+    unsigned int overflow;        // pair buffer too small: number of work items not emitted.  FIRST of the sticky fields: everything above is per batch
     unsigned long long n_align5;  // alignments performed by the 5' aligner (IP:424)
     unsigned long long n_align3;
     unsigned long long sw_cells;
