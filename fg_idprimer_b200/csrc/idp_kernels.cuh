@@ -4,18 +4,20 @@
 //   reads   : BAM-native 4-bit bases, SoA (DevReads); never unpacked to ASCII.
 //   panel   : DevPanel (idp_internal.h) -- primer IUPAC masks 8 bases / 32-bit word, k-mer hash tables whose posting
 //             lists are in the reference's Set iteration order, per-strand sorted location arrays.
-//   results : idp_result (32 B) per read.
+//   results : idp_result (32 B) or idp_result16 (16 B) per read (ResultOut, idp_device.cuh).
 //
 // Kernels (reference function each one covers)
-//   scan_kernel (idp_scan.cuh)  basesInSequencingOrder (PM:39-45) + LocationBasedPrimerMatcher.find (PM:194-213) +
+//   scan_fx_kernel (idp_scanfx.cuh), scan_kernel / member_check_kernel (idp_scan.cuh)
+//                      basesInSequencingOrder (PM:39-45) + LocationBasedPrimerMatcher.find (PM:194-213) +
 //                      getPrimersForAlignmentTasks (PM:98-116) + mismatchAlign / numMismatches (PM:128-147) +
 //                      getBestUngappedAlignment (PM:237-248); reads with no match go to the fall-through list
 //   cand5_thread_kernel / cand5_kernel   GappedAlignmentBasedPrimerMatcher.toAlignmentTasks candidates under -K
 //                      (PM:287-296, 108-116): a thread per read with a register-resident distinct list, a warp per read
 //                      with a shared-memory bitmap for the reads that overflow it
 //   cand3_kernel       matchThreePrime's primersToCheck (IP:490-499)
-//   sw_pairs_kernel    fgbio Aligner.align, one thread per (read, primer) pair (IP:446-448, 509-513); the packed variant
-//                      also yields targetStart / targetEnd
+//   sw_pairs_kernel    fgbio Aligner.align of the (read, primer) pairs (IP:446-448, 509-513), score + targetStart / targetEnd in
+//                      one pass: two pairs per thread in 16-bit half-words (sw_trace2_glocal16 / sw_trace2_local16) where the
+//                      scores allow it, else one pair per thread on 32-bit values (sw_trace_reg) or the generic forms
 //   sw_all_kernel      the same, score only, when every primer is a candidate: one block per read, best two kept on chip
 //   finalize_*_kernel  getBestGappedAlignment (PM:305-328) + (all-primers path) re-alignment of the winner with start
 //                      tracking + finalizedGappedAlignment (IP:459-471)
@@ -1085,80 +1087,7 @@ __device__ __forceinline__ TracedReg sw_trace_reg(const DevPanel &P, const uint3
     TracedReg out{0, 1, 0};
     if (m == 0) { out.score = LOCAL ? 0 : P.gap_open + n * P.gap_extend; return out; }
     if constexpr (!LOCAL) return sw_trace_reg_glocal_shifted<NQ>(P, qbot, n, lo, hi, T, m);
-    if constexpr (LOCAL) return sw_trace_reg_local<NQ>(P, qbot, n, lo, hi, T, m);
-    constexpr int SH = 14, LOW = 0x3FFF, RANK = 0x3000, RD = 0x3000, RL = 0x2000, RU = 0x1000;
-    const int oe = P.tr_open_ext, e = P.tr_ext;  // constant-bank operands
-    const unsigned am = __activemask();
-    const int self = (int)(threadIdx.x & 31u);
-    const int ma = __shfl_sync(am, P.tr_match, self), mi = __shfl_sync(am, P.tr_mismatch, self), keep = __shfl_sync(am, ~RANK, self);  // registers
-    constexpr int NEG = -(1 << 30);  // score -2^16
-    const int off = NQ - n;
-    uint32_t q[NQ / 8];
-#pragma unroll
-    for (int w = 0; w < NQ / 8; ++w) q[w] = __ldg(&qbot[w]);
-    int LN[NQ], M[NQ];  // LN[r] = Left(r, next column), stamped
-#pragma unroll
-    for (int r = 0; r < NQ; ++r) {
-        if (LOCAL) { LN[r] = (__viaddmax_s32(RD, oe, RL + e) & ~RANK) | RL; M[r] = RD; }  // column 0: all zero, start 0
-        else { LN[r] = NEG | RL; M[r] = ((P.gap_open + (r - off + 1) * P.gap_extend) * (1 << SH)) | RU; }  // Up(i,0), start 0
-    }
-    int best = NEG, bestkey = INT_MIN, bj = 0;
-    const int keeplow = __shfl_sync(am, ~LOW, self);
-    TargetStream ts(T);
-    for (int j = 1; j <= m; ++j) {
-        uint32_t t = ts.nib(j - 1);
-        asm volatile("" : "+r"(t));
-        const uint32_t trep = t * 0x11111111u;
-        uint32_t ne[NQ / 8];
-#pragma unroll
-        for (int w = 0; w < NQ / 8; ++w) ne[w] = nib_nonzero(q[w] ^ trep);
-        int mdiag = j - 1, d_up = RD | j, u_up = RU | j;  // row 0: score 0, path starts at this column
-#define IDP_CELL(r)                                                                                              \
-            int dn = ((mdiag + ((ne[(r) >> 3] & (1u << (4 * ((r) & 7)))) ? mi : ma)) & ~RANK) | RD;               \
-            if (LOCAL) dn = dn < 0 ? (RD | j) : dn; /* clamp at zero: the path (re)starts after this cell */      \
-            const int un = (__viaddmax_s32(d_up, oe, u_up + e) & keep) | RU; /* equal scores: opened from Diagonal */ \
-            const int ln = LN[(r)];                                                                               \
-            const int mold = M[(r)];                                                                              \
-            M[(r)] = __vimax3_s32(dn, ln, un); /* equal scores: Diagonal, then Left, then Up */                   \
-            LN[(r)] = (__viaddmax_s32(dn, oe, ln + e) & keep) | RL;
-        // Local best cell: lowest row, then lowest column; Left/Up values never win (each is bounded by a Diagonal value of a
-        // cell scanned earlier, gap scores being <= 0, and ties go to the earlier cell)
-        // as ONE integer comparison: key = score bits | (NQ-1 - row); a larger key is a higher score or the same score in a lower
-        // row, an equal key is the same row in a later column and does not replace
-#define IDP_BEST(r, cond)                                                                      \
-            if (LOCAL) {                                                                       \
-                const int key = (cond) ? ((dn & keeplow) | (NQ - 1 - (r))) : INT_MIN;          \
-                const bool better = key > bestkey;                                             \
-                bestkey = max(bestkey, key); best = better ? dn : best; bj = better ? j : bj;  \
-            }
-#define IDP_ROW(r)                                                                     \
-    case (r): {                                                                        \
-        if ((r) >= hi) break;                                                          \
-        const bool act = (r) >= off;                                                   \
-        IDP_CELL(r)                                                                    \
-        mdiag = act ? mold : mdiag; d_up = act ? dn : d_up; u_up = act ? un : u_up;    \
-        IDP_BEST(r, act)                                                               \
-    }
-        IDP_SWITCH_ROWS(NQ, lo)
-#undef IDP_ROW
-#define IDP_ROW(r)                                                                     \
-    case (r): {                                                                        \
-        IDP_CELL(r)                                                                    \
-        mdiag = mold; d_up = dn; u_up = un;                                            \
-        IDP_BEST(r, true)                                                              \
-    }
-        IDP_SWITCH_ROWS(NQ, hi)
-#undef IDP_ROW
-#undef IDP_CELL
-#undef IDP_BEST
-        if (!LOCAL) {
-            // last row, columns ascending, Diagonal / Left / Up, strict '>': Left(n,j) never exceeds an earlier Diagonal(n,j')
-            if (d_up > (best | LOW)) { best = d_up; bj = j; }
-            if (u_up > (best | LOW)) { best = u_up; bj = j; }
-        }
-    }
-    out.score = best >> SH; out.t_start = (best & 0xFFF) + 1; out.t_end = bj;
-    return out;
+    else return sw_trace_reg_local<NQ>(P, qbot, n, lo, hi, T, m);
 }
 
 // the target of one (read, primer) task: 5' = read prefix of |primer|+slop bases in sequencing order (PM:292-293);

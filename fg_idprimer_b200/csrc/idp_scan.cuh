@@ -3,9 +3,12 @@
 //   basesInSequencingOrder (PM:39-45) . LocationBasedPrimerMatcher.find (PM:194-213) . getPrimersForAlignmentTasks
 //   (PM:98-116) . mismatchAlign / numMismatches (PM:128-147) . getBestUngappedAlignment (PM:237-248)
 //
-// Persistent CTAs; every warp walks its own tiles of 32 reads.  A tile's packed bases (2400 B for 150 bp reads) arrive in
-// shared memory by one TMA bulk copy (cp.async.bulk + mbarrier), double-buffered per warp, so no CTA-wide barrier exists
-// after the prologue.  The panel side sits in shared memory as far as it fits.
+// This is the GENERAL scan kernel: it takes the whole batch when the exact-prefix pass (idp_scanfx.cuh) does not apply, else the
+// list of reads that pass parked (list mode).  Persistent CTAs; every warp walks its own tiles of 32 reads.  On a whole batch a
+// tile's packed bases (2400 B for 150 bp reads) arrive in shared memory by one TMA bulk copy (cp.async.bulk + mbarrier),
+// double-buffered per warp, so no CTA-wide barrier exists after the prologue; in list mode every lane fetches its own read.  The
+// panel side sits in shared memory as far as it fits.  member_check_kernel at the end of the file finishes the reads whose one
+// accepted primer still needs the exact k-mer membership test (ScanLaunch::defer_mask).
 //
 // Two ways to find the accepted primers of a read, both exact:
 //  * bit-sliced (DevPanel::bs_ok: every primer tolerates at most one mismatch): the read's first 12 bases index precomputed
