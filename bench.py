@@ -8,7 +8,9 @@ pairs 2x150 bp per GPU against a 96-pair IUPAC-degenerate panel, -k 6 -K 10, ful
 What the plugin ships by default for a run without --three-prime is the WINDOWED batch (idp_bam_to_batch_window: the
 leading bases the 5' chain can reach, 18 B instead of 75 B per read) and 16-byte result records (idp_match_batch16):
 
-  value              device-resident windowed batch -> idp_match_batch16_device, CUDA events on the launching stream
+  value              device-resident windowed batch -> idp_match_batch16_device, CUDA events on the launching stream; the steps
+                     are enqueued back to back in the context's asynchronous mode 2 (no per-stage events, counters collected once);
+                     stages_ms / roofline come from a second loop over the same steps with the per-stage events recorded
   e2e                pinned HOST windowed batch -> idp_match_batch16, H2D + D2H inside the timed region (wall clock)
   resident_whole_reads / e2e_whole_reads   the same through the 75 B rows and 32-byte records (idp_match_batch*)
   workloads          c3 (gapped-heavy), c4 (5,000-pair panel, 50M pairs strong-split over the GPUs), c5 (mapped/unmapped,
