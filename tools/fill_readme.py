@@ -63,8 +63,11 @@ for name, n in (("r02_bench_2gpu.json", 2), ("r02_bench_4gpu.json", 4), ("r02_be
     if m and not any(r[0].startswith(f"{n} GPUs") for r in rows):
         h = m.get("host_link_ceiling", {})
         rows.append((f"{n} GPUs (weak scaling, 10 M pairs per GPU; `profiles/{name}`)",
-                     f"{m['value'] / G:.1f} G read pairs/s resident ({m['ms_per_step']:.3f} ms per step on the slowest rank = {m['value'] / n / d['value']:.2f} of the single-GPU line above, "
-                     f"which comes from another box: single-GPU runs of this build ranged 0.66-0.70 ms; the counters are reduced once after the run), "
+                     f"{m['value'] / G:.1f} G read pairs/s resident ({m['ms_per_step']:.3f} ms per step on the slowest rank" +
+                     (f", measured with the per-stage events still in the loop: the single-GPU step takes {d['ms_per_step_with_stage_events']:.3f} ms that way, "
+                      f"so {d['ms_per_step_with_stage_events'] / m['ms_per_step']:.2f} of linear" if "ms_per_step_with_stage_events" not in m and "ms_per_step_with_stage_events" in d
+                      else f" = {m['value'] / n / d['value']:.2f} of the single-GPU line above") +
+                     "; another box than the single-GPU line, whose runs of this build ranged 0.66-0.70 ms; the counters are reduced once after the run), "
                      f"{m['e2e']['value'] / G:.2f} G end to end (host link with all ranks copying at once: {h.get('duplex_gbs_per_gpu_each_way', 0):.0f} GB/s per GPU each way)"))
 table = "| | value |\n|---|---|\n" + "\n".join(f"| {a} | {b} |" for a, b in rows) + "\n"
 p = os.path.join(ROOT, "README.md")
